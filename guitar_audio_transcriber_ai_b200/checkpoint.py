@@ -94,13 +94,14 @@ def pack_mlp(state: dict) -> dict:
     """Flattens an MLP state_dict (keys ``net.<i>.weight|bias``) into the arrays gat_load_mlp takes.
 
     Layer order: Linear, LayerNorm, (LeakyReLU, Dropout)... ; 2-d weights are Linear, 1-d are LayerNorm.
+    Linear weights are stored transposed ([in][out]) so a warp reads consecutive outputs.
     """
     idx = sorted({int(k.split(".")[1]) for k in state if k.startswith("net.")})
     linear = [i for i in idx if state[f"net.{i}.weight"].ndim == 2]
     dims = [int(state[f"net.{linear[0]}.weight"].shape[1])] + [int(state[f"net.{i}.weight"].shape[0]) for i in linear]
     flat = []
     for j, i in enumerate(linear):
-        flat += [_f32(state[f"net.{i}.weight"]).ravel(), _f32(state[f"net.{i}.bias"]).ravel()]
+        flat += [np.ascontiguousarray(_f32(state[f"net.{i}.weight"]).T).ravel(), _f32(state[f"net.{i}.bias"]).ravel()]
         if j + 1 < len(linear):
             flat += [_f32(state[f"net.{i + 1}.weight"]).ravel(), _f32(state[f"net.{i + 1}.bias"]).ravel()]
     return {"dims": np.asarray(dims, dtype=np.int32), "params": np.concatenate(flat).astype(np.float32)}

@@ -1,0 +1,265 @@
+// Feature kernels: per-clip RMS scale, fused frame+Hann+rFFT+|.|^2+mel+dB (three chains), MFCC finish.
+//
+//   reference call sites (paths under /root/reference/version_1/source):
+//     audio/features.py:124-126   _normalize_audio_volume          -> clip_scale_kernel
+//     audio/features.py:296-316   torchaudio MelSpectrogram + dB    -> stft_mel_kernel<float, kImage>
+//     audio/features.py:187-193   librosa.feature.mfcc + time-mean  -> stft_mel_kernel<float, kSpec> + mfcc_finish_kernel
+//     audio/slicing.py:107        librosa.onset.onset_strength      -> stft_mel_kernel<double, kSpec> (+ onset.cuh)
+//
+// One persistent kernel serves all three: a CTA takes (clip, chunk of frames) work items, stages the
+// padded, normalised samples of the chunk in shared memory once (each sample is reused by n_fft/hop
+// frames), and each warp turns one frame at a time into mel bins without leaving the SM: the spectrum
+// and the mel power never touch HBM.  The mel filterbank is applied in its banded-sparse form (each FFT
+// bin feeds at most two triangular filters), 2*(n_fft/2+1) MACs per frame instead of the dense
+// n_mels*(n_fft/2+1).
+#pragma once
+#include "fft.cuh"
+
+namespace gat {
+
+struct SparseFb {
+    int n_mels;
+    int nnz;
+    const int* start;    // [n_mels] first FFT bin with a non-zero weight
+    const int* len;      // [n_mels] number of consecutive non-zero weights
+    const int* off;      // [n_mels] offset of the first weight in w
+    const float* w;      // [nnz]
+};
+
+enum { kPadZero = 0, kPadReflect = 1 };
+enum { kOutImage = 0, kOutSpec = 1 };
+
+template <typename T>
+struct StftMelParams {
+    const float* audio;        // [N][n] float32 clips (or one long signal with N = 1)
+    long long n;               // samples per clip
+    int N;                     // clips
+    const float* clip_scale;   // [N] divisor c = rms + 1e-9, or nullptr (no volume normalisation)
+    const unsigned char* frame_gate;  // onset chain: per 512-sample block keep flag, or nullptr
+    float sample_gate;         // onset chain: samples with |y| < sample_gate are zeroed; 0 disables both gates
+    int gate_hop;              // samples per frame_gate entry (512)
+    int hop;
+    int n_frames;              // frames per clip = 1 + n / hop
+    int pad_mode;
+    const T* window;           // [2048]
+    const Cpx<T>* tw;          // [1024]
+    const Cpx<T>* w2;          // [1024]
+    SparseFb fb;
+    int frames_per_cta;
+    int chunks_per_clip;
+    T amin;                    // 1e-10
+    // kOutImage: out[(clip*n_mels + m)*T + t] = 10 log10(max(amin, mel))
+    // kOutSpec : out[(clip*T + t)*n_mels + m] = same, plus per-clip running max in spec_max (ordered ints)
+    T* out;
+    long long* spec_max;       // [N] ordered-integer encoded maxima (kOutSpec only)
+};
+
+__device__ __forceinline__ long long ordered_bits(double v) {
+    long long i = __double_as_longlong(v);
+    return i >= 0 ? i : i ^ 0x7fffffffffffffffLL;
+}
+__device__ __forceinline__ double from_ordered_bits(long long i) {
+    return __longlong_as_double(i >= 0 ? i : i ^ 0x7fffffffffffffffLL);
+}
+
+__device__ __forceinline__ float db10(float x) { return 10.0f * log10f(x); }
+__device__ __forceinline__ double db10(double x) { return 10.0 * log10(x); }
+
+constexpr int kMaxMelsPerLane = 4;   // n_mels <= 128
+
+// Shared-memory footprint of stft_mel_kernel (bytes), mirrored by the host launcher.
+template <typename T>
+__host__ __device__ inline size_t stft_mel_smem_bytes(int nwarps, int frames_per_cta, int hop, int n_mels, int nnz, bool image) {
+    size_t b = 0;
+    b += sizeof(FftTables<T>);
+    b += 2048 * sizeof(T);                                               // window
+    b += ((size_t)(frames_per_cta - 1) * hop + 2048) * sizeof(T);        // staged samples
+    b += (size_t)nwarps * kXbufElems * sizeof(Cpx<T>);                   // per-warp transpose buffers
+    b += (size_t)3 * n_mels * sizeof(int) + (size_t)nnz * sizeof(float); // sparse filterbank
+    if (image) b += (size_t)n_mels * (frames_per_cta + 1) * sizeof(T);   // output tile
+    return b + 64;
+}
+
+template <typename T, int kOut, int kThreads>
+__global__ void __launch_bounds__(kThreads, 1) stft_mel_kernel(StftMelParams<T> p) {
+    GAT_DYN_SMEM(smem_raw);
+    const int nwarps = blockDim.x >> 5;
+    const int lane = lane_id(), warp = warp_id();
+    const int FC = p.frames_per_cta;
+    const int span_len = (FC - 1) * p.hop + 2048;
+    const int n_mels = p.fb.n_mels;
+
+    unsigned char* sp = smem_raw;
+    FftTables<T>* tab = reinterpret_cast<FftTables<T>*>(sp);  sp += sizeof(FftTables<T>);
+    T* win = reinterpret_cast<T*>(sp);                        sp += 2048 * sizeof(T);
+    T* span = reinterpret_cast<T*>(sp);                       sp += (size_t)span_len * sizeof(T);
+    Cpx<T>* xbuf_all = reinterpret_cast<Cpx<T>*>(sp);         sp += (size_t)nwarps * kXbufElems * sizeof(Cpx<T>);
+    int* fb_start = reinterpret_cast<int*>(sp);               sp += n_mels * sizeof(int);
+    int* fb_len = reinterpret_cast<int*>(sp);                 sp += n_mels * sizeof(int);
+    int* fb_off = reinterpret_cast<int*>(sp);                 sp += n_mels * sizeof(int);
+    float* fb_w = reinterpret_cast<float*>(sp);               sp += (size_t)p.fb.nnz * sizeof(float);
+    T* tile = reinterpret_cast<T*>(sp);                       // kOutImage only
+
+    fill_fft_tables<T>(tab, p.tw, p.w2);
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) win[i] = p.window[i];
+    for (int i = threadIdx.x; i < n_mels; i += blockDim.x) {
+        fb_start[i] = p.fb.start[i]; fb_len[i] = p.fb.len[i]; fb_off[i] = p.fb.off[i];
+    }
+    for (int i = threadIdx.x; i < p.fb.nnz; i += blockDim.x) fb_w[i] = p.fb.w[i];
+    __syncthreads();
+
+    Cpx<T>* xbuf = xbuf_all + (size_t)warp * kXbufElems;
+    T* pbuf = reinterpret_cast<T*>(xbuf);   // 1025 power values alias the transpose buffer
+
+    const long long n_work = (long long)p.N * p.chunks_per_clip;
+    for (long long work = blockIdx.x; work < n_work; work += gridDim.x) {
+        const int clip = (int)(work / p.chunks_per_clip);
+        const int chunk = (int)(work % p.chunks_per_clip);
+        const int t0 = chunk * FC;
+        const int nf = min(FC, p.n_frames - t0);
+        const float* src = p.audio + (long long)clip * p.n;
+        const float c = p.clip_scale ? p.clip_scale[clip] : 1.0f;
+        const int need = (nf - 1) * p.hop + 2048;
+
+        // ---- stage the chunk: centre padding, volume normalisation, (onset chain) the two gates
+        for (int i = threadIdx.x; i < need; i += blockDim.x) {
+            long long s = (long long)t0 * p.hop + i - 1024;    // index into the un-padded clip
+            float v;
+            if (p.pad_mode == kPadReflect) {
+                if (s < 0 || s >= p.n) s = reflect_index(s, p.n);
+                v = src[s];
+            } else {
+                v = (s >= 0 && s < p.n) ? src[s] : 0.0f;
+            }
+            if (p.clip_scale) v = __fdiv_rn(v, c);
+            if (p.sample_gate > 0.0f && s >= 0 && s < p.n) {
+                if (!(fabsf(v) >= p.sample_gate)) v = 0.0f;
+                if (p.frame_gate && !p.frame_gate[s / p.gate_hop]) v = 0.0f;
+            }
+            span[i] = (T)v;
+        }
+        __syncthreads();
+
+        T wmax = (T)-1e300;
+        for (int f = warp; f < nf; f += nwarps) {
+            const T* x = span + (size_t)f * p.hop;
+            Cpx<T> v[32];
+#pragma unroll
+            for (int n2 = 0; n2 < 32; ++n2) {
+                const int j = lane + 32 * n2;
+                v[n2] = Cpx<T>{x[2 * j] * win[2 * j], x[2 * j + 1] * win[2 * j + 1]};
+            }
+            T pw[32], pw_nyq;
+            warp_rfft2048_power<T>(v, pw, pw_nyq, xbuf, tab);
+#pragma unroll
+            for (int k1 = 0; k1 < 32; ++k1) pbuf[32 * k1 + lane] = pw[k1];
+            if (lane == 0) pbuf[1024] = pw_nyq;
+            __syncwarp();
+            // banded-sparse mel: lanes take filters in serpentine order so narrow and wide filters pair up
+#pragma unroll
+            for (int q = 0; q < kMaxMelsPerLane; ++q) {
+                const int base = (q >> 1) * 64;
+                const int m = (q & 1) ? base + 63 - lane : base + lane;
+                if (m < n_mels) {
+                    const int s0 = fb_start[m], ln = fb_len[m];
+                    const float* w = fb_w + fb_off[m];
+                    T acc = (T)0;
+                    for (int k = 0; k < ln; ++k) acc += pbuf[s0 + k] * (T)w[k];
+                    const T db = db10(acc > p.amin ? acc : p.amin);
+                    if (kOut == kOutImage) {
+                        tile[m * (FC + 1) + f] = db;
+                    } else {
+                        p.out[((long long)clip * p.n_frames + t0 + f) * n_mels + m] = db;
+                        wmax = db > wmax ? db : wmax;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (kOut == kOutSpec) {
+            wmax = warp_max(wmax);
+            if (lane == 0 && nf > warp) atomicMax(p.spec_max + clip, ordered_bits((double)wmax));
+        }
+        __syncthreads();
+        if (kOut == kOutImage) {
+            for (int idx = threadIdx.x; idx < n_mels * nf; idx += blockDim.x) {
+                const int m = idx / nf, f = idx - m * nf;
+                p.out[((long long)clip * n_mels + m) * p.n_frames + t0 + f] = tile[m * (FC + 1) + f];
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// audio/features.py:124-126 : c = sqrt(mean(y**2)) + 1e-9 in float32.  One CTA per clip.
+__global__ void clip_scale_kernel(const float* __restrict__ audio, long long n, float* __restrict__ scale_out) {
+    __shared__ double red[32];
+    const float* y = audio + (long long)blockIdx.x * n;
+    double acc = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = y[i];
+        acc += (double)__fmul_rn(v, v);
+    }
+    acc = warp_sum(acc);
+    if (lane_id() == 0) red[warp_id()] = acc;
+    __syncthreads();
+    if (warp_id() == 0) {
+        double v = lane_id() < (int)(blockDim.x >> 5) ? red[lane_id()] : 0.0;
+        v = warp_sum(v);
+        if (lane_id() == 0) {
+            const float mean = (float)(v / (double)n);
+            scale_out[blockIdx.x] = __fadd_rn(sqrtf(mean), 1e-9f);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// librosa.power_to_db top_db clamp (max over the clip) + time-mean + DCT-II(ortho), first n_mfcc rows.
+// DCT and time-mean are both linear, so mean_t DCT(S[:,t]) == DCT(mean_t S[:,t]): one 64x128 product per
+// CLIP instead of per frame.  One CTA (128 threads) per clip; thread m owns mel band m.
+struct MfccFinishParams {
+    const float* spec;        // [N][T][128] mel dB (before the top_db clamp)
+    const long long* spec_max;
+    int T;
+    int n_mels;               // 128
+    int n_mfcc;
+    const float* dct;         // [n_mfcc][n_mels]
+    float top_db;             // 80
+    float* out;               // [N][ld]
+    int ld;
+};
+
+__global__ void mfcc_finish_kernel(MfccFinishParams p) {
+    __shared__ float mean_s[128];
+    const int clip = blockIdx.x;
+    const int m = threadIdx.x;
+    const float floor_db = (float)from_ordered_bits(p.spec_max[clip]) - p.top_db;
+    if (m < p.n_mels) {
+        const float* s = p.spec + (long long)clip * p.T * p.n_mels + m;
+        float acc = 0.0f;
+        for (int t = 0; t < p.T; ++t) {
+            const float v = s[(long long)t * p.n_mels];
+            acc += v > floor_db ? v : floor_db;
+        }
+        mean_s[m] = acc / (float)p.T;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < p.n_mfcc; k += blockDim.x) {
+        const float* d = p.dct + (long long)k * p.n_mels;
+        float acc = 0.0f;
+        for (int j = 0; j < p.n_mels; ++j) acc += d[j] * mean_s[j];
+        p.out[(long long)clip * p.ld + k] = acc;
+    }
+}
+
+// sklearn StandardScaler.transform (audio/features.py:145-146): (x - mean)/scale in float64, cast to f32.
+__global__ void standard_scale_kernel(float* __restrict__ x, int N, int F, int ld,
+                                      const double* __restrict__ mean, const double* __restrict__ scale) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * F) return;
+    const int r = i / F, c = i - r * F;
+    x[(long long)r * ld + c] = (float)(((double)x[(long long)r * ld + c] - mean[c]) / scale[c]);
+}
+
+}  // namespace gat

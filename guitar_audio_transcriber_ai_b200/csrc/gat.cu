@@ -1,0 +1,642 @@
+// libgat.so - host side of the C ABI in include/gat.h: context, tables, weight upload, kernel launches.
+// Built by nvcc for sm_100a.  (tests/emu compiles this same file with g++ against a host emulation of the
+// CUDA execution model to debug kernel logic in a GPU-less container; that build is never shipped.)
+#ifdef GAT_CPU_EMU
+#include "cpu_emu.h"
+using std::max;
+using std::min;
+#endif
+
+#include "common.cuh"
+#include "features.cuh"
+#include "fft.cuh"
+#include "infer.cuh"
+#include "onset.cuh"
+#include "yin.cuh"
+
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gat.h"
+
+using namespace gat;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return 1;
+}
+
+#define GAT_CUDA(expr)                                                                           \
+    do {                                                                                         \
+        cudaError_t e_ = (expr);                                                                 \
+        if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) { p = nullptr; return fail("cudaMalloc(%zu) failed", want); }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+template <typename T>
+int upload(DevBuf& b, const T* host, size_t count) {
+    if (b.ensure(count * sizeof(T))) return 1;
+    GAT_CUDA(cudaMemcpy(b.p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+struct SparseFbDev {
+    DevBuf start, len, off, w;
+    int n_mels = 0, nnz = 0;
+    SparseFb view() const { return SparseFb{n_mels, nnz, start.as<int>(), len.as<int>(), off.as<int>(), w.as<float>()}; }
+};
+
+// dense[row m][col f] with given strides -> contiguous non-zero band per filter
+int build_sparse_fb(SparseFbDev& out, const float* dense, int n_mels, int n_freqs, long long stride_m, long long stride_f) {
+    std::vector<int> start(n_mels), len(n_mels), off(n_mels);
+    std::vector<float> w;
+    for (int m = 0; m < n_mels; ++m) {
+        int first = -1, last = -1;
+        for (int f = 0; f < n_freqs; ++f)
+            if (dense[m * stride_m + f * stride_f] != 0.0f) { if (first < 0) first = f; last = f; }
+        start[m] = first < 0 ? 0 : first;
+        len[m] = first < 0 ? 0 : last - first + 1;
+        off[m] = (int)w.size();
+        for (int f = start[m]; f < start[m] + len[m]; ++f) w.push_back(dense[m * stride_m + f * stride_f]);
+    }
+    if (w.empty()) w.push_back(0.0f);
+    out.n_mels = n_mels;
+    out.nnz = (int)w.size();
+    if (upload(out.start, start.data(), n_mels) || upload(out.len, len.data(), n_mels) ||
+        upload(out.off, off.data(), n_mels) || upload(out.w, w.data(), w.size())) return 1;
+    return 0;
+}
+
+}  // namespace
+
+struct gat_ctx {
+    int device = 0;
+    int num_sms = 1;
+    gat_config cfg{};
+    int64_t launches = 0;
+    // tables
+    DevBuf tw32, w2_32, tw64, w2_64, win_mel, win_mfcc, win64, dct;
+    SparseFbDev fb_mel, fb_mfcc;
+    // models
+    DevBuf mlp_params; int mlp_dims[kMlpMaxLayers + 1] = {0}; int mlp_n_linear = 0; int mlp_n_params = 0;
+    DevBuf conv_w[3], conv_b[3], fc1_w, fc1_b, fc2_w, fc2_b;
+    int conv_ch[4] = {0, 0, 0, 0}; int hidden = 0, classes = 0; bool cnn_loaded = false;
+    DevBuf scaler_mean, scaler_scale; int scaler_n = 0;
+    float w_mlp = 0.2f, w_cnn = 0.8f;
+    // scratch
+    DevBuf clip_scale, spec, spec_max, f0, act1, act2, act3, hz_tmp, logits_cnn, logits_mlp;
+    long long act_shape[3] = {0, 0, 0};   // (chunk, H, W) the zero borders of act1/act2 were prepared for
+    DevBuf seg_small, seg_rms, seg_rms_med, seg_gate, seg_env, seg_envn, seg_cand, seg_peaks, seg_frames, seg_table,
+           seg_keep, seg_dest;
+    // end-to-end staging
+    DevBuf e2e_audio[2], e2e_mel, e2e_mfcc, e2e_probs, e2e_mlp_probs, e2e_cnn_probs, e2e_index, e2e_conf;
+    cudaStream_t e2e_stream[2] = {nullptr, nullptr};
+    bool e2e_streams = false;
+};
+
+extern "C" const char* gat_last_error(void) { return g_error.c_str(); }
+extern "C" int gat_version(void) { return 100; }
+extern "C" int64_t gat_launch_count(const gat_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int32_t gat_num_classes(const gat_ctx* ctx) { return ctx ? (ctx->classes ? ctx->classes : ctx->mlp_dims[ctx->mlp_n_linear]) : 0; }
+extern "C" int32_t gat_mel_frames(const gat_ctx* ctx, int64_t n) { return ctx ? (int32_t)(1 + n / ctx->cfg.mel_hop) : 0; }
+
+#define LAUNCH(ctx, kernel, grid, block, smem, stream, ...)              \
+    do {                                                                 \
+        GAT_LAUNCH(kernel, grid, block, smem, (cudaStream_t)(stream), __VA_ARGS__); \
+        ++(ctx)->launches;                                               \
+        GAT_CUDA(cudaGetLastError());                                    \
+    } while (0)
+
+extern "C" int gat_ctx_create(const gat_config* cfg, int device, gat_ctx** out) {
+    if (!cfg || !out) return fail("gat_ctx_create: null argument");
+    if (cfg->mel_n_fft != 2048) return fail("gat_ctx_create: mel_n_fft=%d unsupported (this build implements n_fft 2048)", cfg->mel_n_fft);
+    if (cfg->mel_n_mels < 1 || cfg->mel_n_mels > 32 * kMaxMelsPerLane || cfg->mfcc_n_mels != 128)
+        return fail("gat_ctx_create: unsupported mel sizes (mel %d, mfcc %d)", cfg->mel_n_mels, cfg->mfcc_n_mels);
+    if (cfg->mel_hop < 1 || (cfg->mel_hop & 1)) return fail("gat_ctx_create: mel_hop must be even");
+    if (!cfg->mel_window || !cfg->mel_fb || !cfg->stft_window || !cfg->mfcc_fb || !cfg->dct)
+        return fail("gat_ctx_create: missing table pointer");
+    GAT_CUDA(cudaSetDevice(device));
+    gat_ctx* c = new gat_ctx();
+    c->device = device;
+    c->cfg = *cfg;
+    c->cfg.mel_window = nullptr; c->cfg.mel_fb = nullptr; c->cfg.stft_window = nullptr; c->cfg.mfcc_fb = nullptr; c->cfg.dct = nullptr;
+#ifdef GAT_CPU_EMU
+    c->num_sms = 2;
+#else
+    cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
+#endif
+    // FFT twiddles, computed in long double and rounded once
+    std::vector<Cpx<double>> tw(1024), w2(1024);
+    std::vector<Cpx<float>> twf(1024), w2f(1024);
+    for (int k2 = 0; k2 < 32; ++k2)
+        for (int n1 = 0; n1 < 32; ++n1) {
+            const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)(n1 * k2) / 1024.0L;
+            tw[k2 * 32 + n1] = Cpx<double>{(double)cosl(a), (double)sinl(a)};
+        }
+    for (int k = 0; k < 1024; ++k) {
+        const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / 2048.0L;
+        w2[k] = Cpx<double>{(double)cosl(a), (double)sinl(a)};
+    }
+    for (int i = 0; i < 1024; ++i) {
+        twf[i] = Cpx<float>{(float)tw[i].x, (float)tw[i].y};
+        w2f[i] = Cpx<float>{(float)w2[i].x, (float)w2[i].y};
+    }
+    std::vector<float> win_mfcc(2048);
+    for (int i = 0; i < 2048; ++i) win_mfcc[i] = (float)cfg->stft_window[i];
+    int rc = 0;
+    rc |= upload(c->tw64, tw.data(), 1024); rc |= upload(c->w2_64, w2.data(), 1024);
+    rc |= upload(c->tw32, twf.data(), 1024); rc |= upload(c->w2_32, w2f.data(), 1024);
+    rc |= upload(c->win_mel, cfg->mel_window, 2048);
+    rc |= upload(c->win_mfcc, win_mfcc.data(), 2048);
+    rc |= upload(c->win64, cfg->stft_window, 2048);
+    rc |= upload(c->dct, cfg->dct, (size_t)cfg->mfcc_n_mfcc * cfg->mfcc_n_mels);
+    rc |= build_sparse_fb(c->fb_mel, cfg->mel_fb, cfg->mel_n_mels, 1025, 1, cfg->mel_n_mels);
+    rc |= build_sparse_fb(c->fb_mfcc, cfg->mfcc_fb, cfg->mfcc_n_mels, 1025, 1025, 1);
+    if (rc) { gat_ctx_destroy(c); return 1; }
+    *out = c;
+    return 0;
+}
+
+extern "C" void gat_ctx_destroy(gat_ctx* c) {
+    if (!c) return;
+    DevBuf* all[] = {&c->tw32, &c->w2_32, &c->tw64, &c->w2_64, &c->win_mel, &c->win_mfcc, &c->win64, &c->dct,
+                     &c->fb_mel.start, &c->fb_mel.len, &c->fb_mel.off, &c->fb_mel.w,
+                     &c->fb_mfcc.start, &c->fb_mfcc.len, &c->fb_mfcc.off, &c->fb_mfcc.w,
+                     &c->mlp_params, &c->conv_w[0], &c->conv_w[1], &c->conv_w[2], &c->conv_b[0], &c->conv_b[1], &c->conv_b[2],
+                     &c->fc1_w, &c->fc1_b, &c->fc2_w, &c->fc2_b, &c->scaler_mean, &c->scaler_scale,
+                     &c->clip_scale, &c->spec, &c->spec_max, &c->f0, &c->act1, &c->act2, &c->act3, &c->hz_tmp, &c->logits_cnn, &c->logits_mlp,
+                     &c->seg_small, &c->seg_rms, &c->seg_rms_med, &c->seg_gate, &c->seg_env, &c->seg_envn, &c->seg_cand,
+                     &c->seg_peaks, &c->seg_frames, &c->seg_table, &c->seg_keep, &c->seg_dest,
+                     &c->e2e_audio[0], &c->e2e_audio[1], &c->e2e_mel, &c->e2e_mfcc, &c->e2e_probs, &c->e2e_mlp_probs,
+                     &c->e2e_cnn_probs, &c->e2e_index, &c->e2e_conf};
+    for (DevBuf* b : all) b->release();
+    if (c->e2e_streams) { cudaStreamDestroy(c->e2e_stream[0]); cudaStreamDestroy(c->e2e_stream[1]); }
+    delete c;
+}
+
+extern "C" int gat_load_mlp(gat_ctx* c, const int32_t* dims, int32_t n_linear, const float* params, int64_t n_params) {
+    if (!c || !dims || !params) return fail("gat_load_mlp: null argument");
+    if (n_linear < 1 || n_linear > kMlpMaxLayers) return fail("gat_load_mlp: %d linear layers unsupported", n_linear);
+    int64_t expect = 0;
+    for (int l = 0; l < n_linear; ++l) {
+        if (dims[l] < 1 || dims[l] > kMlpMaxWidth || dims[l + 1] < 1 || dims[l + 1] > kMlpMaxWidth)
+            return fail("gat_load_mlp: layer width out of range (max %d)", kMlpMaxWidth);
+        expect += (int64_t)dims[l] * dims[l + 1] + dims[l + 1] + (l + 1 < n_linear ? 2 * dims[l + 1] : 0);
+    }
+    if (expect != n_params) return fail("gat_load_mlp: expected %lld parameters, got %lld", (long long)expect, (long long)n_params);
+    if (dims[n_linear] > 64) return fail("gat_load_mlp: more than 64 classes unsupported");
+    if (c->cnn_loaded && c->classes != dims[n_linear]) return fail("gat_load_mlp: class count differs from the CNN's");
+    if ((size_t)n_params * 4 + 8 * 2 * kMlpMaxWidth * 4 > 200 * 1024) return fail("gat_load_mlp: parameters exceed shared memory");
+    if (upload(c->mlp_params, params, (size_t)n_params)) return 1;
+    for (int l = 0; l <= n_linear; ++l) c->mlp_dims[l] = dims[l];
+    c->mlp_n_linear = n_linear;
+    c->mlp_n_params = (int)n_params;
+    return 0;
+}
+
+extern "C" int gat_load_cnn(gat_ctx* c, int32_t n_conv, const int32_t* ch, const float* const* conv_w, const float* const* conv_b,
+                            int32_t hidden, int32_t classes, const float* fc1_w, const float* fc1_b,
+                            const float* fc2_w, const float* fc2_b) {
+    if (!c || !ch || !conv_w || !conv_b || !fc1_w || !fc1_b || !fc2_w || !fc2_b) return fail("gat_load_cnn: null argument");
+    if (n_conv != 3 || ch[0] != 1 || ch[1] != 32 || ch[2] != 64 || ch[3] != 128)
+        return fail("gat_load_cnn: only the reference architecture 1->32->64->128 (3x3, pool 2) is implemented");
+    if (hidden < 1 || hidden > 256 || classes < 1 || classes > 64) return fail("gat_load_cnn: hidden/classes out of range");
+    if (c->mlp_n_linear && c->mlp_dims[c->mlp_n_linear] != classes) return fail("gat_load_cnn: class count differs from the MLP's");
+    for (int i = 0; i < 3; ++i) {
+        if (upload(c->conv_w[i], conv_w[i], (size_t)9 * ch[i] * ch[i + 1])) return 1;
+        if (upload(c->conv_b[i], conv_b[i], (size_t)ch[i + 1])) return 1;
+    }
+    if (upload(c->fc1_w, fc1_w, (size_t)ch[3] * 16 * hidden) || upload(c->fc1_b, fc1_b, hidden) ||
+        upload(c->fc2_w, fc2_w, (size_t)hidden * classes) || upload(c->fc2_b, fc2_b, classes)) return 1;
+    for (int i = 0; i < 4; ++i) c->conv_ch[i] = ch[i];
+    c->hidden = hidden; c->classes = classes; c->cnn_loaded = true;
+    return 0;
+}
+
+extern "C" int gat_set_scaler(gat_ctx* c, const double* mean, const double* scale, int32_t n) {
+    if (!c) return fail("gat_set_scaler: null ctx");
+    if (n <= 0) { c->scaler_n = 0; return 0; }
+    if (upload(c->scaler_mean, mean, n) || upload(c->scaler_scale, scale, n)) return 1;
+    c->scaler_n = n;
+    return 0;
+}
+
+extern "C" int gat_set_ensemble_weights(gat_ctx* c, float w_mlp, float w_cnn) {
+    if (!c) return fail("gat_set_ensemble_weights: null ctx");
+    c->w_mlp = w_mlp; c->w_cnn = w_cnn;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------- features
+namespace {
+
+int launch_clip_scale(gat_ctx* c, const float* audio, int64_t N, int64_t n, void* stream) {
+    if (c->clip_scale.ensure((size_t)N * sizeof(float))) return 1;
+    LAUNCH(c, clip_scale_kernel, (unsigned)N, 256, 0, stream, audio, (long long)n, c->clip_scale.as<float>());
+    return 0;
+}
+
+template <typename T, int kOut, int kThreads>
+int launch_stft_mel(gat_ctx* c, StftMelParams<T> p, void* stream) {
+    const int nwarps = kThreads / 32;
+    int fc = (int)(8192 / p.hop) + 1;
+    fc = fc > 32 ? 32 : fc;
+    if (sizeof(T) == 8) fc = fc > 8 ? 8 : fc;
+    if (fc > p.n_frames) fc = p.n_frames;
+    p.frames_per_cta = fc;
+    p.chunks_per_clip = (p.n_frames + fc - 1) / fc;
+    const size_t smem = stft_mel_smem_bytes<T>(nwarps, fc, p.hop, p.fb.n_mels, p.fb.nnz, kOut == kOutImage);
+    if (smem > 227 * 1024) return fail("stft_mel: %zu bytes of shared memory needed (hop %d)", smem, p.hop);
+    auto kfn = stft_mel_kernel<T, kOut, kThreads>;
+    GAT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long work = (long long)p.N * p.chunks_per_clip;
+    const unsigned grid = (unsigned)(work < c->num_sms ? work : c->num_sms);
+    LAUNCH(c, kfn, grid, kThreads, smem, stream, p);
+    return 0;
+}
+
+int run_melspec(gat_ctx* c, const float* audio, int64_t N, int64_t n, bool normalize, bool scale_ready, float* out, void* stream) {
+    if (n <= 1024) return fail("melspec: clips of %lld samples are too short for reflect padding of 1024", (long long)n);
+    if (normalize && !scale_ready && launch_clip_scale(c, audio, N, n, stream)) return 1;
+    StftMelParams<float> p{};
+    p.audio = audio; p.n = n; p.N = (int)N; p.clip_scale = normalize ? c->clip_scale.as<float>() : nullptr;
+    p.frame_gate = nullptr; p.sample_gate = 0.0f; p.gate_hop = 512;
+    p.hop = c->cfg.mel_hop; p.n_frames = (int)(1 + n / c->cfg.mel_hop); p.pad_mode = kPadReflect;
+    p.window = c->win_mel.as<float>(); p.tw = c->tw32.as<Cpx<float>>(); p.w2 = c->w2_32.as<Cpx<float>>();
+    p.fb = c->fb_mel.view(); p.amin = 1e-10f; p.out = out; p.spec_max = nullptr;
+    return launch_stft_mel<float, kOutImage, 512>(c, p, stream);
+}
+
+int run_mfcc(gat_ctx* c, const float* audio, int64_t N, int64_t n, bool normalize, bool scale_ready, float* out, int ld, void* stream) {
+    const int T = (int)(1 + n / 512);
+    if (normalize && !scale_ready && launch_clip_scale(c, audio, N, n, stream)) return 1;
+    if (c->spec.ensure((size_t)N * T * 128 * sizeof(float)) || c->spec_max.ensure((size_t)N * sizeof(long long))) return 1;
+    GAT_CUDA(cudaMemsetAsync(c->spec_max.p, 0x80, (size_t)N * sizeof(long long), (cudaStream_t)stream));
+    StftMelParams<float> p{};
+    p.audio = audio; p.n = n; p.N = (int)N; p.clip_scale = normalize ? c->clip_scale.as<float>() : nullptr;
+    p.frame_gate = nullptr; p.sample_gate = 0.0f; p.gate_hop = 512;
+    p.hop = 512; p.n_frames = T; p.pad_mode = kPadZero;
+    p.window = c->win_mfcc.as<float>(); p.tw = c->tw32.as<Cpx<float>>(); p.w2 = c->w2_32.as<Cpx<float>>();
+    p.fb = c->fb_mfcc.view(); p.amin = 1e-10f; p.out = c->spec.as<float>(); p.spec_max = c->spec_max.as<long long>();
+    if (launch_stft_mel<float, kOutSpec, 512>(c, p, stream)) return 1;
+    MfccFinishParams f{};
+    f.spec = c->spec.as<float>(); f.spec_max = c->spec_max.as<long long>(); f.T = T; f.n_mels = 128;
+    f.n_mfcc = c->cfg.mfcc_n_mfcc; f.dct = c->dct.as<float>(); f.top_db = 80.0f; f.out = out; f.ld = ld;
+    LAUNCH(c, mfcc_finish_kernel, (unsigned)N, 128, 0, stream, f);
+    return 0;
+}
+
+template <int kLPT>
+int launch_yin(gat_ctx* c, const YinParams& p, void* stream) {
+    const int threads = 384;
+    const size_t smem = (size_t)(threads / 32) * yin_smem_per_warp<kLPT>() + 64;
+    auto kfn = yin_kernel<kLPT>;
+    GAT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long work = (long long)p.N * p.T;
+    const long long ctas = (work + threads / 32 - 1) / (threads / 32);
+    const unsigned grid = (unsigned)(ctas < c->num_sms ? ctas : c->num_sms);
+    LAUNCH(c, kfn, grid, threads, smem, stream, p);
+    return 0;
+}
+
+int run_yin(gat_ctx* c, const float* audio, int64_t N, int64_t n, bool normalize, bool scale_ready, double* hz, double* f0_frames,
+            float* feat, int ld, int col, void* stream) {
+    const int T = (int)(1 + n / 512);
+    if (normalize && !scale_ready && launch_clip_scale(c, audio, N, n, stream)) return 1;
+    double* f0 = f0_frames;
+    if (!f0) { if (c->f0.ensure((size_t)N * T * sizeof(double))) return 1; f0 = c->f0.as<double>(); }
+    if (!hz) { if (c->hz_tmp.ensure((size_t)N * sizeof(double))) return 1; hz = c->hz_tmp.as<double>(); }
+    YinParams p{};
+    p.audio = audio; p.n = n; p.N = (int)N; p.clip_scale = normalize ? c->clip_scale.as<float>() : nullptr;
+    p.T = T; p.hop = 512; p.sr = c->cfg.sample_rate;
+    p.min_period = (int)floor((double)c->cfg.sample_rate / c->cfg.yin_fmax);
+    const int mp = (int)ceil((double)c->cfg.sample_rate / c->cfg.yin_fmin);
+    p.max_period = mp < kYinFrame - kYinWin - 1 ? mp : kYinFrame - kYinWin - 1;
+    if (p.min_period < 1 || p.max_period <= p.min_period + 1) return fail("yin: period range [%d, %d] unusable", p.min_period, p.max_period);
+    p.trough_threshold = c->cfg.yin_trough_threshold; p.f0 = f0;
+    const int lags = p.max_period + 1;
+    int rc;
+    if (lags <= 7 * 32) rc = launch_yin<7>(c, p, stream);
+    else if (lags <= 15 * 32) rc = launch_yin<15>(c, p, stream);
+    else rc = launch_yin<33>(c, p, stream);
+    if (rc) return 1;
+    YinMedianParams m{f0, (int)N, T, hz, feat, ld, col};
+    LAUNCH(c, yin_median_kernel, (unsigned)((N + 3) / 4), 128, 0, stream, m);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int gat_melspec_db(gat_ctx* c, const float* audio, int64_t N, int64_t n, int32_t normalize, float* out, void* stream) {
+    if (!c || !audio || !out) return fail("gat_melspec_db: null argument");
+    if (N <= 0) return 0;
+    return run_melspec(c, audio, N, n, normalize != 0, false, out, stream);
+}
+
+extern "C" int gat_mfcc_features(gat_ctx* c, const float* audio, int64_t N, int64_t n, int32_t normalize, int32_t add_pitch,
+                                 int32_t yin_on_normalized, int32_t apply_scaler, float* out, int32_t ld, double* yin_hz, void* stream) {
+    if (!c || !audio || !out) return fail("gat_mfcc_features: null argument");
+    if (N <= 0) return 0;
+    const int F = c->cfg.mfcc_n_mfcc + (add_pitch ? 1 : 0);
+    if (ld < F) return fail("gat_mfcc_features: ld=%d < %d feature columns", ld, F);
+    if (n < 1) return fail("gat_mfcc_features: empty clips");
+    if (run_mfcc(c, audio, N, n, normalize != 0, false, out, ld, stream)) return 1;
+    if (add_pitch) {
+        const bool yn = normalize && yin_on_normalized;
+        if (run_yin(c, audio, N, n, yn, normalize != 0, yin_hz, nullptr, out, ld, c->cfg.mfcc_n_mfcc, stream)) return 1;
+    }
+    if (apply_scaler) {
+        if (c->scaler_n != F) return fail("gat_mfcc_features: scaler has %d columns, features have %d", c->scaler_n, F);
+        const long long tot = (long long)N * F;
+        LAUNCH(c, standard_scale_kernel, (unsigned)((tot + 255) / 256), 256, 0, stream, out, (int)N, F, ld,
+               c->scaler_mean.as<double>(), c->scaler_scale.as<double>());
+    }
+    return 0;
+}
+
+extern "C" int gat_yin(gat_ctx* c, const float* audio, int64_t N, int64_t n, int32_t normalize, double* hz, double* f0_frames, void* stream) {
+    if (!c || !audio || !hz) return fail("gat_yin: null argument");
+    if (N <= 0) return 0;
+    return run_yin(c, audio, N, n, normalize != 0, false, hz, f0_frames, nullptr, 0, 0, stream);
+}
+
+// ------------------------------------------------------------------------------------------------- inference
+namespace {
+
+constexpr int kCnnChunk = 256;   // clips per pass: keeps act1/act2/act3 (~90 MB at T=87) inside the 126 MB L2
+
+int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, float* cnn_logits, void* stream) {
+    if (!c->cnn_loaded) return fail("infer: no CNN loaded (gat_load_cnn)");
+    const int H0 = c->cfg.mel_n_mels, W0 = T;
+    const int H1 = H0 / 2, W1 = W0 / 2, H2 = H1 / 2, W2 = W1 / 2, H3 = H2 / 2, W3 = W2 / 2;
+    if (H3 < 1 || W3 < 1) return fail("infer: mel image %dx%d too small for three 2x2 pools", H0, W0);
+    const long long chunk = N < kCnnChunk ? N : kCnnChunk;
+    const size_t a1 = (size_t)chunk * (H1 + 2) * (W1 + 2) * 32, a2 = (size_t)chunk * (H2 + 2) * (W2 + 2) * 64,
+                 a3 = (size_t)chunk * H3 * W3 * 128;
+    const bool fresh = c->act1.cap < a1 * 4 || c->act2.cap < a2 * 4 || c->act_shape[0] != chunk || c->act_shape[1] != H0 || c->act_shape[2] != W0;
+    if (c->act1.ensure(a1 * 4) || c->act2.ensure(a2 * 4) || c->act3.ensure(a3 * 4)) return 1;
+    if (fresh) {   // zero borders once per geometry; the kernels only ever write interiors
+        GAT_CUDA(cudaMemsetAsync(c->act1.p, 0, a1 * 4, (cudaStream_t)stream));
+        GAT_CUDA(cudaMemsetAsync(c->act2.p, 0, a2 * 4, (cudaStream_t)stream));
+        c->act_shape[0] = chunk; c->act_shape[1] = H0; c->act_shape[2] = W0;
+    }
+    float* logits = cnn_logits;
+    const size_t head_smem = ((size_t)128 * 16 * kHeadClips + (size_t)c->hidden * kHeadClips + kHeadClips * 64) * sizeof(float) + 64;
+    GAT_CUDA(cudaFuncSetAttribute(cnn_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem));
+    for (long long c0 = 0; c0 < N; c0 += chunk) {
+        const int nc = (int)(N - c0 < chunk ? N - c0 : chunk);
+        Conv1Params p1{mel + c0 * H0 * W0, nc, H0, W0, c->conv_w[0].as<float>(), c->conv_b[0].as<float>(), c->act1.as<float>(), 32, 0.01f};
+        LAUNCH(c, conv1_pool_kernel, (unsigned)(nc * ceil_div(H1 * W1, 256)), 256, 0, stream, p1);
+        ConvParams p2{c->act1.as<float>(), nc, H1, W1, c->conv_w[1].as<float>(), c->conv_b[1].as<float>(), c->act2.as<float>(), 1, 0.01f};
+        auto k2 = conv3x3_pool_kernel<32, 64>;
+        LAUNCH(c, k2, (unsigned)(nc * ceil_div(H2 * W2, 32)), 256, 0, stream, p2);
+        ConvParams p3{c->act2.as<float>(), nc, H2, W2, c->conv_w[2].as<float>(), c->conv_b[2].as<float>(), c->act3.as<float>(), 0, 0.01f};
+        auto k3 = conv3x3_pool_kernel<64, 128>;
+        LAUNCH(c, k3, (unsigned)(nc * ceil_div(H3 * W3, 16)), 256, 0, stream, p3);
+        HeadParams ph{c->act3.as<float>(), nc, H3, W3, 128, c->fc1_w.as<float>(), c->fc1_b.as<float>(), c->hidden,
+                      c->fc2_w.as<float>(), c->fc2_b.as<float>(), c->classes, 0.01f,
+                      logits + c0 * c->classes, cnn_probs + c0 * c->classes};
+        LAUNCH(c, cnn_head_kernel, (unsigned)ceil_div(nc, kHeadClips), 256, head_smem, stream, ph);
+    }
+    return 0;
+}
+
+int run_mlp_ensemble(gat_ctx* c, const float* mfcc, int ld, int64_t N, const float* cnn_probs, float* probs, float* mlp_probs,
+                     float* mlp_logits, int64_t* index, float* conf, void* stream) {
+    if (!c->mlp_n_linear) return fail("infer: no MLP loaded (gat_load_mlp)");
+    MlpParams p{};
+    p.x = mfcc; p.N = (int)N; p.ld = ld; p.params = c->mlp_params.as<float>(); p.n_params = c->mlp_n_params;
+    p.n_linear = c->mlp_n_linear;
+    for (int l = 0; l <= c->mlp_n_linear; ++l) p.dims[l] = c->mlp_dims[l];
+    p.slope = 0.1f; p.ln_eps = 1e-5f; p.cnn_probs = cnn_probs; p.w_mlp = c->w_mlp; p.w_cnn = c->w_cnn;
+    p.mlp_logits = mlp_logits; p.mlp_probs = mlp_probs; p.probs = probs; p.index = (long long*)index; p.conf = conf;
+    const size_t smem = ((size_t)c->mlp_n_params + 8 * 2 * kMlpMaxWidth) * sizeof(float) + 64;
+    GAT_CUDA(cudaFuncSetAttribute(mlp_ensemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long ctas = (N + 7) / 8;
+    LAUNCH(c, mlp_ensemble_kernel, (unsigned)(ctas < c->num_sms ? ctas : c->num_sms), 256, smem, stream, p);
+    return 0;
+}
+
+}  // namespace
+
+// argmax / confidence when only the CNN runs (GAT_FLAG_SKIP_MLP): probs == cnn_probs
+namespace gat {
+__global__ void argmax_kernel(const float* __restrict__ probs, int N, int classes, long long* __restrict__ index, float* __restrict__ conf) {
+    const int clip = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    if (clip >= N) return;
+    const int lane = lane_id();
+    float bv = -1.0f; int bi = 0x7fffffff;
+    for (int k = lane; k < classes; k += 32) {
+        const float v = probs[(long long)clip * classes + k];
+        if (v > bv) { bv = v; bi = k; }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, s);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, s);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { index[clip] = bi; conf[clip] = bv; }
+}
+}  // namespace gat
+
+extern "C" int gat_infer(gat_ctx* c, const float* mfcc, int32_t ld, const float* mel, int64_t N, int32_t T, float* probs,
+                         float* mlp_probs, float* cnn_probs, int64_t* index, float* conf, float* mlp_logits, float* cnn_logits,
+                         void* stream) {
+    if (!c || !mfcc || !mel || !probs || !mlp_probs || !cnn_probs || !index || !conf) return fail("gat_infer: null argument");
+    if (N <= 0) return 0;
+    if (ld < c->mlp_dims[0]) return fail("gat_infer: ld=%d < %d MLP inputs", ld, c->mlp_dims[0]);
+    const int classes = c->classes;
+    float* cl = cnn_logits; float* ml = mlp_logits;
+    // logits are optional for the caller but the kernels always write them: use ctx scratch
+    if (!cl) { if (c->logits_cnn.ensure((size_t)N * classes * sizeof(float))) return 1; cl = c->logits_cnn.as<float>(); }
+    if (!ml) { if (c->logits_mlp.ensure((size_t)N * classes * sizeof(float))) return 1; ml = c->logits_mlp.as<float>(); }
+    if (run_cnn(c, mel, N, T, cnn_probs, cl, stream)) return 1;
+    return run_mlp_ensemble(c, mfcc, ld, N, cnn_probs, probs, mlp_probs, ml, index, conf, stream);
+}
+
+// ------------------------------------------------------------------------------------------------- segmentation
+extern "C" int gat_segment(gat_ctx* c, const float* y, int64_t L, const gat_slicer_params* sp, int32_t max_onsets,
+                           int64_t* onsets, int32_t* n_onsets, float* clips, int64_t* clip_table, int32_t* n_clips,
+                           float* rms_db_out, double* env_out, int64_t* frames_out, int32_t* n_frames_out, void* stream) {
+    if (!c || !y || !sp || !onsets || !n_onsets || !clips || !clip_table || !n_clips) return fail("gat_segment: null argument");
+    if (L <= 1024) return fail("gat_segment: signal of %lld samples is too short (reflect padding needs > 1024)", (long long)L);
+    if (max_onsets < 1) return fail("gat_segment: max_onsets must be positive");
+    if (sp->rms_hop < 1 || sp->onset_hop != 512) return fail("gat_segment: onset hop %d unsupported (the reference always uses 512)", sp->onset_hop);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int T = (int)(1 + L / sp->rms_hop);         // rms frames
+    const int To = (int)(1 + L / sp->onset_hop);      // onset frames
+    // small scalars: [0..1] spec max (8B) | [2..3] env min/max (16B) | n_peaks | any_nonzero | gate
+    if (c->seg_small.ensure(64) || c->seg_rms.ensure((size_t)T * 4) || c->seg_rms_med.ensure((size_t)T * 4) ||
+        c->seg_gate.ensure((size_t)T) || c->spec.ensure((size_t)To * 128 * sizeof(double)) ||
+        c->seg_env.ensure((size_t)To * 8) || c->seg_envn.ensure((size_t)To * 8) || c->seg_cand.ensure((size_t)To) ||
+        c->seg_peaks.ensure((size_t)To * 4) || c->seg_frames.ensure((size_t)To * 8) ||
+        c->seg_table.ensure((size_t)max_onsets * 3 * 8) || c->seg_keep.ensure((size_t)max_onsets) ||
+        c->seg_dest.ensure((size_t)max_onsets * 4)) return 1;
+    unsigned char* small = c->seg_small.as<unsigned char>();
+    long long* spec_max = reinterpret_cast<long long*>(small);
+    long long* env_minmax = reinterpret_cast<long long*>(small + 8);
+    int* n_peaks = reinterpret_cast<int*>(small + 24);
+    int* any_nonzero = reinterpret_cast<int*>(small + 28);
+    float* gate_val = reinterpret_cast<float*>(small + 32);
+    GAT_CUDA(cudaMemsetAsync(small, 0x80, 24, st));
+    GAT_CUDA(cudaMemsetAsync(small + 24, 0, 40, st));
+
+    // 1-3: sample gate (fused into the loads) -> frame RMS dB -> median-5 -> p20 + 6 dB frame gate
+    RmsParams rp{y, (long long)L, T, sp->rms_hop, sp->sample_gate, c->seg_rms.as<float>()};
+    LAUNCH(c, rms_db_kernel, (unsigned)ceil_div(T, 128), 128, 0, st, rp);
+    LAUNCH(c, median5_kernel, (unsigned)ceil_div(T, 256), 256, 0, st, c->seg_rms.as<float>(), c->seg_rms_med.as<float>(), T);
+    GateParams gp{c->seg_rms_med.as<float>(), T, sp->p20_k, sp->p20_gamma, sp->gate_offset_db, c->seg_gate.as<unsigned char>(), gate_val};
+    LAUNCH(c, rms_gate_kernel, 1, 1024, 0, st, gp);
+    if (rms_db_out) GAT_CUDA(cudaMemcpyAsync(rms_db_out, c->seg_rms_med.p, (size_t)T * 4, cudaMemcpyDeviceToDevice, st));
+
+    // 4: float64 STFT -> Slaney mel-128 -> dB of the doubly gated signal
+    StftMelParams<double> p{};
+    p.audio = y; p.n = L; p.N = 1; p.clip_scale = nullptr;
+    p.frame_gate = c->seg_gate.as<unsigned char>(); p.sample_gate = sp->sample_gate; p.gate_hop = sp->rms_hop;
+    p.hop = sp->onset_hop; p.n_frames = To; p.pad_mode = kPadZero;
+    p.window = c->win64.as<double>(); p.tw = c->tw64.as<Cpx<double>>(); p.w2 = c->w2_64.as<Cpx<double>>();
+    p.fb = c->fb_mfcc.view(); p.amin = 1e-10; p.out = c->spec.as<double>(); p.spec_max = spec_max;
+    if (launch_stft_mel<double, kOutSpec, 192>(c, p, st)) return 1;
+
+    // 5-7: flux envelope -> normalise + candidate peaks -> sequential wait rule
+    FluxParams fp{c->spec.as<double>(), spec_max, To, 128, 1 + 2048 / (2 * sp->onset_hop), 80.0, c->seg_env.as<double>(), env_minmax};
+    LAUNCH(c, onset_flux_kernel, (unsigned)ceil_div(To, 128), 128, 0, st, fp);
+    PeakParams pp{c->seg_env.as<double>(), env_minmax, To, sp->pre_max, sp->post_max, sp->pre_avg, sp->post_avg, sp->wait,
+                  (double)sp->delta, c->seg_envn.as<double>(), c->seg_cand.as<unsigned char>(), n_peaks, c->seg_peaks.as<int>(), any_nonzero};
+    LAUNCH(c, peak_candidates_kernel, (unsigned)ceil_div(To, 128), 128, 0, st, pp);
+    LAUNCH(c, peak_select_kernel, 1, 32, 0, st, pp);
+    if (env_out) GAT_CUDA(cudaMemcpyAsync(env_out, c->seg_envn.p, (size_t)To * 8, cudaMemcpyDeviceToDevice, st));
+
+    // 8-9: backtrack, min separation, slice table
+    SliceParams s{c->seg_envn.as<double>(), To, n_peaks, c->seg_peaks.as<int>(), sp->onset_hop, (long long)L,
+                  (long long)sp->min_sep_samples, (long long)sp->attack_skip, (long long)sp->clip_len, max_onsets,
+                  n_onsets, (long long*)onsets, c->seg_frames.as<long long>(), c->seg_table.as<long long>()};
+    LAUNCH(c, backtrack_kernel, (unsigned)ceil_div(To, 128), 128, 0, st, s);
+    LAUNCH(c, minsep_table_kernel, 1, 32, 0, st, s);
+    if (frames_out && n_frames_out) {
+        const size_t nb = (size_t)(max_onsets < To ? max_onsets : To) * 8;
+        GAT_CUDA(cudaMemcpyAsync(frames_out, c->seg_frames.p, nb, cudaMemcpyDeviceToDevice, st));
+        GAT_CUDA(cudaMemcpyAsync(n_frames_out, n_peaks, 4, cudaMemcpyDeviceToDevice, st));
+    }
+
+    // 10-11: loudness test, compaction, gather
+    GatherParams g{y, (long long)L, n_onsets, c->seg_table.as<long long>(), (long long)sp->clip_len, sp->min_slice_rms_db,
+                   c->seg_keep.as<unsigned char>(), c->seg_dest.as<int>(), n_clips, clips, (long long*)clip_table, max_onsets};
+    LAUNCH(c, slice_loudness_kernel, (unsigned)max_onsets, 256, 0, st, g);
+    LAUNCH(c, slice_compact_kernel, 1, 32, 0, st, g);
+    LAUNCH(c, slice_gather_kernel, (unsigned)max_onsets, 256, 0, st, g);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------- end to end
+extern "C" int gat_transcribe_clips(gat_ctx* c, const float* audio, int64_t N, int64_t n, int32_t flags, float* probs,
+                                    float* mlp_probs, float* cnn_probs, int64_t* index, float* conf, float* mfcc, float* mel,
+                                    double* yin_hz, void* stream) {
+    if (!c || !audio || !probs || !index || !conf) return fail("gat_transcribe_clips: null argument");
+    if (N <= 0) return 0;
+    const bool skip_mlp = (flags & GAT_FLAG_SKIP_MLP) != 0;
+    const int T = (int)(1 + n / c->cfg.mel_hop);
+    const int classes = c->classes;
+    const int F = c->cfg.mfcc_n_mfcc + 1;
+    if (!c->cnn_loaded) return fail("gat_transcribe_clips: no CNN loaded");
+    if (!skip_mlp && (!mlp_probs || !cnn_probs)) return fail("gat_transcribe_clips: mlp_probs/cnn_probs required unless GAT_FLAG_SKIP_MLP");
+    if (!mel) { if (c->e2e_mel.ensure((size_t)N * c->cfg.mel_n_mels * T * 4)) return 1; mel = c->e2e_mel.as<float>(); }
+    if (!skip_mlp && !mfcc) { if (c->e2e_mfcc.ensure((size_t)N * F * 4)) return 1; mfcc = c->e2e_mfcc.as<float>(); }
+    if (c->logits_cnn.ensure((size_t)N * classes * 4) || c->logits_mlp.ensure((size_t)N * classes * 4)) return 1;
+    float* cnn_logits = c->logits_cnn.as<float>();
+    float* mlp_logits = c->logits_mlp.as<float>();
+    // one RMS pass serves all three chains (the reference recomputes it per chain: features.py:185,311,460,497)
+    if (launch_clip_scale(c, audio, N, n, stream)) return 1;
+    if (run_melspec(c, audio, N, n, true, true, mel, stream)) return 1;
+    if (skip_mlp) {
+        if (run_cnn(c, mel, N, T, probs, cnn_logits, stream)) return 1;
+        if (cnn_probs && cnn_probs != probs)
+            GAT_CUDA(cudaMemcpyAsync(cnn_probs, probs, (size_t)N * classes * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        LAUNCH(c, argmax_kernel, (unsigned)((N + 7) / 8), 256, 0, stream, probs, (int)N, classes, (long long*)index, conf);
+        return 0;
+    }
+    if (run_mfcc(c, audio, N, n, true, true, mfcc, F, stream)) return 1;
+    if (run_yin(c, audio, N, n, (flags & GAT_FLAG_YIN_ON_NORMALIZED) != 0, true, yin_hz, nullptr, mfcc, F, c->cfg.mfcc_n_mfcc, stream)) return 1;
+    if (flags & GAT_FLAG_APPLY_SCALER) {
+        if (c->scaler_n != F) return fail("gat_transcribe_clips: scaler has %d columns, features have %d", c->scaler_n, F);
+        const long long tot = (long long)N * F;
+        LAUNCH(c, standard_scale_kernel, (unsigned)((tot + 255) / 256), 256, 0, stream, mfcc, (int)N, F, F,
+               c->scaler_mean.as<double>(), c->scaler_scale.as<double>());
+    }
+    if (run_cnn(c, mel, N, T, cnn_probs, cnn_logits, stream)) return 1;
+    return run_mlp_ensemble(c, mfcc, F, N, cnn_probs, probs, mlp_probs, mlp_logits, index, conf, stream);
+}
+
+extern "C" int gat_transcribe_clips_host(gat_ctx* c, const float* audio_host, int64_t N, int64_t n, int32_t flags,
+                                         int64_t* index_host, float* conf_host, float* probs_host) {
+    if (!c || !audio_host || !index_host || !conf_host) return fail("gat_transcribe_clips_host: null argument");
+    if (N <= 0) return 0;
+    if (!c->e2e_streams) {
+        GAT_CUDA(cudaStreamCreateWithFlags(&c->e2e_stream[0], cudaStreamNonBlocking));
+        GAT_CUDA(cudaStreamCreateWithFlags(&c->e2e_stream[1], cudaStreamNonBlocking));
+        c->e2e_streams = true;
+    }
+    const int classes = c->classes;
+    const int64_t chunk = N < 512 ? N : 512;   // 512 one-second clips = 45 MB per copy
+    if (c->e2e_audio[0].ensure((size_t)chunk * n * 4) || c->e2e_audio[1].ensure((size_t)chunk * n * 4) ||
+        c->e2e_probs.ensure((size_t)N * classes * 4) || c->e2e_mlp_probs.ensure((size_t)N * classes * 4) ||
+        c->e2e_cnn_probs.ensure((size_t)N * classes * 4) || c->e2e_index.ensure((size_t)N * 8) || c->e2e_conf.ensure((size_t)N * 4)) return 1;
+    // The scratch buffers inside the ctx are shared, so the kernels of consecutive chunks are serialised on
+    // stream 0; stream 1 only carries the host-to-device copy of the NEXT chunk, which is what overlaps.
+    cudaEvent_t copied[2], consumed[2];
+    for (int i = 0; i < 2; ++i) {
+        GAT_CUDA(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+        GAT_CUDA(cudaEventCreateWithFlags(&consumed[i], cudaEventDisableTiming));
+    }
+    int rc = 0;
+    int64_t k = 0;
+    for (int64_t c0 = 0; c0 < N && !rc; c0 += chunk, ++k) {
+        const int b = (int)(k & 1);
+        const int64_t nc = N - c0 < chunk ? N - c0 : chunk;
+        if (k >= 2) GAT_CUDA(cudaStreamWaitEvent(c->e2e_stream[1], consumed[b], 0));
+        GAT_CUDA(cudaMemcpyAsync(c->e2e_audio[b].p, audio_host + c0 * n, (size_t)nc * n * 4, cudaMemcpyHostToDevice, c->e2e_stream[1]));
+        GAT_CUDA(cudaEventRecord(copied[b], c->e2e_stream[1]));
+        GAT_CUDA(cudaStreamWaitEvent(c->e2e_stream[0], copied[b], 0));
+        rc = gat_transcribe_clips(c, c->e2e_audio[b].as<float>(), nc, n, flags, c->e2e_probs.as<float>() + c0 * classes,
+                                  c->e2e_mlp_probs.as<float>() + c0 * classes, c->e2e_cnn_probs.as<float>() + c0 * classes,
+                                  c->e2e_index.as<int64_t>() + c0, c->e2e_conf.as<float>() + c0, nullptr, nullptr, nullptr,
+                                  c->e2e_stream[0]);
+        GAT_CUDA(cudaEventRecord(consumed[b], c->e2e_stream[0]));
+    }
+    if (!rc) {
+        GAT_CUDA(cudaMemcpyAsync(index_host, c->e2e_index.p, (size_t)N * 8, cudaMemcpyDeviceToHost, c->e2e_stream[0]));
+        GAT_CUDA(cudaMemcpyAsync(conf_host, c->e2e_conf.p, (size_t)N * 4, cudaMemcpyDeviceToHost, c->e2e_stream[0]));
+        if (probs_host) GAT_CUDA(cudaMemcpyAsync(probs_host, c->e2e_probs.p, (size_t)N * classes * 4, cudaMemcpyDeviceToHost, c->e2e_stream[0]));
+    }
+    GAT_CUDA(cudaStreamSynchronize(c->e2e_stream[1]));
+    GAT_CUDA(cudaStreamSynchronize(c->e2e_stream[0]));
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(copied[i]); cudaEventDestroy(consumed[i]); }
+    return rc;
+}

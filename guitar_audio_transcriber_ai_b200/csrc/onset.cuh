@@ -1,0 +1,367 @@
+// Whole-file segmentation (reference: audio/slicing.py:30-165): noise gate -> frame RMS gate -> spectral
+// flux onset strength -> peak picking -> backtracking -> minimum separation -> fixed-length slices.
+//
+// The reference runs this chain in float64 (the gates multiply by a float64 mask) with several exact
+// comparisons, so the arithmetic here follows its dtypes AND its summation orders where a decision hangs
+// on them (frame RMS: float32 sequential; mel-band mean: float64 sequential).  The mel spectrogram itself
+// comes from stft_mel_kernel<double, kOutSpec> in features.cuh.
+#pragma once
+#include "common.cuh"
+#include "features.cuh"
+
+namespace gat {
+
+// ---- librosa.feature.rms(frame 2048, hop, reflect centre padding) on the sample-gated signal, then
+//      20*log10(rms + 1e-10) in float32 (slicing.py:44-53).  librosa squares the strided (2048, T) frame
+//      view in float32; numpy keeps the frame axis contiguous in the result, so np.mean over it runs
+//      numpy's PAIRWISE float32 summation per frame: blocks of 128 values, eight interleaved accumulators
+//      per block folded as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), block sums folded as a binary tree.  One
+//      thread per frame reproduces that order exactly (verified bit-for-bit in tests); a warp stages a
+//      32-frame x 32-sample tile at a time so global reads stay coalesced.
+//      np.log10 on float32 is glibc's log10f (not correctly rounded, libm-version dependent); we round the
+//      float64 log10 instead, which can differ from it by <= 3 float32 ulp (~1e-5 dB).
+struct RmsParams {
+    const float* y; long long L; int T; int hop; float sample_gate;
+    float* rms_db;   // [T]
+};
+
+__global__ void __launch_bounds__(128) rms_db_kernel(RmsParams p) {
+    __shared__ float tile[4][32][33];
+    const int lane = lane_id(), warp = warp_id();
+    const int t = (blockIdx.x * 4 + warp) * 32 + lane;
+    const int t_base = (blockIdx.x * 4 + warp) * 32;
+    float r[8];
+    float sums[4];      // binary-counter stack of block sums: 16 blocks of 128 -> 4 levels
+    float total = 0.0f;
+    for (int j0 = 0; j0 < 2048; j0 += 32) {
+        for (int row = 0; row < 32; ++row) {                  // row = frame t_base + row, 32 consecutive samples
+            const int tt = t_base + row;
+            float v = 0.0f;
+            if (tt < p.T) {
+                long long s = (long long)tt * p.hop + j0 + lane - 1024;
+                if (s < 0 || s >= p.L) s = reflect_index(s, p.L);
+                v = p.y[s];
+                if (!(fabsf(v) >= p.sample_gate)) v = 0.0f;
+            }
+            tile[warp][row][lane] = v;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float v = tile[warp][lane][j];
+            const float sq = __fmul_rn(v, v);
+            if (((j0 + j) & 127) < 8) r[j & 7] = sq;           // first eight of a block initialise the lanes
+            else r[j & 7] = __fadd_rn(r[j & 7], sq);
+        }
+        if (((j0 + 32) & 127) == 0) {                          // a block of 128 is complete
+            float bs = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                                 __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+            const int k = j0 >> 7;                             // block index 0..15
+#pragma unroll
+            for (int lvl = 0; lvl < 4; ++lvl) {
+                if ((k >> lvl) & 1) bs = __fadd_rn(sums[lvl], bs);
+                else { sums[lvl] = bs; break; }
+                if (lvl == 3) total = bs;
+            }
+        }
+        __syncwarp();
+    }
+    if (t < p.T) {
+        const float rms = sqrtf(total / 2048.0f);
+        const float l = (float)log10((double)__fadd_rn(rms, 1e-10f));
+        p.rms_db[t] = __fmul_rn(20.0f, l);
+    }
+}
+
+// ---- scipy.ndimage.median_filter(size=5), default mode 'reflect' (edge sample repeated) (slicing.py:55)
+__global__ void median5_kernel(const float* __restrict__ in, float* __restrict__ out, int T) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    float v[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        int i = t + k - 2;
+        // 'reflect': (d c b a | a b c d | d c b a)
+        while (i < 0 || i >= T) { if (i < 0) i = -i - 1; if (i >= T) i = 2 * T - 1 - i; }
+        v[k] = in[i];
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4 - a; ++b)
+            if (v[b] > v[b + 1]) { const float x = v[b]; v[b] = v[b + 1]; v[b + 1] = x; }
+    out[t] = v[2];
+}
+
+// ---- np.percentile(rms_db, 20) with linear interpolation in float32, gate = p20 + 6 dB, frame mask
+//      (slicing.py:59-90).  Exact order statistics by a 4-pass 8-bit radix select; a single CTA.
+struct GateParams {
+    const float* db; int T;
+    int k_lo;            // floor of the virtual index (T-1)*q computed in float32 on the host
+    float gamma;         // its fractional part, float32
+    float gate_offset;   // 6.0
+    unsigned char* frame_gate;   // [T] 1 = keep
+    float* gate_out;     // [1] gate level in dB (diagnostic)
+};
+
+__device__ __forceinline__ unsigned ordered_u32(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_u32(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// k-th smallest (0-based) of db[0..T); every thread of the CTA returns the same value.
+__device__ float radix_select(const float* __restrict__ db, int T, int k, unsigned* hist /*[256] shared*/) {
+    unsigned prefix = 0, mask = 0;
+    int kk = k;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < T; i += blockDim.x) {
+            const unsigned u = ordered_u32(db[i]);
+            if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        // every thread walks the 256 bins (cheap, avoids another broadcast)
+        unsigned cum = 0; int bin = 0;
+        for (; bin < 256; ++bin) {
+            const unsigned h = hist[bin];
+            if (cum + h > (unsigned)kk) break;
+            cum += h;
+        }
+        kk -= (int)cum;
+        prefix |= (unsigned)bin << shift;
+        mask |= 255u << shift;
+        __syncthreads();
+    }
+    return from_ordered_u32(prefix);
+}
+
+__global__ void __launch_bounds__(1024) rms_gate_kernel(GateParams p) {
+    __shared__ unsigned hist[256];
+    const float a = radix_select(p.db, p.T, p.k_lo, hist);
+    const float b = radix_select(p.db, p.T, min(p.k_lo + 1, p.T - 1), hist);
+    // numpy _lerp in float32: a + (b-a)*t, replaced by b - (b-a)*(1-t) where t >= 0.5
+    const float diff = __fsub_rn(b, a);
+    float q = __fadd_rn(a, __fmul_rn(diff, p.gamma));
+    if (p.gamma >= 0.5f) q = __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.0f, p.gamma)));
+    const float gate = __fadd_rn(q, p.gate_offset);
+    if (threadIdx.x == 0) p.gate_out[0] = gate;
+    for (int i = threadIdx.x; i < p.T; i += blockDim.x) p.frame_gate[i] = p.db[i] > gate ? 1 : 0;
+}
+
+// ---- onset strength (librosa.onset.onset_strength): S' = max(S, max(S) - 80); flux[u] = mean_m
+//      relu(S'[u+1][m] - S'[u][m]); env = [0,0,0, flux...][:T].  Also tracks min / max of env.
+struct FluxParams {
+    const double* spec;        // [T][n_mels] mel dB before the top_db clamp
+    const long long* spec_max; // ordered bits of the global max
+    int T, n_mels, lag_pad;    // lag_pad = 1 + 2048/(2*hop) = 3
+    double top_db;
+    double* env;               // [T]
+    long long* env_minmax;     // [2] ordered bits: min (stored negated for atomicMax), max
+};
+
+__global__ void onset_flux_kernel(FluxParams p) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0.0;
+    if (t < p.T) {
+        const int u = t - p.lag_pad;
+        if (u >= 0 && u + 1 < p.T) {
+            const double floor_db = from_ordered_bits(p.spec_max[0]) - p.top_db;
+            const double* s0 = p.spec + (long long)u * p.n_mels;
+            const double* s1 = s0 + p.n_mels;
+            double acc = 0.0;
+            for (int m = 0; m < p.n_mels; ++m) {
+                const double a = s0[m] > floor_db ? s0[m] : floor_db;
+                const double b = s1[m] > floor_db ? s1[m] : floor_db;
+                const double d = b - a;
+                acc = __dadd_rn(acc, d > 0.0 ? d : 0.0);
+            }
+            e = acc / (double)p.n_mels;
+        }
+        p.env[t] = e;
+    }
+    double mx = t < p.T ? e : -1e300, mn = t < p.T ? e : 1e300;
+    mx = warp_max(mx); mn = warp_min(mn);
+    if (lane_id() == 0) {
+        atomicMax(p.env_minmax + 1, ordered_bits(mx));
+        atomicMax(p.env_minmax + 0, ordered_bits(-mn));
+    }
+}
+
+// ---- onset_detect normalisation + candidate peaks (librosa.util.peak_pick's two tests)
+struct PeakParams {
+    const double* env; const long long* env_minmax; int T;
+    int pre_max, post_max, pre_avg, post_avg, wait;
+    double delta;              // float32(0.07) promoted
+    double* envn;              // [T] normalised envelope
+    unsigned char* cand;       // [T]
+    int* n_peaks; int* peaks;  // outputs of peak_select_kernel
+    int* any_nonzero;          // [1]
+};
+
+__global__ void peak_candidates_kernel(PeakParams p) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.T) return;
+    const double mn = -from_ordered_bits(p.env_minmax[0]);
+    const double mx = from_ordered_bits(p.env_minmax[1]);
+    const double den = __dadd_rn(__dsub_rn(mx, mn), 2.2250738585072014e-308);
+    auto x = [&](int i) { return __ddiv_rn(__dsub_rn(p.env[i], mn), den); };
+    const double xt = x(t);
+    p.envn[t] = xt;
+    if (xt != 0.0) atomicExch(p.any_nonzero, 1);
+    const int lo_m = t == 0 ? 0 : max(0, t - p.pre_max), hi_m = min(t + p.post_max, p.T);
+    double mxw = -1e300;
+    for (int i = lo_m; i < hi_m; ++i) { const double v = x(i); mxw = v > mxw ? v : mxw; }
+    bool ok = t == 0 ? (xt >= mxw) : (xt == mxw);
+    if (ok) {
+        const int lo_a = t == 0 ? 0 : max(0, t - p.pre_avg), hi_a = min(t + p.post_avg, p.T);
+        double acc = 0.0;
+        for (int i = lo_a; i < hi_a; ++i) acc = __dadd_rn(acc, x(i));
+        const double avg = __ddiv_rn(acc, (double)(hi_a - lo_a));
+        ok = xt >= __dadd_rn(avg, p.delta);
+    }
+    p.cand[t] = ok ? 1 : 0;
+}
+
+// Sequential `wait` rule: after a peak at n the next frame examined is n + wait + 1.  One warp walks the
+// candidate flags 32 at a time with a ballot; only set bits cost serial work.
+__global__ void peak_select_kernel(PeakParams p) {
+    const int lane = lane_id();
+    int count = 0;
+    int next_ok = 0;                       // first frame index that may be examined
+    if (*p.any_nonzero == 0) { if (lane == 0) *p.n_peaks = 0; return; }
+    for (int base = 0; base < p.T; base += 32) {
+        const int t = base + lane;
+        unsigned m = __ballot_sync(0xffffffffu, t < p.T && p.cand[t]);
+        while (m) {
+            const int b = __ffs((int)m) - 1;
+            m &= m - 1;
+            const int n = base + b;
+            if (n >= next_ok) {
+                if (lane == 0) p.peaks[count] = n;
+                ++count;
+                next_ok = n + p.wait + 1;
+            }
+        }
+    }
+    if (lane == 0) *p.n_peaks = count;
+}
+
+// ---- onset_backtrack + frames_to_samples + greedy minimum separation + slice table (slicing.py:109-136,
+//      :153-161).  K is small (one entry per note), so a single thread does the sequential parts.
+struct SliceParams {
+    const double* envn; int T;
+    const int* n_peaks; const int* peaks;
+    int hop; long long L;
+    long long min_sep_samples;   // int(min_sep * sr)
+    long long skip;              // int(attack_skip_sec * sr)
+    long long length;            // int(length_sec * sr)
+    int max_onsets;
+    int* n_onsets; long long* onsets;          // filtered onset sample positions
+    long long* frames_bt;                      // [n_peaks] backtracked frames (diagnostic)
+    long long* table;                          // [max_onsets][3] start, end, valid
+};
+
+__global__ void backtrack_kernel(SliceParams p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *p.n_peaks) return;
+    int f = p.peaks[i];
+    // nearest local minimum at or before the event; index 0 always qualifies (fix_frames pads it)
+    while (f > 0) {
+        if (f <= p.T - 2 && p.envn[f] <= p.envn[f - 1] && p.envn[f] < p.envn[f + 1]) break;
+        --f;
+    }
+    p.frames_bt[i] = f;
+}
+
+__global__ void minsep_table_kernel(SliceParams p) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int n = *p.n_peaks;
+    int k = 0;
+    long long last = -999999;
+    for (int i = 0; i < n; ++i) {
+        const long long s = p.frames_bt[i] * p.hop;
+        if (s - last >= p.min_sep_samples && k < p.max_onsets) { p.onsets[k++] = s; last = s; }
+    }
+    *p.n_onsets = k;
+    for (int i = 0; i < k; ++i) {
+        const long long next = i + 1 < k ? p.onsets[i + 1] : p.onsets[k - 1];
+        const long long start = p.onsets[i] + p.skip;
+        const long long end = (start + p.length < next) ? start + p.length : next;
+        const bool empty = start >= p.L || end > p.L;
+        p.table[3 * i + 0] = start;
+        p.table[3 * i + 1] = end;
+        p.table[3 * i + 2] = empty ? 0 : 1;
+    }
+}
+
+// ---- is_slice_loud_enough (slicing.py:96-100) on the zero-padded fixed-length clip, compaction, gather.
+struct GatherParams {
+    const float* y; long long L;
+    const int* n_onsets; const long long* table;
+    long long length;
+    float min_rms_db;            // -37
+    unsigned char* keep;         // [max_onsets]
+    int* dest;                   // [max_onsets] compacted position
+    int* n_clips;
+    float* clips;                // [max_onsets][length]
+    long long* clip_table;       // [max_onsets][3]: onset index, start, end
+    int max_onsets;
+};
+
+__global__ void slice_loudness_kernel(GatherParams p) {
+    __shared__ double red[8];
+    const int i = blockIdx.x;
+    if (i >= *p.n_onsets) return;
+    const long long start = p.table[3 * i], end = p.table[3 * i + 1];
+    const bool valid = p.table[3 * i + 2] != 0;
+    double acc = 0.0;
+    if (valid)   // python slicing y[start:end] with end < start is empty; the pad makes it all zeros
+        for (long long s = start + threadIdx.x; s < end; s += blockDim.x) { const float v = p.y[s]; acc += (double)__fmul_rn(v, v); }
+    acc = warp_sum(acc);
+    if (lane_id() == 0) red[warp_id()] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+        bool keep = false;
+        if (valid) {
+            const float rms = sqrtf((float)(s / (double)p.length));
+            const float db = __fmul_rn(20.0f, (float)log10((double)__fadd_rn(rms, 1e-10f)));
+            keep = db > p.min_rms_db;
+        }
+        p.keep[i] = keep ? 1 : 0;
+    }
+}
+
+__global__ void slice_compact_kernel(GatherParams p) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int n = *p.n_onsets;
+    int k = 0;
+    for (int i = 0; i < n; ++i) {
+        p.dest[i] = p.keep[i] ? k : -1;
+        if (p.keep[i]) {
+            p.clip_table[3 * k + 0] = i;
+            p.clip_table[3 * k + 1] = p.table[3 * i];
+            p.clip_table[3 * k + 2] = p.table[3 * i + 1];
+            ++k;
+        }
+    }
+    *p.n_clips = k;
+}
+
+__global__ void slice_gather_kernel(GatherParams p) {
+    const int i = blockIdx.x;
+    if (i >= *p.n_onsets) return;
+    const int d = p.dest[i];
+    if (d < 0) return;
+    const long long start = p.table[3 * i], end = p.table[3 * i + 1];
+    float* o = p.clips + (long long)d * p.length;
+    for (long long j = threadIdx.x; j < p.length; j += blockDim.x)
+        o[j] = (start + j < end) ? p.y[start + j] : 0.0f;
+}
+
+}  // namespace gat

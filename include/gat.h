@@ -1,0 +1,164 @@
+/* gat.h - C ABI of the B200-native guitar-audio-transcriber hot path (libgat.so).
+ *
+ * The reference (gkotti4/guitar-audio-transcriber-ai, version_1) is pure Python: it has no FFI, its
+ * boundary is a handful of Python classes.  Each entry point below replaces the arithmetic behind one of
+ * those call sites (paths relative to /root/reference/version_1/source); INTEGRATION.md shows the ctypes
+ * stub a maintainer would add at each site.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; gat_last_error() returns a thread-local
+ *     message.  No C++ exception crosses the boundary.
+ *   - pointers named *_dev are CUDA device pointers owned by the caller; *_host are host pointers.
+ *     The library never allocates caller-visible memory.  `stream` is a cudaStream_t passed as void*;
+ *     *_dev entry points only enqueue work on it and return.
+ *   - a gat_ctx owns the constant tables, packed weights and scratch buffers of ONE device; it is not
+ *     thread-safe; use one ctx per (device, stream).
+ */
+#ifndef GAT_H_
+#define GAT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gat_ctx gat_ctx;
+
+/* Constant tables are passed in (host pointers, copied) rather than recomputed, so that they are
+ * bit-identical to what the reference's libraries build:
+ *   mel_window  torch.hann_window(n_fft)                          (torchaudio MelSpectrogram)
+ *   mel_fb      torchaudio.functional.melscale_fbanks(...)        [n_fft/2+1][mel_n_mels]
+ *   stft_window scipy.signal.get_window("hann", 2048, fftbins=1)  (librosa.stft, float64)
+ *   mfcc_fb     librosa.filters.mel(sr, 2048, n_mels=128)         [mfcc_n_mels][1025]
+ *   dct         scipy.fft.dct(eye(mfcc_n_mels), type 2, ortho)[:n_mfcc]  [mfcc_n_mfcc][mfcc_n_mels]
+ */
+typedef struct gat_config {
+    int32_t sample_rate;        /* checkpoint target_sr (config.py:29)                               */
+    int32_t mel_n_fft;          /* MelSpecConfig.N_FFT; this build supports 2048                      */
+    int32_t mel_hop;            /* MelSpecConfig.HOP_LENGTH                                           */
+    int32_t mel_n_mels;         /* MelSpecConfig.N_MELS (<= 128)                                      */
+    const float* mel_window;
+    const float* mel_fb;
+    int32_t mfcc_n_mels;        /* librosa default 128                                                */
+    int32_t mfcc_n_mfcc;        /* MFCCConfig.N_MFCC                                                  */
+    const double* stft_window;
+    const float* mfcc_fb;
+    const float* dct;
+    double yin_fmin;            /* YinDsp defaults 50 / 1000 (dsp/yin.py:12)                          */
+    double yin_fmax;
+    double yin_trough_threshold;/* librosa.yin default 0.1                                            */
+} gat_config;
+
+const char* gat_last_error(void);
+int gat_version(void);
+
+/* Transcriber.__init__ / NotePredictor.load_models (transcribe.py:26-75, note_predictor.py:29-80). */
+int gat_ctx_create(const gat_config* cfg, int device, gat_ctx** out);
+void gat_ctx_destroy(gat_ctx* ctx);
+
+/* MLP (training/mlp_trainer.py:32-105).  dims[0..n_linear] = layer widths; params packed per Linear as
+ * W^T[in][out], b[out] and, for every Linear but the last, LayerNorm gamma[out], beta[out]. */
+int gat_load_mlp(gat_ctx* ctx, const int32_t* dims, int32_t n_linear, const float* params_host, int64_t n_params);
+
+/* CNN (training/cnn_trainer.py:30-139), eval-mode BatchNorm already folded into the convs.
+ * conv_w[i]: [9][c_in][c_out]; fc1_w: [flat][hidden] with flat index c*16 + i*4 + j; fc2_w: [hidden][classes]. */
+int gat_load_cnn(gat_ctx* ctx, int32_t n_conv, const int32_t* channels /* n_conv+1 */,
+                 const float* const* conv_w_host, const float* const* conv_b_host,
+                 int32_t hidden, int32_t classes,
+                 const float* fc1_w_host, const float* fc1_b_host,
+                 const float* fc2_w_host, const float* fc2_b_host);
+
+/* sklearn StandardScaler of the MLP checkpoint (features.py:145-146); n = 0 clears it. */
+int gat_set_scaler(gat_ctx* ctx, const double* mean_host, const double* scale_host, int32_t n);
+
+/* NotePredictor.cnn_weight / mlp_weight (note_predictor.py:25-26); defaults 0.8f / 0.2f. */
+int gat_set_ensemble_weights(gat_ctx* ctx, float mlp_weight, float cnn_weight);
+
+/* ---- features ---------------------------------------------------------------------------------- */
+
+/* MelFeatureBuilder.extract_melspec_features per clip (features.py:296-316, :486-502):
+ * out_dev[N][mel_n_mels][T], T = 1 + n / mel_hop.  normalize = NORMALIZE_AUDIO_VOLUME. */
+int gat_melspec_db(gat_ctx* ctx, const float* audio_dev, int64_t N, int64_t n, int32_t normalize,
+                   float* out_dev, void* stream);
+
+/* MelFeatureBuilder.extract_mfcc_features per clip (features.py:182-208, :458-478):
+ * out_dev[N][ld] <- MFCC time-mean (n_mfcc columns) [+ log10(YIN Hz) in column n_mfcc if add_pitch].
+ * yin_on_normalized: 1 = memory path (features.py:473), 0 = file path (:201).
+ * apply_scaler: 1 = StandardScaler.transform afterwards (file path only, features.py:145-146).
+ * yin_hz_dev: optional [N] float64 median pitch (dsp/yin.py:67), may be NULL. */
+int gat_mfcc_features(gat_ctx* ctx, const float* audio_dev, int64_t N, int64_t n, int32_t normalize,
+                      int32_t add_pitch, int32_t yin_on_normalized, int32_t apply_scaler,
+                      float* out_dev, int32_t ld, double* yin_hz_dev, void* stream);
+
+/* YinDsp.estimate_pitch (dsp/yin.py:39-75): hz_dev[N] float64 median f0; f0_frames_dev[N][1+n/512] optional. */
+int gat_yin(gat_ctx* ctx, const float* audio_dev, int64_t N, int64_t n, int32_t normalize,
+            double* hz_dev, double* f0_frames_dev, void* stream);
+
+/* ---- inference --------------------------------------------------------------------------------- */
+
+/* NotePredictor.predict (note_predictor.py:84-135).  mfcc_dev[N][ld] float32, mel_dev[N][mel_n_mels][T].
+ * Outputs (device): probs/mlp_probs/cnn_probs [N][classes], index int64[N], conf float32[N];
+ * mlp_logits_dev / cnn_logits_dev optional (may be NULL). */
+int gat_infer(gat_ctx* ctx, const float* mfcc_dev, int32_t ld, const float* mel_dev, int64_t N, int32_t T,
+              float* probs_dev, float* mlp_probs_dev, float* cnn_probs_dev, int64_t* index_dev, float* conf_dev,
+              float* mlp_logits_dev, float* cnn_logits_dev, void* stream);
+
+/* ---- segmentation ------------------------------------------------------------------------------ */
+
+typedef struct gat_slicer_params {   /* AudioSlicerConfig (config.py:100-107) + sliceNsave arguments */
+    double min_db_threshold;    /* -32.5  apply_db_threshold                  slicing.py:30-39     */
+    float sample_gate;          /* smallest float32 |y| kept by that gate, computed by the caller      */
+    int32_t rms_hop;            /* 512    apply_rms_threshold hop             slicing.py:78         */
+    int32_t p20_k;              /* floor((T-1)*0.2f) in float32 (np.percentile, linear)                */
+    float p20_gamma;            /* fractional part, float32                                             */
+    float gate_offset_db;       /* 6.0                                         slicing.py:63         */
+    int32_t onset_hop;          /* 512 (detect_onsets is called without hop)   slicing.py:151        */
+    int32_t pre_max, post_max, pre_avg, post_avg, wait;  /* librosa onset_detect defaults, ceil-ed     */
+    float delta;                /* 0.07f                                                                */
+    int64_t min_sep_samples;    /* int(MIN_SEP * sr)                           slicing.py:114        */
+    int64_t attack_skip;        /* int(ATTACK_SKIP_SEC * sr)                   slicing.py:127        */
+    int64_t clip_len;           /* int(length_sec * sr)                        slicing.py:126        */
+    float min_slice_rms_db;     /* -37.0                                        slicing.py:96-100     */
+} gat_slicer_params;
+
+/* AudioSlicer.sliceNsave minus file I/O (slicing.py:147-165): y_dev[L] float32 mono at the target rate.
+ * Outputs (device): onsets_dev int64[max_onsets], n_onsets_dev int32[1],
+ *                   clips_dev float32[max_onsets][clip_len] (kept clips, compacted, zero padded),
+ *                   clip_table_dev int64[max_onsets][3] = (onset index, start, end), n_clips_dev int32[1].
+ * Optional diagnostics (NULL to skip): rms_db_dev float32[T] (median-filtered), env_dev float64[T]
+ * (normalised onset envelope), frames_dev int64[max_onsets] (backtracked peak frames), n_frames_dev int32[1]. */
+int gat_segment(gat_ctx* ctx, const float* y_dev, int64_t L, const gat_slicer_params* sp, int32_t max_onsets,
+                int64_t* onsets_dev, int32_t* n_onsets_dev, float* clips_dev, int64_t* clip_table_dev,
+                int32_t* n_clips_dev, float* rms_db_dev, double* env_dev, int64_t* frames_dev,
+                int32_t* n_frames_dev, void* stream);
+
+/* ---- end to end --------------------------------------------------------------------------------- */
+
+#define GAT_FLAG_YIN_ON_NORMALIZED 1   /* transcribe_note path (features.py:473)                    */
+#define GAT_FLAG_APPLY_SCALER      2   /* transcribe(file) path (features.py:145-146)               */
+#define GAT_FLAG_SKIP_MLP          4   /* BASELINE config 2: mel-spectrogram + CNN only              */
+
+/* Transcriber.transcribe_note batched over N equal-length clips already on the device
+ * (transcribe.py:147-199 steps 1-2).  With GAT_FLAG_SKIP_MLP probs == cnn_probs. Optional outputs may be NULL. */
+int gat_transcribe_clips(gat_ctx* ctx, const float* audio_dev, int64_t N, int64_t n, int32_t flags,
+                         float* probs_dev, float* mlp_probs_dev, float* cnn_probs_dev, int64_t* index_dev,
+                         float* conf_dev, float* mfcc_dev /* [N][n_mfcc+1] */, float* mel_dev, double* yin_hz_dev,
+                         void* stream);
+
+/* Same, HOST buffers in and out: copies the clips to the device in chunks (double-buffered against the
+ * kernels), runs gat_transcribe_clips per chunk and copies index / conf / probs back.  Blocks until done.
+ * audio_host should be pinned for the copies to overlap.  probs_host may be NULL. */
+int gat_transcribe_clips_host(gat_ctx* ctx, const float* audio_host, int64_t N, int64_t n, int32_t flags,
+                              int64_t* index_host, float* conf_host, float* probs_host);
+
+/* Number of kernels launched through this ctx so far (bench.py's gpu_launches). */
+int64_t gat_launch_count(const gat_ctx* ctx);
+/* classes of the loaded models, frames of the mel image for n samples. */
+int32_t gat_num_classes(const gat_ctx* ctx);
+int32_t gat_mel_frames(const gat_ctx* ctx, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAT_H_ */
