@@ -95,7 +95,20 @@ int build_sparse_fb(SparseFbDev& out, const float* dense, int n_mels, int n_freq
 
 }  // namespace
 
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+
+// kernels launched through a function pointer are reported under a readable name
+static const char* g_kernel_alias = nullptr;
+static inline const char* kernel_name(const char* expr) {
+    const char* n = g_kernel_alias ? g_kernel_alias : expr;
+    g_kernel_alias = nullptr;
+    return n;
+}
+#define KNAME(s) (g_kernel_alias = (s))
+
 struct gat_ctx {
+    bool profiling = false;
+    std::vector<ProfRec> prof;
     int device = 0;
     int num_sms = 1;
     gat_config cfg{};
@@ -126,12 +139,58 @@ extern "C" int64_t gat_launch_count(const gat_ctx* ctx) { return ctx ? ctx->laun
 extern "C" int32_t gat_num_classes(const gat_ctx* ctx) { return ctx ? (ctx->classes ? ctx->classes : ctx->mlp_dims[ctx->mlp_n_linear]) : 0; }
 extern "C" int32_t gat_mel_frames(const gat_ctx* ctx, int64_t n) { return ctx ? (int32_t)(1 + n / ctx->cfg.mel_hop) : 0; }
 
-#define LAUNCH(ctx, kernel, grid, block, smem, stream, ...)              \
-    do {                                                                 \
-        GAT_LAUNCH(kernel, grid, block, smem, (cudaStream_t)(stream), __VA_ARGS__); \
-        ++(ctx)->launches;                                               \
-        GAT_CUDA(cudaGetLastError());                                    \
+// Every kernel goes through LAUNCH: it counts launches (bench.py's gpu_launches) and, when profiling is
+// switched on with gat_profile_begin, brackets the launch with CUDA events on the launching stream.
+#define LAUNCH(ctx, kernel, grid, block, smem, stream, ...)                                   \
+    do {                                                                                      \
+        cudaEvent_t pe0_ = nullptr, pe1_ = nullptr;                                           \
+        if ((ctx)->profiling) {                                                               \
+            GAT_CUDA(cudaEventCreate(&pe0_)); GAT_CUDA(cudaEventCreate(&pe1_));               \
+            GAT_CUDA(cudaEventRecord(pe0_, (cudaStream_t)(stream)));                          \
+        }                                                                                     \
+        GAT_LAUNCH(kernel, grid, block, smem, (cudaStream_t)(stream), __VA_ARGS__);           \
+        ++(ctx)->launches;                                                                    \
+        GAT_CUDA(cudaGetLastError());                                                         \
+        if ((ctx)->profiling) {                                                               \
+            GAT_CUDA(cudaEventRecord(pe1_, (cudaStream_t)(stream)));                          \
+            (ctx)->prof.push_back(ProfRec{kernel_name(#kernel), pe0_, pe1_});                              \
+        }                                                                                     \
     } while (0)
+
+extern "C" int gat_profile_begin(gat_ctx* c) {
+    if (!c) return fail("gat_profile_begin: null ctx");
+    c->profiling = true;
+    return 0;
+}
+
+// Stops profiling, waits for the recorded launches and writes lines "name launches total_ms\n" into buf.
+extern "C" int gat_profile_end(gat_ctx* c, char* buf, int64_t cap) {
+    if (!c || !buf || cap < 1) return fail("gat_profile_end: bad argument");
+    c->profiling = false;
+    std::vector<std::string> names; std::vector<double> ms; std::vector<long long> cnt;
+    for (ProfRec& r : c->prof) {
+        float t = 0.0f;
+#ifndef GAT_CPU_EMU
+        GAT_CUDA(cudaEventSynchronize(r.e1));
+        GAT_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+#endif
+        cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+        size_t i = 0;
+        for (; i < names.size(); ++i) if (names[i] == r.name) break;
+        if (i == names.size()) { names.push_back(r.name); ms.push_back(0.0); cnt.push_back(0); }
+        ms[i] += t; cnt[i] += 1;
+    }
+    c->prof.clear();
+    std::string out;
+    for (size_t i = 0; i < names.size(); ++i) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s %lld %.6f\n", names[i].c_str(), cnt[i], ms[i]);
+        out += line;
+    }
+    if ((int64_t)out.size() + 1 > cap) return fail("gat_profile_end: buffer too small");
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return 0;
+}
 
 extern "C" int gat_ctx_create(const gat_config* cfg, int device, gat_ctx** out) {
     if (!cfg || !out) return fail("gat_ctx_create: null argument");
@@ -277,6 +336,7 @@ int launch_stft_mel(gat_ctx* c, StftMelParams<T> p, void* stream) {
     GAT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long work = (long long)p.N * p.chunks_per_clip;
     const unsigned grid = (unsigned)(work < c->num_sms ? work : c->num_sms);
+    KNAME(sizeof(T) == 8 ? "stft_mel_f64_spec" : (kOut == kOutImage ? "stft_mel_f32_image" : "stft_mel_f32_spec"));
     LAUNCH(c, kfn, grid, kThreads, smem, stream, p);
     return 0;
 }
@@ -321,6 +381,7 @@ int launch_yin(gat_ctx* c, const YinParams& p, void* stream) {
     const long long work = (long long)p.N * p.T;
     const long long ctas = (work + threads / 32 - 1) / (threads / 32);
     const unsigned grid = (unsigned)(ctas < c->num_sms ? ctas : c->num_sms);
+    KNAME("yin_kernel");
     LAUNCH(c, kfn, grid, threads, smem, stream, p);
     return 0;
 }
@@ -415,9 +476,11 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
         LAUNCH(c, conv1_pool_kernel, (unsigned)(nc * ceil_div(H1 * W1, 256)), 256, 0, stream, p1);
         ConvParams p2{c->act1.as<float>(), nc, H1, W1, c->conv_w[1].as<float>(), c->conv_b[1].as<float>(), c->act2.as<float>(), 1, 0.01f};
         auto k2 = conv3x3_pool_kernel<32, 64>;
+        KNAME("conv2_3x3_pool_32_64");
         LAUNCH(c, k2, (unsigned)(nc * ceil_div(H2 * W2, 32)), 256, 0, stream, p2);
         ConvParams p3{c->act2.as<float>(), nc, H2, W2, c->conv_w[2].as<float>(), c->conv_b[2].as<float>(), c->act3.as<float>(), 0, 0.01f};
         auto k3 = conv3x3_pool_kernel<64, 128>;
+        KNAME("conv3_3x3_pool_64_128");
         LAUNCH(c, k3, (unsigned)(nc * ceil_div(H3 * W3, 16)), 256, 0, stream, p3);
         HeadParams ph{c->act3.as<float>(), nc, H3, W3, 128, c->fc1_w.as<float>(), c->fc1_b.as<float>(), c->hidden,
                       c->fc2_w.as<float>(), c->fc2_b.as<float>(), c->classes, 0.01f,

@@ -91,6 +91,19 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.gat_launch_count(self._ctx))
 
+    def profile_begin(self):
+        self.lib.check(self.lib.gat_profile_begin(self._ctx))
+
+    def profile_end(self) -> dict:
+        """{kernel name: (launches, total milliseconds)} for everything launched since profile_begin."""
+        buf = C.create_string_buffer(1 << 16)
+        self.lib.check(self.lib.gat_profile_end(self._ctx, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.rsplit(" ", 2)
+            out[name] = (int(cnt), float(ms))
+        return out
+
     def mel_frames(self, n: int) -> int:
         return 1 + n // self.hop
 

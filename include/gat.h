@@ -152,6 +152,11 @@ int gat_transcribe_clips(gat_ctx* ctx, const float* audio_dev, int64_t N, int64_
 int gat_transcribe_clips_host(gat_ctx* ctx, const float* audio_host, int64_t N, int64_t n, int32_t flags,
                               int64_t* index_host, float* conf_host, float* probs_host);
 
+/* Per-kernel timing with CUDA events on the launching stream (bench.py's roofline figures).
+ * gat_profile_end writes one line per kernel: "<kernel> <launches> <total ms>\n". */
+int gat_profile_begin(gat_ctx* ctx);
+int gat_profile_end(gat_ctx* ctx, char* buf, int64_t cap);
+
 /* Number of kernels launched through this ctx so far (bench.py's gpu_launches). */
 int64_t gat_launch_count(const gat_ctx* ctx);
 /* classes of the loaded models, frames of the mel image for n samples. */

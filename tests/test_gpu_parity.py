@@ -1,0 +1,234 @@
+"""CUDA path vs the CPU oracle and the committed golden vectors (run with -m gpu on a B200).
+
+Everything goes through the C ABI (libgat.so) via the package's ctypes binding; the oracle (oracle/port.py)
+is only the checker.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import CKPT, golden_audio
+from tolerances import ENV_ABS, PROB_ABS, YIN_CENTS, cents, mel_ok, mel_ok_degenerate, mfcc_ok
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tr22():
+    from guitar_audio_transcriber_ai_b200 import Transcriber
+    return Transcriber("mlp_synth_sr22050.ckpt", "cnn_synth_sr22050.ckpt", CKPT, CKPT, device="cuda:0")
+
+
+@pytest.fixture(scope="module")
+def tr11():
+    from guitar_audio_transcriber_ai_b200 import Transcriber
+    return Transcriber("mlp_v1.0.0.ckpt", "cnn_synth_sr11025.ckpt", CKPT, CKPT, device="cuda:0")
+
+
+def _by_duration(g):
+    groups = {}
+    for k, d in enumerate(g["durations"]):
+        groups.setdefault(float(d), []).append(k)
+    return groups
+
+
+def test_extension_is_the_cuda_build(tr22):
+    from guitar_audio_transcriber_ai_b200 import _lib
+    assert _lib.load().path.name == "libgat.so"
+    assert not getattr(_lib.load(), "_host_emulation", False)
+    assert tr22.engine.device.type == "cuda"
+
+
+@pytest.mark.parametrize("which", ["22050", "11025"])
+def test_features_match_golden(which, tr22, tr11, golden_clips_22050, golden_clips_11025):
+    tr, g = (tr22, golden_clips_22050) if which == "22050" else (tr11, golden_clips_11025)
+    sr = int(g["sr"])
+    for dur, ks in _by_duration(g).items():
+        clips = np.stack([golden_audio(g, k) for k in ks])
+        mel = tr.engine.melspec_db(clips).cpu().numpy()
+        feats, hz = tr.engine.mfcc_features(clips, yin_on_normalized=True)
+        feats, hz = feats.cpu().numpy(), hz.cpu().numpy()
+        for i, k in enumerate(ks):
+            assert mel[i].shape == g[f"mel_{k}"][0].shape
+            assert mel_ok(mel[i], g[f"mel_{k}"][0]), (which, k, np.abs(mel[i] - g[f"mel_{k}"][0]).max())
+            ref = g[f"mfcc_{k}"][0]
+            assert mfcc_ok(feats[i, :64], ref[:64]), (which, k, np.abs(feats[i, :64] - ref[:64]).max())
+            assert abs(feats[i, 64] - ref[64]) <= 2e-6, (which, k)
+            assert cents(hz[i], g[f"yin_hz_{k}"]) <= YIN_CENTS, (which, k, hz[i], g[f"yin_hz_{k}"])
+
+
+def test_yin_frames_and_notes(tr22, golden_clips_22050):
+    from guitar_audio_transcriber_ai_b200 import YinDsp
+    g = golden_clips_22050
+    yin = YinDsp(device="cuda:0")
+    for dur, ks in _by_duration(g).items():
+        clips = np.stack([golden_audio(g, k) for k in ks])
+        hz, f0 = tr22.engine.yin(clips, normalize=False)
+        f0 = f0.cpu().numpy()
+        for i, k in enumerate(ks):
+            ref = g[f"yin_f0_{k}"]
+            assert f0[i].shape == ref.shape
+            assert np.median(cents(f0[i], ref)) <= 0.01
+            assert np.max(cents(f0[i], ref)) <= 0.5, (k, np.max(cents(f0[i], ref)))
+            p, info = yin.estimate_pitch(clips[i], 22050)
+            assert info["midi"] == int(g[f"yin_midi_{k}"]) and info["note_name"] == str(g[f"yin_note_{k}"])
+
+
+@pytest.mark.parametrize("which", ["22050", "11025"])
+def test_predict_from_golden_features(which, tr22, tr11, golden_clips_22050, golden_clips_11025):
+    """NotePredictor.predict on the reference's own features: isolates the CNN/MLP/ensemble kernels."""
+    tr, g = (tr22, golden_clips_22050) if which == "22050" else (tr11, golden_clips_11025)
+    for dur, ks in _by_duration(g).items():
+        mf = np.concatenate([g[f"mfcc_{k}"] for k in ks])
+        ms = np.concatenate([g[f"mel_{k}"] for k in ks])
+        res = tr.predictor.predict(mf, ms)
+        for i, k in enumerate(ks):
+            assert int(res["indices"][i]) == int(g[f"index_{k}"][0])
+            assert str(res["labels"][i]) == str(g[f"label_{k}"][0])
+            assert np.abs(res["probs"][i] - g[f"probs_{k}"][0]).max() <= PROB_ABS
+            assert np.abs(res["per_model_probs"]["mlp"][i] - g[f"mlp_probs_{k}"][0]).max() <= PROB_ABS
+            assert np.abs(res["per_model_probs"]["cnn"][i] - g[f"cnn_probs_{k}"][0]).max() <= PROB_ABS
+            assert abs(float(res["confidences"][i]) - float(g[f"conf_{k}"][0])) <= PROB_ABS
+
+
+@pytest.mark.parametrize("which", ["22050", "11025"])
+def test_transcribe_note_labels_exact(which, tr22, tr11, golden_clips_22050, golden_clips_11025):
+    tr, g = (tr22, golden_clips_22050) if which == "22050" else (tr11, golden_clips_11025)
+    sr = int(g["sr"])
+    for k in range(len(g["seeds"])):
+        res = tr.transcribe_note(golden_audio(g, k), clip_duration=float(g["durations"][k]), sr_in=sr)
+        assert set(res) == {"indices", "labels", "confidences", "probs", "per_model_probs"}
+        assert str(res["labels"][0]) == str(g[f"label_{k}"][0]), (which, k)
+        assert int(res["indices"][0]) == int(g[f"index_{k}"][0])
+        assert np.abs(res["probs"] - g[f"probs_{k}"]).max() <= 5e-5, (which, k, np.abs(res["probs"] - g[f"probs_{k}"]).max())
+        assert res["indices"].dtype == np.int64 and res["probs"].dtype == np.float32
+
+
+def test_segmentation_exact(tr22, golden_phrases):
+    from guitar_audio_transcriber_ai_b200 import synth
+    g = golden_phrases
+    for k, seed in enumerate(g["seeds"]):
+        y, _, _ = synth.phrase(int(seed), sr=22050)
+        r = tr22.engine.segment(y, 0.5, diagnostics=True)
+        assert r["onsets"].cpu().numpy().tolist() == g[f"onsets_{k}"].tolist()
+        assert r["frames"].cpu().numpy().tolist() == g[f"frames_bt_{k}"].tolist()
+        assert np.array_equal(r["table"].cpu().numpy(), g[f"table_{k}"])
+        env = g[f"onset_env_{k}"]
+        en = env - env.min()
+        en = en / (en.max() + np.finfo(np.float64).tiny)
+        assert np.abs(r["env"].cpu().numpy() - en).max() <= ENV_ABS
+        assert np.abs(r["rms_db"].cpu().numpy() - g[f"rms_db_{k}"]).max() <= 5e-5
+
+
+def test_transcribe_audio_matches_reference_pipeline(tr22, golden_phrases):
+    from guitar_audio_transcriber_ai_b200 import synth
+    g = golden_phrases
+    for k, seed in enumerate(g["seeds"]):
+        y, _, _ = synth.phrase(int(seed), sr=22050)
+        res = tr22.transcribe_audio(y, 22050, 0.5)
+        assert [str(s) for s in res["labels"]] == [str(s) for s in g[f"labels_{k}"]]
+        assert res["indices"].tolist() == g[f"indices_{k}"].tolist()
+        assert res["onsets"] == g[f"onsets_{k}"].tolist()
+        assert np.array_equal(res["slice_table"], g[f"table_{k}"])
+        assert np.abs(res["probs"] - g[f"probs_{k}"]).max() <= 5e-5
+        hz = np.array([d[0] for d in res["dsp_info"]])
+        assert np.max(cents(hz, g[f"yin_hz_{k}"])) <= YIN_CENTS
+
+
+def test_live_oracle_on_fresh_inputs(tr22):
+    """Not only the committed vectors: new seeds, CUDA vs oracle/port.py run right here on the host."""
+    import port
+    from guitar_audio_transcriber_ai_b200 import synth
+    from guitar_audio_transcriber_ai_b200.checkpoint import load_checkpoint
+    mlp_ck, cnn_ck = load_checkpoint(CKPT / "mlp_synth_sr22050.ckpt"), load_checkpoint(CKPT / "cnn_synth_sr22050.ckpt")
+    clips, _ = synth.clip_batch(24, 1.0, 22050, seed0=5000)
+    got = tr22.transcribe_notes(clips, 1.0, 22050)
+    for i in range(len(clips)):
+        want = port.transcribe_note(mlp_ck, cnn_ck, clips[i], 1.0, 22050)
+        assert str(got["labels"][i]) == str(want["labels"][0])
+        assert np.abs(got["probs"][i] - want["probs"][0]).max() <= 5e-5
+
+
+def test_edge_cases_against_oracle(tr22):
+    import port
+    from guitar_audio_transcriber_ai_b200 import synth
+    eng = tr22.engine
+    sr = 22050
+    silent = np.zeros(11025, np.float32)
+    dc = np.full(11025, 0.25, np.float32)
+    click = np.zeros(11025, np.float32); click[5000] = 1.0
+    short = synth.note(330.0, 0.2, sr, 9)        # transcribe_note zero-pads it to 0.5 s
+    long_ = synth.note(196.0, 0.9, sr, 10)       # ... and truncates this one
+    for name, a in (("silent", silent), ("dc", dc), ("click", click)):
+        mel = eng.melspec_db(a[None]).cpu().numpy()[0]
+        ref = port.melspec_image(a, sr).numpy()
+        assert np.all(np.isfinite(mel)) and mel_ok_degenerate(mel, ref), name
+        hz, _ = eng.yin(a[None])
+        ref_hz, _ = port.yin_estimate_pitch(a, sr)
+        assert cents(hz.cpu().numpy()[0], ref_hz) <= YIN_CENTS, (name, hz, ref_hz)
+    from guitar_audio_transcriber_ai_b200.checkpoint import load_checkpoint
+    mlp_ck, cnn_ck = load_checkpoint(CKPT / "mlp_synth_sr22050.ckpt"), load_checkpoint(CKPT / "cnn_synth_sr22050.ckpt")
+    for a in (short, long_):
+        got = tr22.transcribe_note(a, 0.5, sr)
+        want = port.transcribe_note(mlp_ck, cnn_ck, a, 0.5, sr)
+        assert str(got["labels"][0]) == str(want["labels"][0])
+        assert np.abs(got["probs"] - want["probs"]).max() <= 5e-5
+
+
+def test_full_size_properties(tr22):
+    """BASELINE config 2 at full size (4096 one-second clips): properties that need no oracle."""
+    from guitar_audio_transcriber_ai_b200 import synth
+    eng = tr22.engine
+    base, _ = synth.clip_batch(64, 1.0, 22050, seed0=9000)
+    reps = 4096 // 64
+    gains = (0.25 + 0.5 * np.arange(reps, dtype=np.float32) / reps)
+    big = torch.from_numpy(np.concatenate([base * g for g in gains])).cuda()
+    out1 = eng.transcribe_clips(big, skip_mlp=True, return_features=True)
+    out2 = eng.transcribe_clips(big, skip_mlp=True, return_features=True)
+    torch.cuda.synchronize()
+    # idempotent / deterministic
+    assert torch.equal(out1["indices"], out2["indices"]) and torch.equal(out1["probs"], out2["probs"])
+    assert torch.equal(out1["mel"], out2["mel"])
+    # batch independence: a clip's result does not depend on its neighbours or its position
+    solo = eng.transcribe_clips(big[1000:1003].contiguous(), skip_mlp=True, return_features=True)
+    assert torch.equal(solo["mel"], out1["mel"][1000:1003]) and torch.equal(solo["probs"], out1["probs"][1000:1003])
+    # volume normalisation makes the features gain-invariant (up to float32 rounding of y/c): same labels
+    idx = out1["indices"].view(reps, 64)
+    assert torch.equal(idx, idx[0:1].expand_as(idx))
+    mel = out1["mel"].view(reps, 64, -1)
+    assert float((mel - mel[0:1]).abs().max()) < 2e-2
+    assert torch.all(torch.isfinite(out1["probs"])) and float((out1["probs"].sum(1) - 1).abs().max()) < 1e-5
+    # and the first 64 agree with the CPU oracle
+    import port
+    from guitar_audio_transcriber_ai_b200.checkpoint import load_checkpoint
+    cnn_ck = load_checkpoint(CKPT / "cnn_synth_sr22050.ckpt")
+    with torch.inference_mode():
+        imgs = torch.stack([port.melspec_image(base[i] * gains[0], 22050) for i in range(16)])
+        probs = torch.softmax(port.cnn_forward(cnn_ck["model"], imgs), -1).numpy()
+    assert np.abs(out1["probs"][:16].cpu().numpy() - probs).max() <= 5e-5
+    assert out1["indices"][:16].cpu().numpy().tolist() == probs.argmax(1).tolist()
+
+
+def test_host_buffer_entry_point(tr22):
+    from guitar_audio_transcriber_ai_b200 import synth
+    clips, _ = synth.clip_batch(700, 0.5, 22050, seed0=7000)   # > one 512-clip chunk: exercises the double buffer
+    pinned = torch.from_numpy(clips).pin_memory()
+    dev = tr22.engine.transcribe_clips(torch.from_numpy(clips).cuda(), yin_on_normalized=True)
+    host = tr22.engine.transcribe_clips_host(pinned, yin_on_normalized=True)
+    assert host["indices"].tolist() == dev["indices"].cpu().numpy().tolist()
+    assert np.array_equal(host["probs"], dev["probs"].cpu().numpy())
+
+
+def test_error_behaviour(tr22):
+    from guitar_audio_transcriber_ai_b200 import Transcriber
+    from guitar_audio_transcriber_ai_b200.engine import Engine
+    with pytest.raises(FileNotFoundError):
+        Transcriber("nope.ckpt", "cnn_synth_sr22050.ckpt", CKPT, CKPT, device="cuda:0")
+    with pytest.raises(ValueError):
+        Engine(22050, {"N_MELS": 64, "N_FFT": 1000, "HOP_LENGTH": 256}, device="cuda:0")
+    with pytest.raises(ValueError):
+        tr22.predictor.predict(None, None)
+    with pytest.raises(UnboundLocalError):
+        tr22.predictor.predict(np.zeros((1, 65), np.float32), None)
+    with pytest.raises(ValueError):
+        tr22.engine.melspec_db(np.zeros((1, 512), np.float32))     # too short for reflect padding
