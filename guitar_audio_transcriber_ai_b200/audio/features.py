@@ -42,8 +42,8 @@ class MelFeatureBuilder:
 
     # ---- reference API
     def extract_inference_features(self, audio_loader, mfcc_config=None, melspec_config=None, scaler=None):
-        """features.py:130-158: (mfcc [N, 65] - float64 when a scaler is applied, as sklearn returns -,
-        melspec torch.Tensor [N, 1, n_mels, T])."""
+        """features.py:130-158: (mfcc float32 [N, 65] - sklearn's StandardScaler keeps float32 input in
+        float32 -, melspec torch.Tensor [N, 1, n_mels, T])."""
         if mfcc_config is None:
             mfcc_config = asdict(MFCCConfig())
         if melspec_config is None:
@@ -58,10 +58,7 @@ class MelFeatureBuilder:
         feats, _ = eng.mfcc_features(dev, mfcc_config["NORMALIZE_AUDIO_VOLUME"], mfcc_config["ADD_PITCH_FEATURES"],
                                      yin_on_normalized=False, apply_scaler=bool(scaler))
         mel = eng.melspec_db(dev, melspec_config["NORMALIZE_AUDIO_VOLUME"])
-        mfcc_features = feats.cpu().numpy()
-        if scaler:
-            mfcc_features = mfcc_features.astype(np.float64)
-        return mfcc_features, mel.cpu()
+        return feats.cpu().numpy(), mel.cpu()
 
     def extract_inference_features_from_audio(self, audio, target_sr=TARGET_SR, mfcc_config=None, melspec_config=None,
                                               scaler=None, melspec_to_db=True):

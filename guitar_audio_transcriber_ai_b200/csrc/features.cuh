@@ -253,13 +253,17 @@ __global__ void mfcc_finish_kernel(MfccFinishParams p) {
     }
 }
 
-// sklearn StandardScaler.transform (audio/features.py:145-146): (x - mean)/scale in float64, cast to f32.
+// sklearn StandardScaler.transform on the float32 feature matrix (audio/features.py:145-146).  sklearn keeps
+// float32 input in float32 and casts mean_/scale_ to it (``X -= xp.astype(self.mean_, X.dtype)``), so the
+// result is fl32(fl32(x - fl32(mean)) / fl32(scale)).  (Older sklearn relied on numpy's mixed in-place
+// rule, fl32(fl32(double(x) - mean) / scale); the two differ by at most one float32 ulp.)
 __global__ void standard_scale_kernel(float* __restrict__ x, int N, int F, int ld,
                                       const double* __restrict__ mean, const double* __restrict__ scale) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N * F) return;
     const int r = i / F, c = i - r * F;
-    x[(long long)r * ld + c] = (float)(((double)x[(long long)r * ld + c] - mean[c]) / scale[c]);
+    const float v = x[(long long)r * ld + c];
+    x[(long long)r * ld + c] = __fdiv_rn(__fsub_rn(v, (float)mean[c]), (float)scale[c]);
 }
 
 }  // namespace gat

@@ -151,9 +151,10 @@ extern "C" int32_t gat_mel_frames(const gat_ctx* ctx, int64_t n) { return ctx ? 
         GAT_LAUNCH(kernel, grid, block, smem, (cudaStream_t)(stream), __VA_ARGS__);           \
         ++(ctx)->launches;                                                                    \
         GAT_CUDA(cudaGetLastError());                                                         \
+        const char* kn_ = kernel_name(#kernel);                                               \
         if ((ctx)->profiling) {                                                               \
             GAT_CUDA(cudaEventRecord(pe1_, (cudaStream_t)(stream)));                          \
-            (ctx)->prof.push_back(ProfRec{kernel_name(#kernel), pe0_, pe1_});                              \
+            (ctx)->prof.push_back(ProfRec{kn_, pe0_, pe1_});                                  \
         }                                                                                     \
     } while (0)
 
@@ -459,7 +460,7 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
     if (H3 < 1 || W3 < 1) return fail("infer: mel image %dx%d too small for three 2x2 pools", H0, W0);
     const long long chunk = N < kCnnChunk ? N : kCnnChunk;
     const size_t a1 = (size_t)chunk * (H1 + 2) * (W1 + 2) * 32, a2 = (size_t)chunk * (H2 + 2) * (W2 + 2) * 64,
-                 a3 = (size_t)chunk * H3 * W3 * 128;
+                 a3 = (size_t)N * H3 * W3 * 128;     // act3 is kept for all clips: the head runs once over the batch
     const bool fresh = c->act1.cap < a1 * 4 || c->act2.cap < a2 * 4 || c->act_shape[0] != chunk || c->act_shape[1] != H0 || c->act_shape[2] != W0;
     if (c->act1.ensure(a1 * 4) || c->act2.ensure(a2 * 4) || c->act3.ensure(a3 * 4)) return 1;
     if (fresh) {   // zero borders once per geometry; the kernels only ever write interiors
@@ -478,15 +479,15 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
         auto k2 = conv3x3_pool_kernel<32, 64>;
         KNAME("conv2_3x3_pool_32_64");
         LAUNCH(c, k2, (unsigned)(nc * ceil_div(H2 * W2, 32)), 256, 0, stream, p2);
-        ConvParams p3{c->act2.as<float>(), nc, H2, W2, c->conv_w[2].as<float>(), c->conv_b[2].as<float>(), c->act3.as<float>(), 0, 0.01f};
+        ConvParams p3{c->act2.as<float>(), nc, H2, W2, c->conv_w[2].as<float>(), c->conv_b[2].as<float>(),
+                      c->act3.as<float>() + (size_t)c0 * H3 * W3 * 128, 0, 0.01f};
         auto k3 = conv3x3_pool_kernel<64, 128>;
         KNAME("conv3_3x3_pool_64_128");
         LAUNCH(c, k3, (unsigned)(nc * ceil_div(H3 * W3, 16)), 256, 0, stream, p3);
-        HeadParams ph{c->act3.as<float>(), nc, H3, W3, 128, c->fc1_w.as<float>(), c->fc1_b.as<float>(), c->hidden,
-                      c->fc2_w.as<float>(), c->fc2_b.as<float>(), c->classes, 0.01f,
-                      logits + c0 * c->classes, cnn_probs + c0 * c->classes};
-        LAUNCH(c, cnn_head_kernel, (unsigned)ceil_div(nc, kHeadClips), 256, head_smem, stream, ph);
     }
+    HeadParams ph{c->act3.as<float>(), (int)N, H3, W3, 128, c->fc1_w.as<float>(), c->fc1_b.as<float>(), c->hidden,
+                  c->fc2_w.as<float>(), c->fc2_b.as<float>(), c->classes, 0.01f, logits, cnn_probs};
+    LAUNCH(c, cnn_head_kernel, (unsigned)ceil_div((int)N, kHeadClips), 256, head_smem, stream, ph);
     return 0;
 }
 

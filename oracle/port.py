@@ -112,7 +112,8 @@ def extract_inference_features_from_audio(audio, target_sr=TARGET_SR, mfcc_confi
 def extract_inference_features(wavs, target_sr, mfcc_config=None, melspec_config=None, scaler=None):
     """audio/features.py:130-158 over already-loaded, equal-length clips (the loader's pad_to_max=True).
 
-    Here the scaler IS applied (:145-146) and the result becomes float64 (sklearn)."""
+    Here the scaler IS applied (:145-146); sklearn keeps the float32 matrix in float32 (mean_/scale_ are
+    cast to it), so the result is float32."""
     mfcc_config = mfcc_config or MFCC_DEFAULTS
     melspec_config = melspec_config or MELSPEC_DEFAULTS
     X = np.vstack([mfcc_vector(w, target_sr, mfcc_config["N_MFCC"], mfcc_config["NORMALIZE_AUDIO_VOLUME"],

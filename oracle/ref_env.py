@@ -25,9 +25,11 @@ def available() -> bool:
 
 
 def _stub(name: str, **attrs) -> types.ModuleType:
+    import importlib.machinery
     mod = types.ModuleType(name)
     mod.__dict__.update(attrs)
     mod.__path__ = []  # behave like a package so "import a.b" works
+    mod.__spec__ = importlib.machinery.ModuleSpec(name, None)  # other libraries probe find_spec(name)
     sys.modules[name] = mod
     return mod
 

@@ -1,0 +1,54 @@
+"""Kernel LOGIC checked in this GPU-less container: csrc/*.cu(h) compiled for the host against tests/emu/cpu_emu.h
+(one std::thread per CUDA thread) and driven through the same C ABI and Python engine as the CUDA build.
+This validates indexing / FFT decomposition / scans before GPU time is spent; the real parity gate is
+tests/test_gpu_parity.py on the B200."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import CKPT, golden_audio
+from tolerances import ENV_ABS, PROB_ABS, YIN_CENTS, cents, mel_ok, mfcc_ok
+
+
+@pytest.fixture(scope="module")
+def emu_tr():
+    if torch.cuda.is_available():
+        pytest.skip("a real GPU is present: the CUDA build is tested instead")
+    import emu_loader
+    from guitar_audio_transcriber_ai_b200 import _lib
+    saved = (_lib._LIB, _lib.load)
+    emu_loader.install()
+    from guitar_audio_transcriber_ai_b200 import Transcriber
+    tr = Transcriber("mlp_synth_sr22050.ckpt", "cnn_synth_sr22050.ckpt", CKPT, CKPT, device="cpu")
+    yield tr
+    tr.engine.close()
+    _lib._LIB, _lib.load = saved
+    from guitar_audio_transcriber_ai_b200.dsp import yin
+    yin._ENGINES.clear()
+
+
+def test_emu_features_and_labels(emu_tr, golden_clips_22050):
+    g = golden_clips_22050
+    ks = [0, 5, 13]                                                        # two 0.5 s clips and a 1 s clip
+    for k in ks:
+        a = golden_audio(g, k)
+        mel = emu_tr.engine.melspec_db(a[None]).numpy()[0]
+        feats, hz = emu_tr.engine.mfcc_features(a[None], yin_on_normalized=True)
+        assert mel_ok(mel, g[f"mel_{k}"][0]) and mfcc_ok(feats.numpy()[0, :64], g[f"mfcc_{k}"][0, :64])
+        assert cents(hz.numpy()[0], g[f"yin_hz_{k}"]) <= YIN_CENTS
+        res = emu_tr.transcribe_note(a, float(g["durations"][k]), 22050)
+        assert str(res["labels"][0]) == str(g[f"label_{k}"][0])
+        assert np.abs(res["probs"] - g[f"probs_{k}"]).max() <= 5e-5
+
+
+def test_emu_segmentation(emu_tr, golden_phrases):
+    from guitar_audio_transcriber_ai_b200 import synth
+    g = golden_phrases
+    y, _, _ = synth.phrase(int(g["seeds"][1]), sr=22050)
+    r = emu_tr.engine.segment(y, 0.5, diagnostics=True)
+    assert r["onsets"].numpy().tolist() == g["onsets_1"].tolist()
+    assert r["frames"].numpy().tolist() == g["frames_bt_1"].tolist()
+    assert np.array_equal(r["table"].numpy(), g["table_1"])
+    env = g["onset_env_1"]
+    en = (env - env.min()) / ((env - env.min()).max() + np.finfo(np.float64).tiny)
+    assert np.abs(r["env"].numpy() - en).max() <= ENV_ABS

@@ -1,0 +1,96 @@
+"""oracle/port.py (the portable CPU restatement) against the vectors produced by the reference's own files
+(oracle/make_golden.py), and - where /root/reference exists - against those files run live."""
+import numpy as np
+import pytest
+
+from conftest import CKPT, golden_audio
+
+import port
+import ref_env
+from guitar_audio_transcriber_ai_b200.checkpoint import load_checkpoint
+
+
+def _ckpts(sr):
+    mlp = "mlp_synth_sr22050.ckpt" if sr == 22050 else "mlp_v1.0.0.ckpt"
+    return load_checkpoint(CKPT / mlp), load_checkpoint(CKPT / f"cnn_synth_sr{sr}.ckpt")
+
+
+@pytest.mark.parametrize("which", ["22050", "11025"])
+def test_port_reproduces_golden_clips(which, golden_clips_22050, golden_clips_11025):
+    g = golden_clips_22050 if which == "22050" else golden_clips_11025
+    sr = int(g["sr"])
+    mlp_ck, cnn_ck = _ckpts(sr)
+    for k in range(0, len(g["seeds"]), 3):
+        a = golden_audio(g, k)
+        res = port.transcribe_note(mlp_ck, cnn_ck, a, float(g["durations"][k]), sr)
+        mf, ms = port.extract_inference_features_from_audio(a, sr, mlp_ck["config"]["features"]["params"],
+                                                            cnn_ck["config"]["features"]["params"])
+        # generated on this image; another CPU may take other SIMD paths in MKL/pocketfft: tight, not bitwise
+        assert np.abs(ms - g[f"mel_{k}"]).max() <= 2e-3
+        assert np.abs(mf - g[f"mfcc_{k}"]).max() <= 1e-3
+        assert res["labels"][0] == str(g[f"label_{k}"][0]) and int(res["indices"][0]) == int(g[f"index_{k}"][0])
+        assert np.abs(res["probs"] - g[f"probs_{k}"]).max() <= 1e-5
+        hz, info = port.yin_estimate_pitch(a, sr)
+        assert abs(hz - float(g[f"yin_hz_{k}"])) <= 1e-6 * hz and info["note_name"] == str(g[f"yin_note_{k}"])
+
+
+def test_port_reproduces_golden_phrases(golden_phrases):
+    from guitar_audio_transcriber_ai_b200 import synth
+    g = golden_phrases
+    mlp_ck, cnn_ck = _ckpts(22050)
+    for k in (0, 2):
+        y, _, _ = synth.phrase(int(g["seeds"][k]), sr=22050)
+        res = port.transcribe_audio(mlp_ck, cnn_ck, y, 22050, 0.5)
+        assert res["onsets"] == g[f"onsets_{k}"].tolist()
+        assert np.array_equal(res["slice_table"], g[f"table_{k}"])
+        assert [str(s) for s in res["labels"]] == [str(s) for s in g[f"labels_{k}"]]
+        assert np.abs(res["probs"] - g[f"probs_{k}"]).max() <= 1e-5
+
+
+def test_reference_quirks_are_kept(golden_phrases):
+    """Behaviours SURVEY 8(a) lists as parity-relevant."""
+    g = golden_phrases
+    for k in range(len(g["seeds"])):
+        assert len(g[f"table_{k}"]) <= len(g[f"onsets_{k}"]) - 1          # the last onset never yields a clip
+    mlp_ck, cnn_ck = _ckpts(22050)
+    a = np.zeros(11025, np.float32); a[::50] = 0.3
+    mf_mem, _ = port.extract_inference_features_from_audio(a, 22050)
+    X_file, _ = port.extract_inference_features([a], 22050, scaler=mlp_ck["scaler"])
+    assert mf_mem.dtype == np.float32 and X_file.dtype == np.float32      # scaler only on the file path (sklearn keeps f32)
+    assert not np.allclose(mf_mem, X_file)
+    empty, times = port.slice_audio(np.zeros(1000, np.float32), 900, 1500, sr=22050)
+    assert empty.shape == (0,) and not port.is_slice_loud_enough(empty, -37.0)
+    assert port.yin_estimate_pitch(_tone(185.0), 22050)[1]["note_name"] == "F♯3"   # unicode sharp, unlike class labels
+
+
+def _tone(f0):
+    t = np.arange(11025) / 22050
+    return (0.4 * np.sin(2 * np.pi * f0 * t)).astype(np.float32)
+
+
+@pytest.mark.skipif(not ref_env.available(), reason="reference tree not present (GPU box)")
+def test_port_equals_reference_files_live():
+    import contextlib
+    ns = ref_env.install()
+    fb = ns.features.MelFeatureBuilder()
+    mlp_ck, cnn_ck = _ckpts(22050)
+    rng = np.random.default_rng(11)
+    a = (0.3 * np.sin(2 * np.pi * 247.0 * np.arange(11025) / 22050) + 0.01 * rng.standard_normal(11025)).astype(np.float32)
+    with contextlib.redirect_stdout(None):
+        mf, ms = fb.extract_inference_features_from_audio(a, 22050, mlp_ck["config"]["features"]["params"],
+                                                          cnn_ck["config"]["features"]["params"], None)
+        hz, info = ns.yin.YinDsp().estimate_pitch(a, 22050)
+        npred = ns.note_predictor.NotePredictor(device="cpu")
+        npred.load_models(mlp_ck, cnn_ck)
+        ref = npred.predict(mf, ms)
+    pmf, pms = port.extract_inference_features_from_audio(a, 22050, mlp_ck["config"]["features"]["params"],
+                                                          cnn_ck["config"]["features"]["params"])
+    assert np.array_equal(mf, pmf) and np.array_equal(ms, pms)
+    assert (hz, info) == port.yin_estimate_pitch(a, 22050)
+    got = port.predict(mlp_ck, cnn_ck, pmf, pms)
+    assert np.array_equal(ref["probs"], got["probs"]) and ref["labels"] == got["labels"]
+    sl = ns.slicing.AudioSlicer()
+    from guitar_audio_transcriber_ai_b200 import synth
+    y, _, _ = synth.phrase(7)
+    g = sl.apply_rms_threshold(sl.apply_db_threshold(y=y, min_db=-32.5), hop_len=512)
+    assert sl.detect_onsets(y=g, sr=22050, min_sep=0.3) == port.slice_in_memory(y, 22050, 0.5)[0]
