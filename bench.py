@@ -156,9 +156,9 @@ def kernel_table(prof: dict, steps: int, n_clips: int, T: int, peaks: dict):
     work = {   # kernel -> (bound, algorithmic bytes or flops per STEP)
         "clip_scale_kernel": ("hbm", n_clips * (4 * n + 4)),
         "stft_mel_f32_image": ("hbm", n_clips * (4 * n + 4 * 64 * T)),
-        "conv1_pool_kernel": ("hbm", n_clips * (4 * 64 * T + 4 * H1 * W1 * 32)),
-        "conv2_3x3_pool_32_64": ("tensor", n_clips * 2.0 * H1 * W1 * 64 * 32 * 9),
-        "conv3_3x3_pool_64_128": ("tensor", n_clips * 2.0 * H2 * W2 * 128 * 64 * 9),
+        "conv1_pool_planes_kernel": ("hbm", n_clips * (4 * 64 * T + 2 * 4 * H1 * W1 * 32)),
+        "conv2_tc_32_64": ("tensor", n_clips * 2.0 * H1 * W1 * 64 * 32 * 9),
+        "conv3_tc_64_128": ("tensor", n_clips * 2.0 * H2 * W2 * 128 * 64 * 9),
         "cnn_head_kernel": ("tensor", n_clips * 2.0 * (2048 * 256 + 256 * 47)),
         "argmax_kernel": ("hbm", n_clips * (4 * 47 + 12)),
     }

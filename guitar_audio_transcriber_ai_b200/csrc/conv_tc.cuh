@@ -1,0 +1,276 @@
+// conv2 / conv3 of the CNN (training/cnn_trainer.py:52-76: Conv2d 3x3 pad 1 -> BatchNorm -> LeakyReLU ->
+// MaxPool2) as an implicit GEMM on the Blackwell tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM).
+//
+//   D[pixel (M = 128)][c_out (N)] += A[pixel][k] * B[c_out][k],   k = (tap, c_in)
+//
+// * Activations live in HBM as "chunk planes": [clip][c_in/4][padded pixel][4 floats], split into a TF32
+//   `hi` array and an exact fp32 remainder `lo` (x = hi + lo).  With that layout and the no-swizzle K-major
+//   operand format, the rows an MMA reads for tap (ky,kx) are the SAME shared-memory planes addressed
+//   (ky*Wp + kx) * 16 bytes further: im2col costs nothing and every load is a contiguous 1-D bulk (TMA) copy.
+// * 3xTF32: hi*hi + lo*hi + hi*lo accumulate in the FP32 TMEM accumulator, which keeps the logits
+//   float32-faithful (the reference runs the CNN in fp32); measured max error 5e-6 on |x| ~ 7.
+// * One CTA per SM, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2-5 =
+//   epilogue.  A work item is a GROUP of three consecutive 128-pixel tiles covering R whole image rows, so
+//   every 2x2 pooling window is inside the group: the epilogue moves 32 channels at a time TMEM -> registers ->
+//   shared staging, pools, adds the BN-folded bias, applies LeakyReLU and writes the next layer's planes
+//   (already split hi/lo) or the dense NHWC tensor the classifier head reads.
+#pragma once
+#ifndef GAT_CPU_EMU
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace gat {
+
+constexpr int kTcTiles = 3;                       // 128-pixel tiles per group
+constexpr int kTcGroupPix = 128 * kTcTiles;
+constexpr int kTcThreads = 192;
+constexpr int kTcStageStride = 33;                // floats per staged pixel (32 channels + 1 pad)
+
+struct ConvTcParams {
+    const float* in_hi; const float* in_lo;       // [clip][CIN/4][Hp*Wp][4]
+    const float* w;                               // [9 taps][CIN/32][hi|lo][8 chunks][COUT][4]
+    const float* bias;                            // [COUT] (BatchNorm folded)
+    int n_clips, H, W;                            // conv input size without the border; Hp = H+2, Wp = W+2
+    int R;                                        // image rows per group (even, R*Wp <= 384)
+    int groups_per_clip;
+    int out_planes;                               // 1: write next layer's planes (hi/lo); 0: dense NHWC
+    float* out_hi; float* out_lo;
+    float slope;
+};
+
+__host__ __device__ inline int conv_tc_plane_pixels(int Wp) { return kTcGroupPix + 2 * Wp + 2; }
+
+template <int COUT>
+__host__ __device__ inline size_t conv_tc_smem_bytes(int Wp, int nstage) {
+    return (size_t)2 * 8 * conv_tc_plane_pixels(Wp) * 16          // A: hi|lo x 8 chunks x plane
+         + (size_t)nstage * 2 * 8 * COUT * 16                      // weight ring
+         + (size_t)kTcGroupPix * kTcStageStride * 4                // epilogue staging
+         + 256;                                                    // barriers, tmem slot, alignment
+}
+
+template <int CIN, int COUT, int NSTAGE>
+__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) {
+    using namespace tc;
+    constexpr int NKB = CIN / 32;
+    constexpr uint32_t W_STAGE = 2 * 8 * COUT * 16;
+    constexpr uint32_t TMEM_COLS = kTcTiles * COUT <= 256 ? 256 : 512;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int Wp = p.W + 2, Hp = p.H + 2;
+    const int Pg = conv_tc_plane_pixels(Wp);
+    const uint32_t plane = (uint32_t)Pg * 16;
+    unsigned char* a_buf = smem;                                   // [part][chunk][Pg][16 B]
+    unsigned char* w_buf = a_buf + (size_t)2 * 8 * plane;
+    float* staging = reinterpret_cast<float*>(w_buf + (size_t)NSTAGE * W_STAGE);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(staging) + (size_t)kTcGroupPix * kTcStageStride * 4);
+    uint64_t* a_full = bars + 0; uint64_t* a_empty = bars + 1; uint64_t* acc_full = bars + 2; uint64_t* acc_empty = bars + 3;
+    uint64_t* w_full = bars + 4; uint64_t* w_empty = bars + 4 + NSTAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * NSTAGE);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, 1); mbar_init(a_empty, 1); mbar_init(acc_full, 1); mbar_init(acc_empty, 4);
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    fence_before_thread_sync();
+    __syncthreads();
+    fence_after_thread_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    const int n_work = p.n_clips * p.groups_per_clip;
+    const long long plane_pix = (long long)Hp * Wp;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            uint32_t it = 0, use = 0;
+            for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
+                const int clip = work / p.groups_per_clip, gi = work - clip * p.groups_per_clip;
+                const long long q_start = (long long)(gi * p.R) * Wp - 1;      // (y0-1)*Wp - 1 with y0 = 1 + gi*R
+                for (int kb = 0; kb < NKB; ++kb, ++it) {
+                    mbar_wait(a_empty, (it & 1) ^ 1);
+                    mbar_expect_tx(a_full, 16 * plane);
+                    for (int part = 0; part < 2; ++part) {
+                        const float* src = part ? p.in_lo : p.in_hi;
+                        for (int c = 0; c < 8; ++c) {
+                            const long long pl = (long long)clip * (CIN / 4) + kb * 8 + c;
+                            bulk_g2s(a_buf + (size_t)(part * 8 + c) * plane, src + (pl * plane_pix + q_start) * 4, plane, a_full);
+                        }
+                    }
+                    for (int tap = 0; tap < 9; ++tap, ++use) {
+                        const uint32_t st = use % NSTAGE;
+                        mbar_wait(w_empty + st, ((use / NSTAGE) & 1) ^ 1);
+                        mbar_expect_tx(w_full + st, W_STAGE);
+                        bulk_g2s(w_buf + (size_t)st * W_STAGE, p.w + (size_t)(tap * NKB + kb) * (W_STAGE / 4), W_STAGE, w_full + st);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer (single thread)
+        if (lane == 0) {
+            const uint32_t idesc = idesc_tf32(128, COUT);
+            const uint32_t a_hi = smem_u32(a_buf), a_lo = a_hi + 8 * plane;
+            uint32_t it = 0, use = 0, wi = 0;
+            for (int work = blockIdx.x; work < n_work; work += gridDim.x, ++wi) {
+                mbar_wait(acc_empty, (wi & 1) ^ 1);
+                fence_after_thread_sync();
+                for (int kb = 0; kb < NKB; ++kb, ++it) {
+                    mbar_wait(a_full, it & 1);
+                    for (int tap = 0; tap < 9; ++tap, ++use) {
+                        const uint32_t st = use % NSTAGE;
+                        mbar_wait(w_full + st, (use / NSTAGE) & 1);
+                        fence_after_thread_sync();
+                        const uint32_t w_hi = smem_u32(w_buf) + st * W_STAGE, w_lo = w_hi + 8 * COUT * 16;
+                        const uint32_t row_off = (uint32_t)((tap / 3) * Wp + (tap % 3)) * 16;
+#pragma unroll
+                        for (int g = 0; g < kTcTiles; ++g) {
+                            const uint32_t d = tmem + (uint32_t)(g * COUT);
+#pragma unroll
+                            for (int s = 0; s < 4; ++s) {
+                                const uint32_t ao = row_off + (uint32_t)(g * 128) * 16 + (uint32_t)(2 * s) * plane;
+                                const uint32_t bo = (uint32_t)(2 * s) * COUT * 16;
+                                const uint64_t dah = smem_desc_kmajor_noswizzle(a_hi + ao, plane, 128);
+                                const uint64_t dal = smem_desc_kmajor_noswizzle(a_lo + ao, plane, 128);
+                                const uint64_t dbh = smem_desc_kmajor_noswizzle(w_hi + bo, COUT * 16, 128);
+                                const uint64_t dbl = smem_desc_kmajor_noswizzle(w_lo + bo, COUT * 16, 128);
+                                mma_tf32(d, dah, dbh, idesc, (kb | tap | s) != 0 ? 1u : 0u);
+                                mma_tf32(d, dal, dbh, idesc, 1u);
+                                mma_tf32(d, dah, dbl, idesc, 1u);
+                            }
+                        }
+                        mma_commit(w_empty + st);           // weights of this stage are free once those MMAs retire
+                    }
+                    mma_commit(a_empty);                    // ... and so is the activation buffer
+                }
+                mma_commit(acc_full);                       // accumulators of the group are complete
+            }
+        }
+    } else {
+        // ===================================================== epilogue (4 warps = 128 threads)
+        const int quarter = warp & 3;                       // the TMEM lanes this warp may read: 32*quarter ..
+        const int et = (warp - 2) * 32 + lane;
+        const int Hpool = p.H / 2, Wpool = p.W / 2;
+        const int Wp_out = Wpool + 2;
+        const long long Pout = (long long)(Hpool + 2) * Wp_out;
+        uint32_t wi = 0;
+        for (int work = blockIdx.x; work < n_work; work += gridDim.x, ++wi) {
+            const int clip = work / p.groups_per_clip, gi = work - clip * p.groups_per_clip;
+            int prow = Hpool - gi * (p.R / 2);              // pooled rows produced by this group
+            prow = prow < p.R / 2 ? prow : p.R / 2;
+            mbar_wait(acc_full, wi & 1);
+            fence_after_thread_sync();
+            for (int cb = 0; cb < COUT / 32; ++cb) {
+#pragma unroll
+                for (int g = 0; g < kTcTiles; ++g) {
+                    float v[32];
+                    tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * COUT + cb * 32), v);
+                    float* dst = staging + (size_t)(g * 128 + quarter * 32 + lane) * kTcStageStride;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) dst[j] = v[j];
+                }
+                if (cb == COUT / 32 - 1) {                  // TMEM fully drained: the next group's MMAs may start
+                    fence_before_thread_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty);
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int n_items = prow * Wpool * 8;
+                for (int item = et; item < n_items; item += 128) {
+                    const int px = item % Wpool;
+                    const int rest = item / Wpool;
+                    const int r = rest % prow, ch = rest / prow;
+                    const float* s00 = staging + (size_t)(2 * r * Wp + 1 + 2 * px) * kTcStageStride + ch * 4;
+                    const float* s10 = s00 + (size_t)Wp * kTcStageStride;
+                    float o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float m = fmaxf(fmaxf(s00[e], s00[kTcStageStride + e]), fmaxf(s10[e], s10[kTcStageStride + e]));
+                        const float z = m + __ldg(p.bias + cb * 32 + ch * 4 + e);
+                        o[e] = z > 0.0f ? z : z * p.slope;
+                    }
+                    const int Y = gi * (p.R / 2) + r;
+                    if (p.out_planes) {
+                        const long long chunk_out = (long long)clip * (COUT / 4) + cb * 8 + ch;
+                        const long long off = (chunk_out * Pout + (long long)(Y + 1) * Wp_out + px + 1) * 4;
+                        float4 hi = make_float4(tf32_hi(o[0]), tf32_hi(o[1]), tf32_hi(o[2]), tf32_hi(o[3]));
+                        float4 lo = make_float4(o[0] - hi.x, o[1] - hi.y, o[2] - hi.z, o[3] - hi.w);
+                        *reinterpret_cast<float4*>(p.out_hi + off) = hi;
+                        *reinterpret_cast<float4*>(p.out_lo + off) = lo;
+                    } else {
+                        const long long off = (((long long)clip * Hpool + Y) * Wpool + px) * COUT + cb * 32 + ch * 4;
+                        *reinterpret_cast<float4*>(p.out_hi + off) = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+        }
+    }
+    fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// conv1 (C_in = 1, CUDA cores) writing conv2's operand directly: chunk planes, hi/lo split.
+struct Conv1PlanesParams {
+    const float* in; int N, H, W;
+    const float* w; const float* bias;    // [9][32], [32]
+    float* out_hi; float* out_lo;         // [clip][8][(H/2+2)*(W/2+2)][4]
+    float slope;
+};
+
+__global__ void __launch_bounds__(256) conv1_pool_planes_kernel(Conv1PlanesParams p) {
+    __shared__ float ws[9 * 32];
+    __shared__ float bs[32];
+    for (int i = threadIdx.x; i < 9 * 32; i += blockDim.x) ws[i] = p.w[i];
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) bs[i] = p.bias[i];
+    __syncthreads();
+    const int Hq = p.H / 2, Wq = p.W / 2;
+    const int tiles = ceil_div(Hq * Wq, (int)blockDim.x);
+    const int clip = blockIdx.x / tiles;
+    const int q = (blockIdx.x - clip * tiles) * blockDim.x + threadIdx.x;
+    if (q >= Hq * Wq) return;
+    const int py = q / Wq, px = q - py * Wq;
+    const float* img = p.in + (long long)clip * p.H * p.W;
+    float patch[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int y = 2 * py - 1 + a, x = 2 * px - 1 + b;
+            patch[a][b] = (y >= 0 && y < p.H && x >= 0 && x < p.W) ? img[y * p.W + x] : 0.0f;
+        }
+    const long long Pout = (long long)(Hq + 2) * (Wq + 2);
+    const long long pix = (long long)(py + 1) * (Wq + 2) + px + 1;
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = ch * 4 + e;
+            float best = -3.0e38f;
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) acc = fmaf(patch[a + ky][b + kx], ws[(ky * 3 + kx) * 32 + c], acc);
+                    best = fmaxf(best, acc);
+                }
+            const float z = best + bs[c];
+            o[e] = z > 0.0f ? z : z * p.slope;
+        }
+        const long long off = (((long long)clip * 8 + ch) * Pout + pix) * 4;
+        const float4 hi = make_float4(tc::tf32_hi(o[0]), tc::tf32_hi(o[1]), tc::tf32_hi(o[2]), tc::tf32_hi(o[3]));
+        *reinterpret_cast<float4*>(p.out_hi + off) = hi;
+        *reinterpret_cast<float4*>(p.out_lo + off) = make_float4(o[0] - hi.x, o[1] - hi.y, o[2] - hi.z, o[3] - hi.w);
+    }
+}
+
+}  // namespace gat
+#endif  // GAT_CPU_EMU

@@ -8,6 +8,7 @@ using std::min;
 #endif
 
 #include "common.cuh"
+#include "conv_tc.cuh"
 #include "features.cuh"
 #include "fft.cuh"
 #include "infer.cuh"
@@ -119,6 +120,7 @@ struct gat_ctx {
     // models
     DevBuf mlp_params; int mlp_dims[kMlpMaxLayers + 1] = {0}; int mlp_n_linear = 0; int mlp_n_params = 0;
     DevBuf conv_w[3], conv_b[3], fc1_w, fc1_b, fc2_w, fc2_b;
+    DevBuf conv_w_tc[3];   // conv2/conv3 weights in the tensor-core operand layout (hi/lo TF32 split)
     int conv_ch[4] = {0, 0, 0, 0}; int hidden = 0, classes = 0; bool cnn_loaded = false;
     DevBuf scaler_mean, scaler_scale; int scaler_n = 0;
     float w_mlp = 0.2f, w_cnn = 0.8f;
@@ -248,7 +250,7 @@ extern "C" void gat_ctx_destroy(gat_ctx* c) {
     DevBuf* all[] = {&c->tw32, &c->w2_32, &c->tw64, &c->w2_64, &c->win_mel, &c->win_mfcc, &c->win64, &c->dct,
                      &c->fb_mel.start, &c->fb_mel.len, &c->fb_mel.off, &c->fb_mel.w,
                      &c->fb_mfcc.start, &c->fb_mfcc.len, &c->fb_mfcc.off, &c->fb_mfcc.w,
-                     &c->mlp_params, &c->conv_w[0], &c->conv_w[1], &c->conv_w[2], &c->conv_b[0], &c->conv_b[1], &c->conv_b[2],
+                     &c->mlp_params, &c->conv_w_tc[1], &c->conv_w_tc[2], &c->conv_w[0], &c->conv_w[1], &c->conv_w[2], &c->conv_b[0], &c->conv_b[1], &c->conv_b[2],
                      &c->fc1_w, &c->fc1_b, &c->fc2_w, &c->fc2_b, &c->scaler_mean, &c->scaler_scale,
                      &c->clip_scale, &c->spec, &c->spec_max, &c->f0, &c->act1, &c->act2, &c->act3, &c->hz_tmp, &c->logits_cnn, &c->logits_mlp,
                      &c->seg_small, &c->seg_rms, &c->seg_rms_med, &c->seg_gate, &c->seg_env, &c->seg_envn, &c->seg_cand,
@@ -292,6 +294,23 @@ extern "C" int gat_load_cnn(gat_ctx* c, int32_t n_conv, const int32_t* ch, const
         if (upload(c->conv_w[i], conv_w[i], (size_t)9 * ch[i] * ch[i + 1])) return 1;
         if (upload(c->conv_b[i], conv_b[i], (size_t)ch[i + 1])) return 1;
     }
+#ifndef GAT_CPU_EMU
+    for (int i = 1; i < 3; ++i) {   // [tap][c_in/32][hi|lo][8 chunks][c_out][4]: one contiguous blob per (tap, K block)
+        const int cin = ch[i], cout = ch[i + 1], nkb = cin / 32;
+        std::vector<float> t((size_t)9 * nkb * 2 * 8 * cout * 4);
+        for (int tap = 0; tap < 9; ++tap)
+            for (int ci = 0; ci < cin; ++ci)
+                for (int oc = 0; oc < cout; ++oc) {
+                    const float w = conv_w[i][((size_t)tap * cin + ci) * cout + oc];
+                    const float hi = tc::tf32_hi(w);
+                    const size_t base = ((size_t)(tap * nkb + ci / 32) * 2) * 8 * cout * 4;
+                    const size_t idx = ((size_t)((ci % 32) / 4) * cout + oc) * 4 + (ci % 4);
+                    t[base + idx] = hi;
+                    t[base + (size_t)8 * cout * 4 + idx] = w - hi;
+                }
+        if (upload(c->conv_w_tc[i], t.data(), t.size())) return 1;
+    }
+#endif
     if (upload(c->fc1_w, fc1_w, (size_t)ch[3] * 16 * hidden) || upload(c->fc1_b, fc1_b, hidden) ||
         upload(c->fc2_w, fc2_w, (size_t)hidden * classes) || upload(c->fc2_b, fc2_b, classes)) return 1;
     for (int i = 0; i < 4; ++i) c->conv_ch[i] = ch[i];
@@ -451,7 +470,10 @@ extern "C" int gat_yin(gat_ctx* c, const float* audio, int64_t N, int64_t n, int
 // ------------------------------------------------------------------------------------------------- inference
 namespace {
 
-constexpr int kCnnChunk = 256;   // clips per pass: keeps act1/act2/act3 (~90 MB at T=87) inside the 126 MB L2
+#ifdef GAT_CPU_EMU
+// Host-emulation stand-in (tests/emu only): the tcgen05 kernels cannot be emulated, so the emulation build
+// keeps a plain CUDA-core formulation of the same layers to exercise everything around them.
+constexpr int kCnnChunk = 256;
 
 int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, float* cnn_logits, void* stream) {
     if (!c->cnn_loaded) return fail("infer: no CNN loaded (gat_load_cnn)");
@@ -460,36 +482,96 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
     if (H3 < 1 || W3 < 1) return fail("infer: mel image %dx%d too small for three 2x2 pools", H0, W0);
     const long long chunk = N < kCnnChunk ? N : kCnnChunk;
     const size_t a1 = (size_t)chunk * (H1 + 2) * (W1 + 2) * 32, a2 = (size_t)chunk * (H2 + 2) * (W2 + 2) * 64,
-                 a3 = (size_t)N * H3 * W3 * 128;     // act3 is kept for all clips: the head runs once over the batch
+                 a3 = (size_t)N * H3 * W3 * 128;
     const bool fresh = c->act1.cap < a1 * 4 || c->act2.cap < a2 * 4 || c->act_shape[0] != chunk || c->act_shape[1] != H0 || c->act_shape[2] != W0;
     if (c->act1.ensure(a1 * 4) || c->act2.ensure(a2 * 4) || c->act3.ensure(a3 * 4)) return 1;
-    if (fresh) {   // zero borders once per geometry; the kernels only ever write interiors
+    if (fresh) {
         GAT_CUDA(cudaMemsetAsync(c->act1.p, 0, a1 * 4, (cudaStream_t)stream));
         GAT_CUDA(cudaMemsetAsync(c->act2.p, 0, a2 * 4, (cudaStream_t)stream));
         c->act_shape[0] = chunk; c->act_shape[1] = H0; c->act_shape[2] = W0;
     }
-    float* logits = cnn_logits;
     const size_t head_smem = ((size_t)128 * 16 * kHeadClips + (size_t)c->hidden * kHeadClips + kHeadClips * 64) * sizeof(float) + 64;
-    GAT_CUDA(cudaFuncSetAttribute(cnn_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem));
     for (long long c0 = 0; c0 < N; c0 += chunk) {
         const int nc = (int)(N - c0 < chunk ? N - c0 : chunk);
         Conv1Params p1{mel + c0 * H0 * W0, nc, H0, W0, c->conv_w[0].as<float>(), c->conv_b[0].as<float>(), c->act1.as<float>(), 32, 0.01f};
         LAUNCH(c, conv1_pool_kernel, (unsigned)(nc * ceil_div(H1 * W1, 256)), 256, 0, stream, p1);
         ConvParams p2{c->act1.as<float>(), nc, H1, W1, c->conv_w[1].as<float>(), c->conv_b[1].as<float>(), c->act2.as<float>(), 1, 0.01f};
         auto k2 = conv3x3_pool_kernel<32, 64>;
-        KNAME("conv2_3x3_pool_32_64");
         LAUNCH(c, k2, (unsigned)(nc * ceil_div(H2 * W2, 32)), 256, 0, stream, p2);
         ConvParams p3{c->act2.as<float>(), nc, H2, W2, c->conv_w[2].as<float>(), c->conv_b[2].as<float>(),
                       c->act3.as<float>() + (size_t)c0 * H3 * W3 * 128, 0, 0.01f};
         auto k3 = conv3x3_pool_kernel<64, 128>;
-        KNAME("conv3_3x3_pool_64_128");
         LAUNCH(c, k3, (unsigned)(nc * ceil_div(H3 * W3, 16)), 256, 0, stream, p3);
     }
     HeadParams ph{c->act3.as<float>(), (int)N, H3, W3, 128, c->fc1_w.as<float>(), c->fc1_b.as<float>(), c->hidden,
-                  c->fc2_w.as<float>(), c->fc2_b.as<float>(), c->classes, 0.01f, logits, cnn_probs};
+                  c->fc2_w.as<float>(), c->fc2_b.as<float>(), c->classes, 0.01f, cnn_logits, cnn_probs};
     LAUNCH(c, cnn_head_kernel, (unsigned)ceil_div((int)N, kHeadClips), 256, head_smem, stream, ph);
     return 0;
 }
+#else
+// conv1 on CUDA cores (C_in = 1), conv2/conv3 as tcgen05 implicit GEMMs (csrc/conv_tc.cuh), head once per batch.
+// Clips go through the convs num_sms at a time: conv3 then has exactly one group per SM and conv2 four,
+// and act1+act2 (hi/lo planes, ~0.6 MB per clip at T = 87) stay inside the 126 MB L2 between layers.
+constexpr size_t kActGuard = 65536;   // bytes before/after the plane buffers: halo reads of edge groups stay in bounds
+
+inline int conv_tc_rows(int H, int Wp) {
+    int R = 2 * (kTcGroupPix / (2 * Wp));
+    const int hmax = 2 * (H / 2);
+    return R < hmax ? R : hmax;
+}
+
+int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, float* cnn_logits, void* stream) {
+    if (!c->cnn_loaded) return fail("infer: no CNN loaded (gat_load_cnn)");
+    const int H0 = c->cfg.mel_n_mels, W0 = T;
+    const int H1 = H0 / 2, W1 = W0 / 2, H2 = H1 / 2, W2 = W1 / 2, H3 = H2 / 2, W3 = W2 / 2;
+    if (H3 < 1 || W3 < 1) return fail("infer: mel image %dx%d too small for three 2x2 pools", H0, W0);
+    const int R2 = conv_tc_rows(H1, W1 + 2), R3 = conv_tc_rows(H2, W2 + 2);
+    const size_t smem2 = conv_tc_smem_bytes<64>(W1 + 2, 3), smem3 = conv_tc_smem_bytes<128>(W2 + 2, 2);
+    if (R2 < 2 || R3 < 2 || smem2 > 227 * 1024 || smem3 > 227 * 1024)
+        return fail("infer: mel image of %d frames is too wide for the tensor-core conv tiling of this build", W0);
+    const long long chunk = N < c->num_sms ? N : c->num_sms;
+    const size_t P1 = (size_t)(H1 + 2) * (W1 + 2), P2 = (size_t)(H2 + 2) * (W2 + 2);
+    const size_t a1 = (size_t)chunk * 8 * P1 * 4 * 4, a2 = (size_t)chunk * 16 * P2 * 4 * 4;   // bytes of ONE of hi/lo
+    const size_t a3 = (size_t)N * H3 * W3 * 128 * 4;
+    const bool fresh = c->act1.cap < 2 * a1 + 2 * kActGuard || c->act2.cap < 2 * a2 + 2 * kActGuard ||
+                       c->act_shape[0] != chunk || c->act_shape[1] != H0 || c->act_shape[2] != W0;
+    if (c->act1.ensure(2 * a1 + 2 * kActGuard) || c->act2.ensure(2 * a2 + 2 * kActGuard) || c->act3.ensure(a3)) return 1;
+    if (fresh) {   // zero borders (and guards) once per geometry; the kernels only ever write interiors
+        GAT_CUDA(cudaMemsetAsync(c->act1.p, 0, 2 * a1 + 2 * kActGuard, (cudaStream_t)stream));
+        GAT_CUDA(cudaMemsetAsync(c->act2.p, 0, 2 * a2 + 2 * kActGuard, (cudaStream_t)stream));
+        c->act_shape[0] = chunk; c->act_shape[1] = H0; c->act_shape[2] = W0;
+    }
+    float* act1_hi = reinterpret_cast<float*>(c->act1.as<unsigned char>() + kActGuard);
+    float* act1_lo = reinterpret_cast<float*>(c->act1.as<unsigned char>() + kActGuard + a1);
+    float* act2_hi = reinterpret_cast<float*>(c->act2.as<unsigned char>() + kActGuard);
+    float* act2_lo = reinterpret_cast<float*>(c->act2.as<unsigned char>() + kActGuard + a2);
+    auto k2 = conv_tc_kernel<32, 64, 3>;
+    auto k3 = conv_tc_kernel<64, 128, 2>;
+    GAT_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    GAT_CUDA(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+    const size_t head_smem = ((size_t)128 * 16 * kHeadClips + (size_t)c->hidden * kHeadClips + kHeadClips * 64) * sizeof(float) + 64;
+    GAT_CUDA(cudaFuncSetAttribute(cnn_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem));
+    for (long long c0 = 0; c0 < N; c0 += chunk) {
+        const int nc = (int)(N - c0 < chunk ? N - c0 : chunk);
+        Conv1PlanesParams p1{mel + c0 * H0 * W0, nc, H0, W0, c->conv_w[0].as<float>(), c->conv_b[0].as<float>(), act1_hi, act1_lo, 0.01f};
+        LAUNCH(c, conv1_pool_planes_kernel, (unsigned)(nc * ceil_div(H1 * W1, 256)), 256, 0, stream, p1);
+        ConvTcParams p2{act1_hi, act1_lo, c->conv_w_tc[1].as<float>(), c->conv_b[1].as<float>(), nc, H1, W1, R2,
+                        ceil_div(H1 / 2, R2 / 2), 1, act2_hi, act2_lo, 0.01f};
+        const int work2 = nc * p2.groups_per_clip;
+        KNAME("conv2_tc_32_64");
+        LAUNCH(c, k2, (unsigned)(work2 < c->num_sms ? work2 : c->num_sms), kTcThreads, smem2, stream, p2);
+        ConvTcParams p3{act2_hi, act2_lo, c->conv_w_tc[2].as<float>(), c->conv_b[2].as<float>(), nc, H2, W2, R3,
+                        ceil_div(H2 / 2, R3 / 2), 0, c->act3.as<float>() + (size_t)c0 * H3 * W3 * 128, nullptr, 0.01f};
+        const int work3 = nc * p3.groups_per_clip;
+        KNAME("conv3_tc_64_128");
+        LAUNCH(c, k3, (unsigned)(work3 < c->num_sms ? work3 : c->num_sms), kTcThreads, smem3, stream, p3);
+    }
+    HeadParams ph{c->act3.as<float>(), (int)N, H3, W3, 128, c->fc1_w.as<float>(), c->fc1_b.as<float>(), c->hidden,
+                  c->fc2_w.as<float>(), c->fc2_b.as<float>(), c->classes, 0.01f, cnn_logits, cnn_probs};
+    LAUNCH(c, cnn_head_kernel, (unsigned)ceil_div((int)N, kHeadClips), 256, head_smem, stream, ph);
+    return 0;
+}
+#endif
 
 int run_mlp_ensemble(gat_ctx* c, const float* mfcc, int ld, int64_t N, const float* cnn_probs, float* probs, float* mlp_probs,
                      float* mlp_logits, int64_t* index, float* conf, void* stream) {

@@ -12,6 +12,7 @@ namespace gat {
 
 __device__ __forceinline__ float leaky(float v, float slope) { return v > 0.0f ? v : v * slope; }
 
+#ifdef GAT_CPU_EMU   // CUDA-core conv layers: host-emulation stand-ins for csrc/conv_tc.cuh (tests/emu only)
 // ---------------------------------------------------------------------------------------------------
 // conv1: C_in = 1.  in [N][H][W] (mel-dB image), out padded NHWC [N][H/2+2][W/2+2][C] with zero border.
 struct Conv1Params {
@@ -132,6 +133,8 @@ __global__ void __launch_bounds__(256) conv3x3_pool_kernel(ConvParams p) {
     *reinterpret_cast<float4*>(o + g * 8) = make_float4(r[0], r[1], r[2], r[3]);
     *reinterpret_cast<float4*>(o + g * 8 + 4) = make_float4(r[4], r[5], r[6], r[7]);
 }
+
+#endif  // GAT_CPU_EMU
 
 // ---------------------------------------------------------------------------------------------------
 // AdaptiveAvgPool2d((4,4)) + Flatten (C-major) + Linear + LeakyReLU + Linear + softmax.
