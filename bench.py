@@ -159,7 +159,9 @@ def kernel_table(prof: dict, steps: int, n_clips: int, T: int, peaks: dict):
         "conv1_pool_planes_kernel": ("hbm", n_clips * (4 * 64 * T + 2 * 4 * H1 * W1 * 32)),
         "conv2_tc_32_64": ("tensor", n_clips * 2.0 * H1 * W1 * 64 * 32 * 9),
         "conv3_tc_64_128": ("tensor", n_clips * 2.0 * H2 * W2 * 128 * 64 * 9),
-        "cnn_head_kernel": ("tensor", n_clips * 2.0 * (2048 * 256 + 256 * 47)),
+        "avgpool_planes_kernel": ("hbm", n_clips * (4 * 8 * (T // 8) * 128 + 2 * 4 * 2048)),
+        "fc1_tc_2048_256": ("tensor", n_clips * 2.0 * 2048 * 256),
+        "fc2_softmax_kernel": ("hbm", n_clips * (4 * 256 + 8 * 47)),
         "argmax_kernel": ("hbm", n_clips * (4 * 47 + 12)),
     }
     rows = []

@@ -17,14 +17,23 @@
 
 namespace gat {
 
+// Banded-sparse mel filterbank in "lane slot" form.  Lane l of a warp owns up to kMaxMelsPerLane filters
+// (slot q -> entry q*32 + l).  The host pads each band downwards so that, within a slot, the 32 band
+// starts are distinct modulo 32 and each band's weights begin at an offset congruent to its start: then
+// in every iteration of the gather loop the 32 lanes hit 32 different shared-memory banks, for the power
+// spectrum and for the weights alike (see build_sparse_fb in gat.cu for the assignment).
 struct SparseFb {
     int n_mels;
-    int nnz;
-    const int* start;    // [n_mels] first FFT bin with a non-zero weight
-    const int* len;      // [n_mels] number of consecutive non-zero weights
-    const int* off;      // [n_mels] offset of the first weight in w
+    int n_slots;         // ceil(n_mels / 32)
+    int nnz;             // length of w including alignment gaps
+    const int* start;    // [n_slots*32] first bin of the (padded) band; may be negative (reads land in zeros)
+    const int* len;      // [n_slots*32] bins in the padded band (0 = empty slot)
+    const int* off;      // [n_slots*32] offset of the band's first weight in w
+    const int* mel;      // [n_slots*32] filter index the slot produces, -1 if empty
     const float* w;      // [nnz]
 };
+
+constexpr int kPbufLead = 32;   // zeros in front of the power spectrum so padded bands may start below bin 0
 
 enum { kPadZero = 0, kPadReflect = 1 };
 enum { kOutImage = 0, kOutSpec = 1 };
@@ -75,7 +84,7 @@ __host__ __device__ inline size_t stft_mel_smem_bytes(int nwarps, int frames_per
     b += 2048 * sizeof(T);                                               // window
     b += ((size_t)(frames_per_cta - 1) * hop + 2048) * sizeof(T);        // staged samples
     b += (size_t)nwarps * kXbufElems * sizeof(Cpx<T>);                   // per-warp transpose buffers
-    b += (size_t)3 * n_mels * sizeof(int) + (size_t)nnz * sizeof(float); // sparse filterbank
+    b += (size_t)4 * kMaxMelsPerLane * 32 * sizeof(int) + (size_t)nnz * sizeof(float); // sparse filterbank (lane slots)
     if (image) b += (size_t)n_mels * (frames_per_cta + 1) * sizeof(T);   // output tile
     return b + 64;
 }
@@ -94,16 +103,20 @@ __global__ void __launch_bounds__(kThreads, 1) stft_mel_kernel(StftMelParams<T> 
     T* win = reinterpret_cast<T*>(sp);                        sp += 2048 * sizeof(T);
     T* span = reinterpret_cast<T*>(sp);                       sp += (size_t)span_len * sizeof(T);
     Cpx<T>* xbuf_all = reinterpret_cast<Cpx<T>*>(sp);         sp += (size_t)nwarps * kXbufElems * sizeof(Cpx<T>);
-    int* fb_start = reinterpret_cast<int*>(sp);               sp += n_mels * sizeof(int);
-    int* fb_len = reinterpret_cast<int*>(sp);                 sp += n_mels * sizeof(int);
-    int* fb_off = reinterpret_cast<int*>(sp);                 sp += n_mels * sizeof(int);
+    constexpr int kSlotEntries = kMaxMelsPerLane * 32;
+    int* fb_start = reinterpret_cast<int*>(sp);               sp += kSlotEntries * sizeof(int);
+    int* fb_len = reinterpret_cast<int*>(sp);                 sp += kSlotEntries * sizeof(int);
+    int* fb_off = reinterpret_cast<int*>(sp);                 sp += kSlotEntries * sizeof(int);
+    int* fb_mel = reinterpret_cast<int*>(sp);                 sp += kSlotEntries * sizeof(int);
     float* fb_w = reinterpret_cast<float*>(sp);               sp += (size_t)p.fb.nnz * sizeof(float);
     T* tile = reinterpret_cast<T*>(sp);                       // kOutImage only
 
     fill_fft_tables<T>(tab, p.tw, p.w2);
     for (int i = threadIdx.x; i < 2048; i += blockDim.x) win[i] = p.window[i];
-    for (int i = threadIdx.x; i < n_mels; i += blockDim.x) {
-        fb_start[i] = p.fb.start[i]; fb_len[i] = p.fb.len[i]; fb_off[i] = p.fb.off[i];
+    for (int i = threadIdx.x; i < kSlotEntries; i += blockDim.x) {
+        const bool live = i < p.fb.n_slots * 32;
+        fb_start[i] = live ? p.fb.start[i] : 0; fb_len[i] = live ? p.fb.len[i] : 0;
+        fb_off[i] = live ? p.fb.off[i] : 0;     fb_mel[i] = live ? p.fb.mel[i] : -1;
     }
     for (int i = threadIdx.x; i < p.fb.nnz; i += blockDim.x) fb_w[i] = p.fb.w[i];
     __syncthreads();
@@ -144,27 +157,32 @@ __global__ void __launch_bounds__(kThreads, 1) stft_mel_kernel(StftMelParams<T> 
         for (int f = warp; f < nf; f += nwarps) {
             const T* x = span + (size_t)f * p.hop;
             Cpx<T> v[32];
+            const Cpx<T>* x2 = reinterpret_cast<const Cpx<T>*>(x);       // (x[2j], x[2j+1]) as one aligned vector
+            const Cpx<T>* w2v = reinterpret_cast<const Cpx<T>*>(win);
 #pragma unroll
             for (int n2 = 0; n2 < 32; ++n2) {
                 const int j = lane + 32 * n2;
-                v[n2] = Cpx<T>{x[2 * j] * win[2 * j], x[2 * j + 1] * win[2 * j + 1]};
+                const Cpx<T> xv = x2[j], wv = w2v[j];
+                v[n2] = Cpx<T>{xv.x * wv.x, xv.y * wv.y};
             }
             T pw[32], pw_nyq;
             warp_rfft2048_power<T>(v, pw, pw_nyq, xbuf, tab);
+            pbuf[lane] = (T)0;                                          // kPbufLead zeros in front of bin 0
 #pragma unroll
-            for (int k1 = 0; k1 < 32; ++k1) pbuf[32 * k1 + lane] = pw[k1];
-            if (lane == 0) pbuf[1024] = pw_nyq;
+            for (int k1 = 0; k1 < 32; ++k1) pbuf[kPbufLead + 32 * k1 + lane] = pw[k1];
+            if (lane == 0) pbuf[kPbufLead + 1024] = pw_nyq;
             __syncwarp();
-            // banded-sparse mel: lanes take filters in serpentine order so narrow and wide filters pair up
+            // banded-sparse mel, one filter per (lane, slot); bank-conflict free by construction
 #pragma unroll
             for (int q = 0; q < kMaxMelsPerLane; ++q) {
-                const int base = (q >> 1) * 64;
-                const int m = (q & 1) ? base + 63 - lane : base + lane;
-                if (m < n_mels) {
-                    const int s0 = fb_start[m], ln = fb_len[m];
-                    const float* w = fb_w + fb_off[m];
-                    T acc = (T)0;
-                    for (int k = 0; k < ln; ++k) acc += pbuf[s0 + k] * (T)w[k];
+                const int e = q * 32 + lane;
+                const int m = fb_mel[e];
+                const int ln = fb_len[e];
+                const T* pb = pbuf + kPbufLead + fb_start[e];
+                const float* w = fb_w + fb_off[e];
+                T acc = (T)0;
+                for (int k = 0; k < ln; ++k) acc += pb[k] * (T)w[k];
+                if (m >= 0) {
                     const T db = db10(acc > p.amin ? acc : p.amin);
                     if (kOut == kOutImage) {
                         tile[m * (FC + 1) + f] = db;

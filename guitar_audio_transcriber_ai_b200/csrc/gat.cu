@@ -9,12 +9,14 @@ using std::min;
 
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "fc_tc.cuh"
 #include "features.cuh"
 #include "fft.cuh"
 #include "infer.cuh"
 #include "onset.cuh"
 #include "yin.cuh"
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstring>
 #include <string>
@@ -68,29 +70,65 @@ int upload(DevBuf& b, const T* host, size_t count) {
 }
 
 struct SparseFbDev {
-    DevBuf start, len, off, w;
-    int n_mels = 0, nnz = 0;
-    SparseFb view() const { return SparseFb{n_mels, nnz, start.as<int>(), len.as<int>(), off.as<int>(), w.as<float>()}; }
+    DevBuf start, len, off, mel, w;
+    int n_mels = 0, n_slots = 0, nnz = 0;
+    SparseFb view() const {
+        return SparseFb{n_mels, n_slots, nnz, start.as<int>(), len.as<int>(), off.as<int>(), mel.as<int>(), w.as<float>()};
+    }
 };
 
-// dense[row m][col f] with given strides -> contiguous non-zero band per filter
+// dense[filter m][bin f] (given strides) -> lane-slot banded form for stft_mel_kernel.
+// Slot q holds filters 32q .. 32q+31.  Each filter is given to the lane equal to its (possibly lowered)
+// band start modulo 32, so that the 32 bands of a slot start in 32 different banks; lowering a start by d
+// costs d zero-weight iterations.  Long filters choose first, and prefer lanes whose earlier slots are short,
+// which keeps the per-lane totals (the warp's loop count) balanced.
 int build_sparse_fb(SparseFbDev& out, const float* dense, int n_mels, int n_freqs, long long stride_m, long long stride_f) {
-    std::vector<int> start(n_mels), len(n_mels), off(n_mels);
-    std::vector<float> w;
+    const int n_slots = (n_mels + 31) / 32;
+    std::vector<int> first(n_mels), length(n_mels);
     for (int m = 0; m < n_mels; ++m) {
-        int first = -1, last = -1;
+        int lo = -1, hi = -1;
         for (int f = 0; f < n_freqs; ++f)
-            if (dense[m * stride_m + f * stride_f] != 0.0f) { if (first < 0) first = f; last = f; }
-        start[m] = first < 0 ? 0 : first;
-        len[m] = first < 0 ? 0 : last - first + 1;
-        off[m] = (int)w.size();
-        for (int f = start[m]; f < start[m] + len[m]; ++f) w.push_back(dense[m * stride_m + f * stride_f]);
+            if (dense[m * stride_m + f * stride_f] != 0.0f) { if (lo < 0) lo = f; hi = f; }
+        first[m] = lo < 0 ? 0 : lo;
+        length[m] = lo < 0 ? 0 : hi - lo + 1;
+    }
+    std::vector<int> start(n_slots * 32, 0), len(n_slots * 32, 0), off(n_slots * 32, 0), mel(n_slots * 32, -1);
+    std::vector<int> lane_load(32, 0);
+    std::vector<float> w;
+    for (int q = 0; q < n_slots; ++q) {
+        std::vector<int> ids;
+        for (int m = 32 * q; m < n_mels && m < 32 * q + 32; ++m) ids.push_back(m);
+        std::sort(ids.begin(), ids.end(), [&](int a, int b) { return length[a] > length[b]; });
+        std::vector<char> taken(32, 0);
+        for (int m : ids) {
+            int best_lane = -1, best_cost = 1 << 30;
+            for (int lane = 0; lane < 32; ++lane) {
+                if (taken[lane]) continue;
+                const int d = ((first[m] - lane) % 32 + 32) % 32;           // lower the start to hit this bank
+                const int cost = lane_load[lane] + length[m] + d;
+                if (cost < best_cost) { best_cost = cost; best_lane = lane; }
+            }
+            const int d = ((first[m] - best_lane) % 32 + 32) % 32;
+            const int e = q * 32 + best_lane;
+            taken[best_lane] = 1;
+            lane_load[best_lane] += length[m] + d;
+            start[e] = first[m] - d;
+            len[e] = length[m] ? length[m] + d : 0;
+            mel[e] = m;
+            // weights begin at an offset congruent to the lane as well
+            while ((int)(w.size() % 32) != best_lane) w.push_back(0.0f);
+            off[e] = (int)w.size();
+            for (int k = 0; k < len[e]; ++k) {
+                const int f = start[e] + k;
+                w.push_back(f >= first[m] ? dense[m * stride_m + (long long)f * stride_f] : 0.0f);
+            }
+        }
     }
     if (w.empty()) w.push_back(0.0f);
-    out.n_mels = n_mels;
-    out.nnz = (int)w.size();
-    if (upload(out.start, start.data(), n_mels) || upload(out.len, len.data(), n_mels) ||
-        upload(out.off, off.data(), n_mels) || upload(out.w, w.data(), w.size())) return 1;
+    out.n_mels = n_mels; out.n_slots = n_slots; out.nnz = (int)w.size();
+    if (upload(out.start, start.data(), start.size()) || upload(out.len, len.data(), len.size()) ||
+        upload(out.off, off.data(), off.size()) || upload(out.mel, mel.data(), mel.size()) ||
+        upload(out.w, w.data(), w.size())) return 1;
     return 0;
 }
 
@@ -121,6 +159,7 @@ struct gat_ctx {
     DevBuf mlp_params; int mlp_dims[kMlpMaxLayers + 1] = {0}; int mlp_n_linear = 0; int mlp_n_params = 0;
     DevBuf conv_w[3], conv_b[3], fc1_w, fc1_b, fc2_w, fc2_b;
     DevBuf conv_w_tc[3];   // conv2/conv3 weights in the tensor-core operand layout (hi/lo TF32 split)
+    DevBuf fc1_w_tc, feat_planes, hid;
     int conv_ch[4] = {0, 0, 0, 0}; int hidden = 0, classes = 0; bool cnn_loaded = false;
     DevBuf scaler_mean, scaler_scale; int scaler_n = 0;
     float w_mlp = 0.2f, w_cnn = 0.8f;
@@ -248,9 +287,9 @@ extern "C" int gat_ctx_create(const gat_config* cfg, int device, gat_ctx** out) 
 extern "C" void gat_ctx_destroy(gat_ctx* c) {
     if (!c) return;
     DevBuf* all[] = {&c->tw32, &c->w2_32, &c->tw64, &c->w2_64, &c->win_mel, &c->win_mfcc, &c->win64, &c->dct,
-                     &c->fb_mel.start, &c->fb_mel.len, &c->fb_mel.off, &c->fb_mel.w,
-                     &c->fb_mfcc.start, &c->fb_mfcc.len, &c->fb_mfcc.off, &c->fb_mfcc.w,
-                     &c->mlp_params, &c->conv_w_tc[1], &c->conv_w_tc[2], &c->conv_w[0], &c->conv_w[1], &c->conv_w[2], &c->conv_b[0], &c->conv_b[1], &c->conv_b[2],
+                     &c->fb_mel.start, &c->fb_mel.len, &c->fb_mel.off, &c->fb_mel.mel, &c->fb_mel.w,
+                     &c->fb_mfcc.start, &c->fb_mfcc.len, &c->fb_mfcc.off, &c->fb_mfcc.mel, &c->fb_mfcc.w,
+                     &c->mlp_params, &c->conv_w_tc[1], &c->conv_w_tc[2], &c->fc1_w_tc, &c->feat_planes, &c->hid, &c->conv_w[0], &c->conv_w[1], &c->conv_w[2], &c->conv_b[0], &c->conv_b[1], &c->conv_b[2],
                      &c->fc1_w, &c->fc1_b, &c->fc2_w, &c->fc2_b, &c->scaler_mean, &c->scaler_scale,
                      &c->clip_scale, &c->spec, &c->spec_max, &c->f0, &c->act1, &c->act2, &c->act3, &c->hz_tmp, &c->logits_cnn, &c->logits_mlp,
                      &c->seg_small, &c->seg_rms, &c->seg_rms_med, &c->seg_gate, &c->seg_env, &c->seg_envn, &c->seg_cand,
@@ -309,6 +348,21 @@ extern "C" int gat_load_cnn(gat_ctx* c, int32_t n_conv, const int32_t* ch, const
                     t[base + (size_t)8 * cout * 4 + idx] = w - hi;
                 }
         if (upload(c->conv_w_tc[i], t.data(), t.size())) return 1;
+    }
+    {   // FC1: [k/32][hi|lo][8 chunks][hidden][4]
+        if (hidden != 256) return fail("gat_load_cnn: the tensor-core head is built for hidden = 256 (got %d)", hidden);
+        const int K = ch[3] * 16;
+        std::vector<float> t((size_t)(K / 32) * 2 * 8 * hidden * 4);
+        for (int k = 0; k < K; ++k)
+            for (int oc = 0; oc < hidden; ++oc) {
+                const float w = fc1_w[(size_t)k * hidden + oc];
+                const float hi = tc::tf32_hi(w);
+                const size_t base = ((size_t)(k / 32) * 2) * 8 * hidden * 4;
+                const size_t idx = ((size_t)((k % 32) / 4) * hidden + oc) * 4 + (k % 4);
+                t[base + idx] = hi;
+                t[base + (size_t)8 * hidden * 4 + idx] = w - hi;
+            }
+        if (upload(c->fc1_w_tc, t.data(), t.size())) return 1;
     }
 #endif
     if (upload(c->fc1_w, fc1_w, (size_t)ch[3] * 16 * hidden) || upload(c->fc1_b, fc1_b, hidden) ||
@@ -549,8 +603,6 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
     auto k3 = conv_tc_kernel<64, 128, 2>;
     GAT_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     GAT_CUDA(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-    const size_t head_smem = ((size_t)128 * 16 * kHeadClips + (size_t)c->hidden * kHeadClips + kHeadClips * 64) * sizeof(float) + 64;
-    GAT_CUDA(cudaFuncSetAttribute(cnn_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem));
     for (long long c0 = 0; c0 < N; c0 += chunk) {
         const int nc = (int)(N - c0 < chunk ? N - c0 : chunk);
         Conv1PlanesParams p1{mel + c0 * H0 * W0, nc, H0, W0, c->conv_w[0].as<float>(), c->conv_b[0].as<float>(), act1_hi, act1_lo, 0.01f};
@@ -566,9 +618,25 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
         KNAME("conv3_tc_64_128");
         LAUNCH(c, k3, (unsigned)(work3 < c->num_sms ? work3 : c->num_sms), kTcThreads, smem3, stream, p3);
     }
-    HeadParams ph{c->act3.as<float>(), (int)N, H3, W3, 128, c->fc1_w.as<float>(), c->fc1_b.as<float>(), c->hidden,
-                  c->fc2_w.as<float>(), c->fc2_b.as<float>(), c->classes, 0.01f, cnn_logits, cnn_probs};
-    LAUNCH(c, cnn_head_kernel, (unsigned)ceil_div((int)N, kHeadClips), 256, head_smem, stream, ph);
+    // head: adaptive average pool -> FC1 (tcgen05) -> FC2 + softmax
+    const long long rows_pad = (N + 127) / 128 * 128;
+    const size_t feat_bytes = (size_t)512 * rows_pad * 16;
+    if (c->feat_planes.ensure(2 * feat_bytes) || c->hid.ensure((size_t)N * 256 * 4)) return 1;
+    float* feat_hi = c->feat_planes.as<float>();
+    float* feat_lo = reinterpret_cast<float*>(c->feat_planes.as<unsigned char>() + feat_bytes);
+    AvgPoolPlanesParams pa{c->act3.as<float>(), (int)N, H3, W3, 128, feat_hi, feat_lo, rows_pad};
+    LAUNCH(c, avgpool_planes_kernel, (unsigned)((N * 4 * 128 + 255) / 256), 256, 0, stream, pa);
+    auto kf = fc_tc_kernel<256>;
+    const size_t fc_smem = fc_tc_smem_bytes<256>();
+    GAT_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fc_smem));
+    FcTcParams pf{feat_hi, feat_lo, rows_pad, c->fc1_w_tc.as<float>(), c->fc1_b.as<float>(), (int)N, 2048, 0.01f, c->hid.as<float>()};
+    KNAME("fc1_tc_2048_256");
+    LAUNCH(c, kf, (unsigned)(rows_pad / 128), 192, fc_smem, stream, pf);
+    Fc2Params p2f{c->hid.as<float>(), (int)N, 256, c->fc2_w.as<float>(), c->fc2_b.as<float>(), c->classes, cnn_logits, cnn_probs};
+    const size_t fc2_smem = (size_t)256 * c->classes * 4 + 64;
+    GAT_CUDA(cudaFuncSetAttribute(fc2_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fc2_smem));
+    const long long ctas2 = (N + 7) / 8;
+    LAUNCH(c, fc2_softmax_kernel, (unsigned)(ctas2 < 2 * c->num_sms ? ctas2 : 2 * c->num_sms), 256, fc2_smem, stream, p2f);
     return 0;
 }
 #endif
@@ -750,7 +818,8 @@ extern "C" int gat_transcribe_clips_host(gat_ctx* c, const float* audio_host, in
         c->e2e_streams = true;
     }
     const int classes = c->classes;
-    const int64_t chunk = N < 512 ? N : 512;   // 512 one-second clips = 45 MB per copy
+    const int64_t want = 4 * (int64_t)c->num_sms;   // a multiple of the conv kernels' num_sms-clip passes (592 clips = 52 MB at 1 s)
+    const int64_t chunk = N < want ? N : want;
     if (c->e2e_audio[0].ensure((size_t)chunk * n * 4) || c->e2e_audio[1].ensure((size_t)chunk * n * 4) ||
         c->e2e_probs.ensure((size_t)N * classes * 4) || c->e2e_mlp_probs.ensure((size_t)N * classes * 4) ||
         c->e2e_cnn_probs.ensure((size_t)N * classes * 4) || c->e2e_index.ensure((size_t)N * 8) || c->e2e_conf.ensure((size_t)N * 4)) return 1;

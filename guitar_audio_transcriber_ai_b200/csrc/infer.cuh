@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(256) conv3x3_pool_kernel(ConvParams p) {
 
 #endif  // GAT_CPU_EMU
 
+#ifdef GAT_CPU_EMU   // CUDA-core head: host-emulation stand-in for csrc/fc_tc.cuh (tests/emu only)
 // ---------------------------------------------------------------------------------------------------
 // AdaptiveAvgPool2d((4,4)) + Flatten (C-major) + Linear + LeakyReLU + Linear + softmax.
 // A CTA of 256 threads handles kHeadClips clips so the 2 MB of FC1 weights are streamed once per group.
@@ -225,6 +226,8 @@ __global__ void __launch_bounds__(256) cnn_head_kernel(HeadParams p) {
         if (lane + 32 < p.classes) { p.logits[o + lane + 32] = v1; p.probs[o + lane + 32] = e1 / sum; }
     }
 }
+
+#endif  // GAT_CPU_EMU
 
 // ---------------------------------------------------------------------------------------------------
 // MLP forward (Linear -> LayerNorm -> LeakyReLU(0.1))* -> Linear -> softmax, then the ensemble
