@@ -311,6 +311,12 @@ def run_ours(args):
 
 
 def main():
+    # Exactly ONE line may reach stdout (the JSON record): libraries such as NCCL print banners to the C-level
+    # stdout, so route fd 1 to stderr for the duration of the run and emit the record on the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -18,22 +18,25 @@
 namespace gat {
 
 // Banded-sparse mel filterbank in "lane slot" form.  Lane l of a warp owns up to kMaxMelsPerLane filters
-// (slot q -> entry q*32 + l).  The host pads each band downwards so that, within a slot, the 32 band
-// starts are distinct modulo 32 and each band's weights begin at an offset congruent to its start: then
-// in every iteration of the gather loop the 32 lanes hit 32 different shared-memory banks, for the power
-// spectrum and for the weights alike (see build_sparse_fb in gat.cu for the assignment).
+// (slot q -> entry q*32 + l).  The gather loop reads four bins and four weights per step (128-bit loads).
+// The host lowers each band's start to a multiple of 4 congruent to 4*(l mod 8) modulo 32 and places its
+// weights at an offset with the same residue: in each 8-lane phase of a 128-bit shared load the lanes then
+// touch 8 different 16-byte bank groups, for the power spectrum and for the weights alike (see
+// build_sparse_fb in gat.cu for the assignment).  `len` counts groups of four bins.
 struct SparseFb {
     int n_mels;
     int n_slots;         // ceil(n_mels / 32)
     int nnz;             // length of w including alignment gaps
     const int* start;    // [n_slots*32] first bin of the (padded) band; may be negative (reads land in zeros)
-    const int* len;      // [n_slots*32] bins in the padded band (0 = empty slot)
+    const int* len;      // [n_slots*32] groups of 4 bins in the padded band (0 = empty slot)
     const int* off;      // [n_slots*32] offset of the band's first weight in w
     const int* mel;      // [n_slots*32] filter index the slot produces, -1 if empty
     const float* w;      // [nnz]
 };
 
 constexpr int kPbufLead = 32;   // zeros in front of the power spectrum so padded bands may start below bin 0
+
+template <typename T> struct __align__(4 * sizeof(T)) Vec4 { T x, y, z, w; };
 
 enum { kPadZero = 0, kPadReflect = 1 };
 enum { kOutImage = 0, kOutSpec = 1 };
@@ -112,7 +115,7 @@ __global__ void __launch_bounds__(kThreads, 1) stft_mel_kernel(StftMelParams<T> 
     T* tile = reinterpret_cast<T*>(sp);                       // kOutImage only
 
     fill_fft_tables<T>(tab, p.tw, p.w2);
-    for (int i = threadIdx.x; i < 2048; i += blockDim.x) win[i] = p.window[i];
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) win[i] = (T)0.5 * p.window[i];   // 1/2 of the Hermitian split, exact
     for (int i = threadIdx.x; i < kSlotEntries; i += blockDim.x) {
         const bool live = i < p.fb.n_slots * 32;
         fb_start[i] = live ? p.fb.start[i] : 0; fb_len[i] = live ? p.fb.len[i] : 0;
@@ -165,23 +168,24 @@ __global__ void __launch_bounds__(kThreads, 1) stft_mel_kernel(StftMelParams<T> 
                 const Cpx<T> xv = x2[j], wv = w2v[j];
                 v[n2] = Cpx<T>{xv.x * wv.x, xv.y * wv.y};
             }
-            T pw[32], pw_nyq;
-            warp_rfft2048_power<T>(v, pw, pw_nyq, xbuf, tab);
-            pbuf[lane] = (T)0;                                          // kPbufLead zeros in front of bin 0
-#pragma unroll
-            for (int k1 = 0; k1 < 32; ++k1) pbuf[kPbufLead + 32 * k1 + lane] = pw[k1];
-            if (lane == 0) pbuf[kPbufLead + 1024] = pw_nyq;
-            __syncwarp();
-            // banded-sparse mel, one filter per (lane, slot); bank-conflict free by construction
+            warp_rfft2048_power<T>(v, xbuf, kPbufLead, tab);
+            // banded-sparse mel, one filter per (lane, slot), four bins per step; bank-conflict free by construction
 #pragma unroll
             for (int q = 0; q < kMaxMelsPerLane; ++q) {
                 const int e = q * 32 + lane;
                 const int m = fb_mel[e];
                 const int ln = fb_len[e];
-                const T* pb = pbuf + kPbufLead + fb_start[e];
-                const float* w = fb_w + fb_off[e];
+                const Vec4<T>* pb = reinterpret_cast<const Vec4<T>*>(pbuf + kPbufLead + fb_start[e]);
+                const float4* w = reinterpret_cast<const float4*>(fb_w + fb_off[e]);
                 T acc = (T)0;
-                for (int k = 0; k < ln; ++k) acc += pb[k] * (T)w[k];
+                for (int k = 0; k < ln; ++k) {
+                    const Vec4<T> pv = pb[k];
+                    const float4 wv = w[k];
+                    acc += pv.x * (T)wv.x;
+                    acc += pv.y * (T)wv.y;
+                    acc += pv.z * (T)wv.z;
+                    acc += pv.w * (T)wv.w;
+                }
                 if (m >= 0) {
                     const T db = db10(acc > p.amin ? acc : p.amin);
                     if (kOut == kOutImage) {

@@ -3,7 +3,7 @@
 // A 2048-point real frame is folded into 1024 complex points z[j] = x[2j] + i x[2j+1]; one warp
 // transforms it as 32 x 32: every lane runs a 32-point FFT in registers (over n2, stride 32), the result
 // is twiddled by W_1024^(n1*k2) and transposed through shared memory, every lane runs a second 32-point
-// FFT (over n1), and the Hermitian split X[k] = E[k] + W_2048^k O[k] recovers bins 0..1024.  No block
+// FFT (over n1), and the Hermitian split X[k] = E[k] + W_2048^k O[k] recovers bins 0..1024 (two at a time).  No block
 // barrier is involved: only __syncwarp.  T is float (feature chains) or double (onset chain, which the
 // reference runs in float64: slicing.py:37,90 promote the gated signal).
 #pragma once
@@ -101,14 +101,15 @@ __device__ void fill_fft_tables(FftTables<T>* tab, const Cpx<T>* __restrict__ g_
 constexpr int kXbufStride = 33;                       // complex elements per row of the transpose buffer
 constexpr int kXbufElems = 32 * kXbufStride;          // per warp
 
-// Forward real FFT of one 2048-sample frame by one warp.
-//   v[n2]   in : z[lane + 32*n2] = (x[2j], x[2j+1]) (already windowed), j = lane + 32*n2
-//   pw[r]   out: |X[32*r + lane]|^2 for r = 0..31 ;  pw_nyq: |X[1024]|^2 (valid on lane 0)
-//   xbuf       : per-warp scratch of kXbufElems complex values
-//   If kKeepSpectrum, the complex bins are left in v[] as X[32*r+lane] -> v[r] (and nyq in *nyq_out).
+// Forward real FFT of one 2048-sample frame by one warp, power spectrum left in shared memory.
+//   v[n2]  in : z[lane + 32*n2] = (x[2j], x[2j+1]) * 0.5 * window, j = lane + 32*n2.  The caller folds the
+//               Hermitian split's factor 1/2 into the window (an exact power-of-two scaling).
+//   xbuf      : per-warp scratch of kXbufElems complex values; on return, reinterpreted as T[],
+//               pbuf[lead + k] = |X[k]|^2 for k = 0..1024 and pbuf[0..lead) = 0.
+// Bins k and 1024-k share E = Z[k] + conj Z[1024-k] and T = W_2048^k * O: |X[k]|^2 = |E+T|^2 and
+// |X[1024-k]|^2 = |E-T|^2, so each lane handles 16 pairs instead of 32 single bins.
 template <typename T>
-__device__ __forceinline__ void warp_rfft2048_power(Cpx<T> (&v)[32], T (&pw)[32], T& pw_nyq,
-                                                    Cpx<T>* xbuf, const FftTables<T>* tab) {
+__device__ __forceinline__ void warp_rfft2048_power(Cpx<T> (&v)[32], Cpx<T>* xbuf, int lead, const FftTables<T>* tab) {
     const int lane = lane_id();
     // pass 1: 32-point FFT over n2 (in registers)
     fft32_dif<T>(v);
@@ -129,25 +130,33 @@ __device__ __forceinline__ void warp_rfft2048_power(Cpx<T> (&v)[32], T (&pw)[32]
 #pragma unroll
     for (int r = 0; r < 32; ++r) xbuf[32 * bitrev5(r) + lane] = v[r];
     __syncwarp();
+    Cpx<T> b[16];
 #pragma unroll
-    for (int k1 = 0; k1 < 32; ++k1) {
+    for (int k1 = 0; k1 < 16; ++k1) b[k1] = xbuf[(1024 - (32 * k1 + lane)) & 1023];     // Z[(1024-k) mod 1024]
+    __syncwarp();                                         // every lane holds its partners: xbuf becomes pbuf
+    T* pbuf = reinterpret_cast<T*>(xbuf);
+    if (lane < lead) pbuf[lane] = (T)0;
+    if (lane < 4) pbuf[lead + 1025 + lane] = (T)0;        // tail read (times zero weights) by the vectorised mel loop
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) {
         const int k = 32 * k1 + lane;
         const Cpx<T> a = v[bitrev5(k1)];
-        const Cpx<T> b = xbuf[(1024 - k) & 1023];            // Z[(1024-k) mod 1024]
         const Cpx<T> w = tab->w2[k];
-        // E = (A + conj B)/2 ; O = -i (A - conj B)/2 ; X = E + W^k O
-        const T er = T(0.5) * (a.x + b.x), ei = T(0.5) * (a.y - b.y);
-        const T orr = T(0.5) * (a.y + b.y), oi = T(-0.5) * (a.x - b.x);
-        const T xr = er + (orr * w.x - oi * w.y);
-        const T xi = ei + (orr * w.y + oi * w.x);
-        pw[k1] = xr * xr + xi * xi;
+        const T er = a.x + b[k1].x, ei = a.y - b[k1].y;   // E = A + conj B
+        const T orr = a.y + b[k1].y, oi = b[k1].x - a.x;  // O = -i (A - conj B)
+        const T tr = orr * w.x - oi * w.y, ti = orr * w.y + oi * w.x;
+        const T pr = er + tr, pi = ei + ti, mr = er - tr, mi = ei - ti;
+        pbuf[lead + k] = pr * pr + pi * pi;
+        pbuf[lead + 1024 - k] = mr * mr + mi * mi;
     }
-    {
-        const Cpx<T> z0 = xbuf[0];
-        const T n = z0.x - z0.y;     // X[1024] = Re Z0 - Im Z0 (X[0] = Re Z0 + Im Z0 comes out of the loop)
-        pw_nyq = n * n;
+    if (lane == 0) {                                      // k = 512 pairs with itself: W^512 = -i
+        const Cpx<T> a = v[bitrev5(16)];
+        const T er = a.x + a.x, oi = (T)0, orr = a.y + a.y;
+        (void)oi;
+        // E = (2 Re a, 0), O = (2 Im a, 0), T = W*O = (0, -2 Im a)
+        pbuf[lead + 512] = er * er + orr * orr;
     }
-    __syncwarp();                    // xbuf may be reused by the caller from here on
+    __syncwarp();
 }
 
 }  // namespace gat

@@ -78,10 +78,10 @@ struct SparseFbDev {
 };
 
 // dense[filter m][bin f] (given strides) -> lane-slot banded form for stft_mel_kernel.
-// Slot q holds filters 32q .. 32q+31.  Each filter is given to the lane equal to its (possibly lowered)
-// band start modulo 32, so that the 32 bands of a slot start in 32 different banks; lowering a start by d
-// costs d zero-weight iterations.  Long filters choose first, and prefer lanes whose earlier slots are short,
-// which keeps the per-lane totals (the warp's loop count) balanced.
+// Slot q holds filters 32q .. 32q+31.  A filter given to lane l has its band start lowered to the nearest
+// value congruent to 4*(l mod 8) modulo 32 (cost: up to 31 zero-weight bins) and its length rounded up to a
+// multiple of 4, so the kernel can use conflict-free 128-bit loads.  Long filters choose first and prefer
+// lanes whose earlier slots are short, which keeps the per-lane totals (the warp's loop count) balanced.
 int build_sparse_fb(SparseFbDev& out, const float* dense, int n_mels, int n_freqs, long long stride_m, long long stride_f) {
     const int n_slots = (n_mels + 31) / 32;
     std::vector<int> first(n_mels), length(n_mels);
@@ -95,6 +95,7 @@ int build_sparse_fb(SparseFbDev& out, const float* dense, int n_mels, int n_freq
     std::vector<int> start(n_slots * 32, 0), len(n_slots * 32, 0), off(n_slots * 32, 0), mel(n_slots * 32, -1);
     std::vector<int> lane_load(32, 0);
     std::vector<float> w;
+    auto lower = [](int f, int lane) { return ((f - 4 * (lane % 8)) % 32 + 32) % 32; };
     for (int q = 0; q < n_slots; ++q) {
         std::vector<int> ids;
         for (int m = 32 * q; m < n_mels && m < 32 * q + 32; ++m) ids.push_back(m);
@@ -104,23 +105,22 @@ int build_sparse_fb(SparseFbDev& out, const float* dense, int n_mels, int n_freq
             int best_lane = -1, best_cost = 1 << 30;
             for (int lane = 0; lane < 32; ++lane) {
                 if (taken[lane]) continue;
-                const int d = ((first[m] - lane) % 32 + 32) % 32;           // lower the start to hit this bank
-                const int cost = lane_load[lane] + length[m] + d;
+                const int cost = lane_load[lane] + (length[m] + lower(first[m], lane) + 3) / 4;
                 if (cost < best_cost) { best_cost = cost; best_lane = lane; }
             }
-            const int d = ((first[m] - best_lane) % 32 + 32) % 32;
+            const int d = lower(first[m], best_lane);
             const int e = q * 32 + best_lane;
+            const int groups = length[m] ? (length[m] + d + 3) / 4 : 0;
             taken[best_lane] = 1;
-            lane_load[best_lane] += length[m] + d;
+            lane_load[best_lane] += groups;
             start[e] = first[m] - d;
-            len[e] = length[m] ? length[m] + d : 0;
+            len[e] = groups;
             mel[e] = m;
-            // weights begin at an offset congruent to the lane as well
-            while ((int)(w.size() % 32) != best_lane) w.push_back(0.0f);
+            while ((int)(w.size() % 32) != 4 * (best_lane % 8)) w.push_back(0.0f);
             off[e] = (int)w.size();
-            for (int k = 0; k < len[e]; ++k) {
+            for (int k = 0; k < 4 * groups; ++k) {
                 const int f = start[e] + k;
-                w.push_back(f >= first[m] ? dense[m * stride_m + (long long)f * stride_f] : 0.0f);
+                w.push_back(f >= first[m] && f < first[m] + length[m] ? dense[m * stride_m + (long long)f * stride_f] : 0.0f);
             }
         }
     }
