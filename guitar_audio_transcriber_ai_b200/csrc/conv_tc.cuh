@@ -36,6 +36,7 @@ struct ConvTcParams {
     int out_planes;                               // 1: write next layer's planes (hi/lo); 0: dense NHWC
     float* out_hi; float* out_lo;
     float slope;
+    long long* debug;                             // optional [grid][8] cycle counters (profiling builds), else nullptr
 };
 
 __host__ __device__ inline int conv_tc_plane_pixels(int Wp) { return kTcGroupPix + 2 * Wp + 2; }
@@ -53,7 +54,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
     using namespace tc;
     constexpr int NKB = CIN / 32;
     constexpr uint32_t W_STAGE = 2 * 8 * COUT * 16;
-    constexpr uint32_t TMEM_COLS = kTcTiles * COUT <= 256 ? 256 : 512;
+    constexpr int ACC = (2 * kTcTiles * COUT <= 512) ? 2 : 1;      // accumulator sets in TMEM (conv2: 2 x 192 columns)
+    constexpr uint32_t TMEM_COLS = ACC * kTcTiles * COUT <= 256 ? 256 : 512;
     extern __shared__ __align__(128) unsigned char smem[];
     const int Wp = p.W + 2, Hp = p.H + 2;
     const int Pg = conv_tc_plane_pixels(Wp);
@@ -62,13 +64,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
     unsigned char* w_buf = a_buf + (size_t)2 * 8 * plane;
     float* staging = reinterpret_cast<float*>(w_buf + (size_t)NSTAGE * W_STAGE);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(staging) + (size_t)kTcGroupPix * kTcStageStride * 4);
-    uint64_t* a_full = bars + 0; uint64_t* a_empty = bars + 1; uint64_t* acc_full = bars + 2; uint64_t* acc_empty = bars + 3;
-    uint64_t* w_full = bars + 4; uint64_t* w_empty = bars + 4 + NSTAGE;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * NSTAGE);
+    uint64_t* a_full = bars + 0; uint64_t* a_empty = bars + 1; uint64_t* acc_full = bars + 2; uint64_t* acc_empty = bars + 4;
+    uint64_t* w_full = bars + 6; uint64_t* w_empty = bars + 6 + NSTAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * NSTAGE);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        mbar_init(a_full, 1); mbar_init(a_empty, 1); mbar_init(acc_full, 1); mbar_init(acc_empty, 4);
+        mbar_init(a_full, 1); mbar_init(a_empty, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1); }
         fence_barrier_init();
     }
@@ -111,40 +114,58 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
         // ===================================================== MMA issuer (single thread)
         if (lane == 0) {
             const uint32_t idesc = idesc_tf32(128, COUT);
-            const uint32_t a_hi = smem_u32(a_buf), a_lo = a_hi + 8 * plane;
+            // Descriptors differ only in their start address: keep the low words as integers and add offsets.
+            // low word = (addr >> 4) | (LBO >> 4) << 16 ; high word = (SBO >> 4) | version 1 at bit 46.
+            constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
+            const uint32_t a_lbo = (plane >> 4) << 16, b_lbo = ((uint32_t)(COUT * 16) >> 4) << 16;
+            const uint32_t a_hi = (smem_u32(a_buf) >> 4) | a_lbo, a_lo = a_hi + ((8 * plane) >> 4);
+            const uint32_t a_step = (2 * plane) >> 4;                     // two 16-byte K chunks per MMA
+            constexpr uint32_t b_step = (2 * COUT * 16) >> 4;
+            auto desc = [](uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; };
             uint32_t it = 0, use = 0, wi = 0;
+            long long t_acc = 0, t_a = 0, t_w = 0, t0 = 0, t_begin = clock64();
             for (int work = blockIdx.x; work < n_work; work += gridDim.x, ++wi) {
-                mbar_wait(acc_empty, (wi & 1) ^ 1);
+                const uint32_t as = wi % ACC;
+                t0 = clock64();
+                mbar_wait(acc_empty + as, ((wi / ACC) & 1) ^ 1);
+                t_acc += clock64() - t0;
                 fence_after_thread_sync();
+                const uint32_t d_base = tmem + as * (uint32_t)(kTcTiles * COUT);
+                uint32_t accumulate = 0;
                 for (int kb = 0; kb < NKB; ++kb, ++it) {
+                    t0 = clock64();
                     mbar_wait(a_full, it & 1);
+                    t_a += clock64() - t0;
                     for (int tap = 0; tap < 9; ++tap, ++use) {
                         const uint32_t st = use % NSTAGE;
+                        t0 = clock64();
                         mbar_wait(w_full + st, (use / NSTAGE) & 1);
+                        t_w += clock64() - t0;
                         fence_after_thread_sync();
-                        const uint32_t w_hi = smem_u32(w_buf) + st * W_STAGE, w_lo = w_hi + 8 * COUT * 16;
-                        const uint32_t row_off = (uint32_t)((tap / 3) * Wp + (tap % 3)) * 16;
+                        const uint32_t row_off = (uint32_t)((tap / 3) * Wp + (tap % 3));          // in 16-byte units
+                        const uint32_t w_hi = ((smem_u32(w_buf) + st * W_STAGE) >> 4) | b_lbo, w_lo = w_hi + ((8 * COUT * 16) >> 4);
 #pragma unroll
-                        for (int g = 0; g < kTcTiles; ++g) {
-                            const uint32_t d = tmem + (uint32_t)(g * COUT);
+                        for (int s = 0; s < 4; ++s) {
+                            const uint64_t dbh = desc(w_hi + s * b_step), dbl = desc(w_lo + s * b_step);
+                            const uint32_t ah = a_hi + row_off + s * a_step, al = a_lo + row_off + s * a_step;
 #pragma unroll
-                            for (int s = 0; s < 4; ++s) {
-                                const uint32_t ao = row_off + (uint32_t)(g * 128) * 16 + (uint32_t)(2 * s) * plane;
-                                const uint32_t bo = (uint32_t)(2 * s) * COUT * 16;
-                                const uint64_t dah = smem_desc_kmajor_noswizzle(a_hi + ao, plane, 128);
-                                const uint64_t dal = smem_desc_kmajor_noswizzle(a_lo + ao, plane, 128);
-                                const uint64_t dbh = smem_desc_kmajor_noswizzle(w_hi + bo, COUT * 16, 128);
-                                const uint64_t dbl = smem_desc_kmajor_noswizzle(w_lo + bo, COUT * 16, 128);
-                                mma_tf32(d, dah, dbh, idesc, (kb | tap | s) != 0 ? 1u : 0u);
-                                mma_tf32(d, dal, dbh, idesc, 1u);
-                                mma_tf32(d, dah, dbl, idesc, 1u);
+                            for (int g = 0; g < kTcTiles; ++g) {
+                                const uint32_t d = d_base + (uint32_t)(g * COUT);
+                                mma_tf32(d, desc(ah + g * 128), dbh, idesc, s == 0 ? accumulate : 1u);
+                                mma_tf32(d, desc(al + g * 128), dbh, idesc, 1u);
+                                mma_tf32(d, desc(ah + g * 128), dbl, idesc, 1u);
                             }
                         }
+                        accumulate = 1;
                         mma_commit(w_empty + st);           // weights of this stage are free once those MMAs retire
                     }
                     mma_commit(a_empty);                    // ... and so is the activation buffer
                 }
-                mma_commit(acc_full);                       // accumulators of the group are complete
+                mma_commit(acc_full + as);                  // accumulators of the group are complete
+            }
+            if (p.debug) {
+                long long* d = p.debug + (long long)blockIdx.x * 8;
+                d[0] = clock64() - t_begin; d[1] = t_acc; d[2] = t_a; d[3] = t_w;
             }
         }
     } else {
@@ -155,17 +176,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
         const int Wp_out = Wpool + 2;
         const long long Pout = (long long)(Hpool + 2) * Wp_out;
         uint32_t wi = 0;
+        long long e_wait = 0, e_total = clock64();
         for (int work = blockIdx.x; work < n_work; work += gridDim.x, ++wi) {
             const int clip = work / p.groups_per_clip, gi = work - clip * p.groups_per_clip;
             int prow = Hpool - gi * (p.R / 2);              // pooled rows produced by this group
             prow = prow < p.R / 2 ? prow : p.R / 2;
-            mbar_wait(acc_full, wi & 1);
+            const uint32_t as = wi % ACC;
+            const uint32_t t_acc = tmem + as * (uint32_t)(kTcTiles * COUT);
+            const long long e0 = clock64();
+            mbar_wait(acc_full + as, (wi / ACC) & 1);
+            e_wait += clock64() - e0;
             fence_after_thread_sync();
             for (int cb = 0; cb < COUT / 32; ++cb) {
 #pragma unroll
                 for (int g = 0; g < kTcTiles; ++g) {
                     float v[32];
-                    tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * COUT + cb * 32), v);
+                    tmem_ld32(t_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * COUT + cb * 32), v);
                     float* dst = staging + (size_t)(g * 128 + quarter * 32 + lane) * kTcStageStride;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) dst[j] = v[j];
@@ -173,7 +199,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
                 if (cb == COUT / 32 - 1) {                  // TMEM fully drained: the next group's MMAs may start
                     fence_before_thread_sync();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty);
+                    if (lane == 0) mbar_arrive(acc_empty + as);
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 const int n_items = prow * Wpool * 8;
@@ -205,6 +231,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
+        }
+        if (p.debug && et == 0) {
+            long long* d = p.debug + (long long)blockIdx.x * 8;
+            d[4] = clock64() - e_total; d[5] = e_wait;
         }
     }
     fence_before_thread_sync();

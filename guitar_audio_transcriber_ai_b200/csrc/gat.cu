@@ -159,7 +159,8 @@ struct gat_ctx {
     DevBuf mlp_params; int mlp_dims[kMlpMaxLayers + 1] = {0}; int mlp_n_linear = 0; int mlp_n_params = 0;
     DevBuf conv_w[3], conv_b[3], fc1_w, fc1_b, fc2_w, fc2_b;
     DevBuf conv_w_tc[3];   // conv2/conv3 weights in the tensor-core operand layout (hi/lo TF32 split)
-    DevBuf fc1_w_tc, feat_planes, hid;
+    DevBuf fc1_w_tc, feat_planes, hid, tc_debug_buf;
+    bool tc_debug = false;
     int conv_ch[4] = {0, 0, 0, 0}; int hidden = 0, classes = 0; bool cnn_loaded = false;
     DevBuf scaler_mean, scaler_scale; int scaler_n = 0;
     float w_mlp = 0.2f, w_cnn = 0.8f;
@@ -198,6 +199,20 @@ extern "C" int32_t gat_mel_frames(const gat_ctx* ctx, int64_t n) { return ctx ? 
             (ctx)->prof.push_back(ProfRec{kn_, pe0_, pe1_});                                  \
         }                                                                                     \
     } while (0)
+
+// Diagnostics: cycle counters of the conv_tc pipeline roles (last launch of each layer), 2 x 148 x 8 int64.
+extern "C" int gat_debug_tc_counters(gat_ctx* c, long long* out_host, int64_t n) {
+    if (!c) return fail("gat_debug_tc_counters: null ctx");
+    if (!out_host) {   // enable
+        if (c->tc_debug_buf.ensure(2 * 148 * 8 * 8)) return 1;
+        GAT_CUDA(cudaMemset(c->tc_debug_buf.p, 0, 2 * 148 * 8 * 8));
+        c->tc_debug = true;
+        return 0;
+    }
+    GAT_CUDA(cudaDeviceSynchronize());
+    GAT_CUDA(cudaMemcpy(out_host, c->tc_debug_buf.p, (size_t)(n < 2 * 148 * 8 ? n : 2 * 148 * 8) * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
 
 extern "C" int gat_profile_begin(gat_ctx* c) {
     if (!c) return fail("gat_profile_begin: null ctx");
@@ -289,7 +304,7 @@ extern "C" void gat_ctx_destroy(gat_ctx* c) {
     DevBuf* all[] = {&c->tw32, &c->w2_32, &c->tw64, &c->w2_64, &c->win_mel, &c->win_mfcc, &c->win64, &c->dct,
                      &c->fb_mel.start, &c->fb_mel.len, &c->fb_mel.off, &c->fb_mel.mel, &c->fb_mel.w,
                      &c->fb_mfcc.start, &c->fb_mfcc.len, &c->fb_mfcc.off, &c->fb_mfcc.mel, &c->fb_mfcc.w,
-                     &c->mlp_params, &c->conv_w_tc[1], &c->conv_w_tc[2], &c->fc1_w_tc, &c->feat_planes, &c->hid, &c->conv_w[0], &c->conv_w[1], &c->conv_w[2], &c->conv_b[0], &c->conv_b[1], &c->conv_b[2],
+                     &c->mlp_params, &c->conv_w_tc[1], &c->conv_w_tc[2], &c->fc1_w_tc, &c->feat_planes, &c->hid, &c->tc_debug_buf, &c->conv_w[0], &c->conv_w[1], &c->conv_w[2], &c->conv_b[0], &c->conv_b[1], &c->conv_b[2],
                      &c->fc1_w, &c->fc1_b, &c->fc2_w, &c->fc2_b, &c->scaler_mean, &c->scaler_scale,
                      &c->clip_scale, &c->spec, &c->spec_max, &c->f0, &c->act1, &c->act2, &c->act3, &c->hz_tmp, &c->logits_cnn, &c->logits_mlp,
                      &c->seg_small, &c->seg_rms, &c->seg_rms_med, &c->seg_gate, &c->seg_env, &c->seg_envn, &c->seg_cand,
@@ -608,12 +623,13 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
         Conv1PlanesParams p1{mel + c0 * H0 * W0, nc, H0, W0, c->conv_w[0].as<float>(), c->conv_b[0].as<float>(), act1_hi, act1_lo, 0.01f};
         LAUNCH(c, conv1_pool_planes_kernel, (unsigned)(nc * ceil_div(H1 * W1, 256)), 256, 0, stream, p1);
         ConvTcParams p2{act1_hi, act1_lo, c->conv_w_tc[1].as<float>(), c->conv_b[1].as<float>(), nc, H1, W1, R2,
-                        ceil_div(H1 / 2, R2 / 2), 1, act2_hi, act2_lo, 0.01f};
+                        ceil_div(H1 / 2, R2 / 2), 1, act2_hi, act2_lo, 0.01f, c->tc_debug ? c->tc_debug_buf.as<long long>() : nullptr};
         const int work2 = nc * p2.groups_per_clip;
         KNAME("conv2_tc_32_64");
         LAUNCH(c, k2, (unsigned)(work2 < c->num_sms ? work2 : c->num_sms), kTcThreads, smem2, stream, p2);
         ConvTcParams p3{act2_hi, act2_lo, c->conv_w_tc[2].as<float>(), c->conv_b[2].as<float>(), nc, H2, W2, R3,
-                        ceil_div(H2 / 2, R3 / 2), 0, c->act3.as<float>() + (size_t)c0 * H3 * W3 * 128, nullptr, 0.01f};
+                        ceil_div(H2 / 2, R3 / 2), 0, c->act3.as<float>() + (size_t)c0 * H3 * W3 * 128, nullptr, 0.01f,
+                        c->tc_debug ? c->tc_debug_buf.as<long long>() + 148 * 8 : nullptr};
         const int work3 = nc * p3.groups_per_clip;
         KNAME("conv3_tc_64_128");
         LAUNCH(c, k3, (unsigned)(work3 < c->num_sms ? work3 : c->num_sms), kTcThreads, smem3, stream, p3);

@@ -157,6 +157,11 @@ int gat_transcribe_clips_host(gat_ctx* ctx, const float* audio_host, int64_t N, 
 int gat_profile_begin(gat_ctx* ctx);
 int gat_profile_end(gat_ctx* ctx, char* buf, int64_t cap);
 
+/* Diagnostics for the tensor-core conv pipeline: call with out_host = NULL to switch the in-kernel cycle
+ * counters on; call again with a buffer of 2*148*8 int64 to read them (conv2 then conv3; per CTA:
+ * MMA-thread total, wait acc_empty, wait a_full, wait w_full, epilogue total, epilogue wait acc_full). */
+int gat_debug_tc_counters(gat_ctx* ctx, long long* out_host, int64_t n);
+
 /* Number of kernels launched through this ctx so far (bench.py's gpu_launches). */
 int64_t gat_launch_count(const gat_ctx* ctx);
 /* classes of the loaded models, frames of the mel image for n samples. */
