@@ -54,4 +54,17 @@ __device__ __forceinline__ long long reflect_index(long long i, long long n) {
 
 __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Asynchronous 4-byte global -> shared copies (LDGSTS): no register staging, completion by group.
+#ifndef GAT_CPU_EMU
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+#else
+inline void cp_async4(float* dst_smem, const float* src) { *dst_smem = *src; }
+inline void cp_async_commit() {}
+inline void cp_async_wait_all() {}
+#endif
+
 }  // namespace gat

@@ -50,6 +50,7 @@ struct StftMelParams {
     const unsigned char* frame_gate;  // onset chain: per 512-sample block keep flag, or nullptr
     float sample_gate;         // onset chain: samples with |y| < sample_gate are zeroed; 0 disables both gates
     int gate_hop;              // samples per frame_gate entry (512)
+    int use_async;             // 1: prefetch the next chunk's samples with cp.async into a raw landing zone
     int hop;
     int n_frames;              // frames per clip = 1 + n / hop
     int pad_mode;
@@ -81,11 +82,12 @@ constexpr int kMaxMelsPerLane = 4;   // n_mels <= 128
 
 // Shared-memory footprint of stft_mel_kernel (bytes), mirrored by the host launcher.
 template <typename T>
-__host__ __device__ inline size_t stft_mel_smem_bytes(int nwarps, int frames_per_cta, int hop, int n_mels, int nnz, bool image) {
+__host__ __device__ inline size_t stft_mel_smem_bytes(int nwarps, int frames_per_cta, int hop, int n_mels, int nnz, bool image, bool async) {
     size_t b = 0;
     b += sizeof(FftTables<T>);
     b += 2048 * sizeof(T);                                               // window
     b += ((size_t)(frames_per_cta - 1) * hop + 2048) * sizeof(T);        // staged samples
+    if (async) b += ((size_t)(frames_per_cta - 1) * hop + 2048 + 8) * sizeof(float);   // raw landing zone (async path)
     b += (size_t)nwarps * kXbufElems * sizeof(Cpx<T>);                   // per-warp transpose buffers
     b += (size_t)4 * kMaxMelsPerLane * 32 * sizeof(int) + (size_t)nnz * sizeof(float); // sparse filterbank (lane slots)
     if (image) b += (size_t)n_mels * (frames_per_cta + 1) * sizeof(T);   // output tile
@@ -105,6 +107,8 @@ __global__ void __launch_bounds__(kThreads, 1) stft_mel_kernel(StftMelParams<T> 
     FftTables<T>* tab = reinterpret_cast<FftTables<T>*>(sp);  sp += sizeof(FftTables<T>);
     T* win = reinterpret_cast<T*>(sp);                        sp += 2048 * sizeof(T);
     T* span = reinterpret_cast<T*>(sp);                       sp += (size_t)span_len * sizeof(T);
+    const bool kAsync = p.use_async != 0;     // prefetch the next chunk's samples with cp.async while this one is transformed
+    float* raw = reinterpret_cast<float*>(sp);                if (kAsync) sp += (size_t)(span_len + 8) * sizeof(float);
     Cpx<T>* xbuf_all = reinterpret_cast<Cpx<T>*>(sp);         sp += (size_t)nwarps * kXbufElems * sizeof(Cpx<T>);
     constexpr int kSlotEntries = kMaxMelsPerLane * 32;
     int* fb_start = reinterpret_cast<int*>(sp);               sp += kSlotEntries * sizeof(int);
@@ -128,6 +132,20 @@ __global__ void __launch_bounds__(kThreads, 1) stft_mel_kernel(StftMelParams<T> 
     T* pbuf = reinterpret_cast<T*>(xbuf);   // 1025 power values alias the transpose buffer
 
     const long long n_work = (long long)p.N * p.chunks_per_clip;
+    // Raw sample range a work item needs: padded index range [t0*hop, t0*hop + need) <-> samples s0 .. s0+need.
+    auto issue_prefetch = [&](long long work) {
+        const int clip = (int)(work / p.chunks_per_clip);
+        const int t0 = (int)(work % p.chunks_per_clip) * FC;
+        const int nf = min(FC, p.n_frames - t0);
+        const long long s0 = (long long)t0 * p.hop - 1024;
+        const long long lo = s0 < 0 ? 0 : s0;
+        long long hi = s0 + (nf - 1) * p.hop + 2048;
+        hi = hi > p.n ? p.n : hi;
+        const float* src = p.audio + (long long)clip * p.n + lo;
+        for (int i = threadIdx.x; i < (int)(hi - lo); i += blockDim.x) cp_async4(raw + i, src + i);
+        cp_async_commit();
+    };
+    if (kAsync && (long long)blockIdx.x < n_work) issue_prefetch(blockIdx.x);
     for (long long work = blockIdx.x; work < n_work; work += gridDim.x) {
         const int clip = (int)(work / p.chunks_per_clip);
         const int chunk = (int)(work % p.chunks_per_clip);
@@ -136,25 +154,28 @@ __global__ void __launch_bounds__(kThreads, 1) stft_mel_kernel(StftMelParams<T> 
         const float* src = p.audio + (long long)clip * p.n;
         const float c = p.clip_scale ? p.clip_scale[clip] : 1.0f;
         const int need = (nf - 1) * p.hop + 2048;
+        const long long s0 = (long long)t0 * p.hop - 1024;
+        const long long lo = s0 < 0 ? 0 : s0;
+        long long hi = s0 + need;
+        hi = hi > p.n ? p.n : hi;
+        if (kAsync) { cp_async_wait_all(); __syncthreads(); }     // this chunk's raw samples have landed
 
         // ---- stage the chunk: centre padding, volume normalisation, (onset chain) the two gates
         for (int i = threadIdx.x; i < need; i += blockDim.x) {
-            long long s = (long long)t0 * p.hop + i - 1024;    // index into the un-padded clip
-            float v;
-            if (p.pad_mode == kPadReflect) {
-                if (s < 0 || s >= p.n) s = reflect_index(s, p.n);
-                v = src[s];
-            } else {
-                v = (s >= 0 && s < p.n) ? src[s] : 0.0f;
-            }
+            long long s = s0 + i;                                  // index into the un-padded clip
+            bool inside = s >= 0 && s < p.n;
+            if (!inside && p.pad_mode == kPadReflect) { s = reflect_index(s, p.n); inside = true; }
+            float v = 0.0f;
+            if (inside) v = (kAsync && s >= lo && s < hi) ? raw[s - lo] : src[s];
             if (p.clip_scale) v = __fdiv_rn(v, c);
-            if (p.sample_gate > 0.0f && s >= 0 && s < p.n) {
+            if (p.sample_gate > 0.0f && inside) {
                 if (!(fabsf(v) >= p.sample_gate)) v = 0.0f;
                 if (p.frame_gate && !p.frame_gate[s / p.gate_hop]) v = 0.0f;
             }
             span[i] = (T)v;
         }
         __syncthreads();
+        if (kAsync && work + gridDim.x < n_work) issue_prefetch(work + gridDim.x);   // overlaps the FFT phase below
 
         T wmax = (T)-1e300;
         for (int f = warp; f < nf; f += nwarps) {

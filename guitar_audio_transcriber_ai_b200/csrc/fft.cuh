@@ -126,14 +126,19 @@ __device__ __forceinline__ void warp_rfft2048_power(Cpx<T> (&v)[32], Cpx<T>* xbu
     for (int n1 = 0; n1 < 32; ++n1) v[n1] = xbuf[lane * kXbufStride + n1];
     __syncwarp();
     fft32_dif<T>(v);
-    // v[bitrev5(k1)] = Z[32*k1 + lane]; publish Z in natural order for the Hermitian split
-#pragma unroll
-    for (int r = 0; r < 32; ++r) xbuf[32 * bitrev5(r) + lane] = v[r];
-    __syncwarp();
+    // v[bitrev5(k1)] = Z[32*k1 + lane].  The Hermitian partner Z[1024-k] of k = 32*k1 + lane sits in lane
+    // (32 - lane) % 32 at k1' = 31 - k1 (lane 0 pairs with itself: k1' = (32 - k1) % 32): one shuffle per value.
     Cpx<T> b[16];
+    const int partner = (32 - lane) & 31;
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) b[k1] = xbuf[(1024 - (32 * k1 + lane)) & 1023];     // Z[(1024-k) mod 1024]
-    __syncwarp();                                         // every lane holds its partners: xbuf becomes pbuf
+    for (int k1 = 0; k1 < 16; ++k1) {
+        const Cpx<T> other = v[bitrev5(31 - k1)];
+        const Cpx<T> self = v[bitrev5((32 - k1) & 31)];
+        const T bx = __shfl_sync(0xffffffffu, other.x, partner);
+        const T by = __shfl_sync(0xffffffffu, other.y, partner);
+        b[k1] = lane == 0 ? self : Cpx<T>{bx, by};
+    }
+    // xbuf was last READ before the second FFT (with a __syncwarp after), so it can take the spectrum now
     T* pbuf = reinterpret_cast<T*>(xbuf);
     if (lane < lead) pbuf[lane] = (T)0;
     if (lane < 4) pbuf[lead + 1025 + lane] = (T)0;        // tail read (times zero weights) by the vectorised mel loop
@@ -151,9 +156,7 @@ __device__ __forceinline__ void warp_rfft2048_power(Cpx<T> (&v)[32], Cpx<T>* xbu
     }
     if (lane == 0) {                                      // k = 512 pairs with itself: W^512 = -i
         const Cpx<T> a = v[bitrev5(16)];
-        const T er = a.x + a.x, oi = (T)0, orr = a.y + a.y;
-        (void)oi;
-        // E = (2 Re a, 0), O = (2 Im a, 0), T = W*O = (0, -2 Im a)
+        const T er = a.x + a.x, orr = a.y + a.y;          // E = (2 Re a, 0), O = (2 Im a, 0), T = W*O = (0, -2 Im a)
         pbuf[lead + 512] = er * er + orr * orr;
     }
     __syncwarp();

@@ -416,10 +416,19 @@ int launch_stft_mel(gat_ctx* c, StftMelParams<T> p, void* stream) {
     int fc = (int)(8192 / p.hop) + 1;
     fc = fc > 32 ? 32 : fc;
     if (sizeof(T) == 8) fc = fc > 8 ? 8 : fc;
+    // Asynchronous prefetch needs a second (raw) copy of the chunk in shared memory: use it when at least one frame
+    // per warp still fits (CNN chain at hop 256: 16 frames), otherwise stage synchronously with the larger chunk.
+    bool async = false;
+    if (sizeof(T) == 4) {
+        int fa = fc;
+        while (fa > nwarps && stft_mel_smem_bytes<T>(nwarps, fa, p.hop, p.fb.n_mels, p.fb.nnz, kOut == kOutImage, true) > 227 * 1024) fa = (fa + 1) / 2;
+        if (fa >= nwarps && stft_mel_smem_bytes<T>(nwarps, fa, p.hop, p.fb.n_mels, p.fb.nnz, kOut == kOutImage, true) <= 227 * 1024) { async = true; fc = fa; }
+    }
+    p.use_async = async ? 1 : 0;
     if (fc > p.n_frames) fc = p.n_frames;
     p.frames_per_cta = fc;
     p.chunks_per_clip = (p.n_frames + fc - 1) / fc;
-    const size_t smem = stft_mel_smem_bytes<T>(nwarps, fc, p.hop, p.fb.n_mels, p.fb.nnz, kOut == kOutImage);
+    const size_t smem = stft_mel_smem_bytes<T>(nwarps, fc, p.hop, p.fb.n_mels, p.fb.nnz, kOut == kOutImage, async);
     if (smem > 227 * 1024) return fail("stft_mel: %zu bytes of shared memory needed (hop %d)", smem, p.hop);
     auto kfn = stft_mel_kernel<T, kOut, kThreads>;
     GAT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
