@@ -734,7 +734,7 @@ extern "C" int gat_segment(gat_ctx* c, const float* y, int64_t L, const gat_slic
     // small scalars: [0..1] spec max (8B) | [2..3] env min/max (16B) | n_peaks | any_nonzero | gate
     if (c->seg_small.ensure(64) || c->seg_rms.ensure((size_t)T * 4) || c->seg_rms_med.ensure((size_t)T * 4) ||
         c->seg_gate.ensure((size_t)T) || c->spec.ensure((size_t)To * 128 * sizeof(double)) ||
-        c->seg_env.ensure((size_t)To * 8) || c->seg_envn.ensure((size_t)To * 8) || c->seg_cand.ensure((size_t)To) ||
+        c->seg_env.ensure((size_t)To * 8) || c->seg_envn.ensure((size_t)To * 8) || c->seg_cand.ensure((size_t)(To / 32 + 2) * 4) ||
         c->seg_peaks.ensure((size_t)To * 4) || c->seg_frames.ensure((size_t)To * 8) ||
         c->seg_table.ensure((size_t)max_onsets * 3 * 8) || c->seg_keep.ensure((size_t)max_onsets) ||
         c->seg_dest.ensure((size_t)max_onsets * 4)) return 1;
@@ -768,7 +768,7 @@ extern "C" int gat_segment(gat_ctx* c, const float* y, int64_t L, const gat_slic
     FluxParams fp{c->spec.as<double>(), spec_max, To, 128, 1 + 2048 / (2 * sp->onset_hop), 80.0, c->seg_env.as<double>(), env_minmax};
     LAUNCH(c, onset_flux_kernel, (unsigned)ceil_div(To, 128), 128, 0, st, fp);
     PeakParams pp{c->seg_env.as<double>(), env_minmax, To, sp->pre_max, sp->post_max, sp->pre_avg, sp->post_avg, sp->wait,
-                  (double)sp->delta, c->seg_envn.as<double>(), c->seg_cand.as<unsigned char>(), n_peaks, c->seg_peaks.as<int>(), any_nonzero};
+                  (double)sp->delta, c->seg_envn.as<double>(), c->seg_cand.as<unsigned>(), n_peaks, c->seg_peaks.as<int>(), any_nonzero};
     LAUNCH(c, peak_candidates_kernel, (unsigned)ceil_div(To, 128), 128, 0, st, pp);
     LAUNCH(c, peak_select_kernel, 1, 32, 0, st, pp);
     if (env_out) GAT_CUDA(cudaMemcpyAsync(env_out, c->seg_envn.p, (size_t)To * 8, cudaMemcpyDeviceToDevice, st));
@@ -778,7 +778,7 @@ extern "C" int gat_segment(gat_ctx* c, const float* y, int64_t L, const gat_slic
                   (long long)sp->min_sep_samples, (long long)sp->attack_skip, (long long)sp->clip_len, max_onsets,
                   n_onsets, (long long*)onsets, c->seg_frames.as<long long>(), c->seg_table.as<long long>()};
     LAUNCH(c, backtrack_kernel, (unsigned)ceil_div(To, 128), 128, 0, st, s);
-    LAUNCH(c, minsep_table_kernel, 1, 32, 0, st, s);
+    LAUNCH(c, minsep_table_kernel, 1, 1024, 0, st, s);
     if (frames_out && n_frames_out) {
         const size_t nb = (size_t)(max_onsets < To ? max_onsets : To) * 8;
         GAT_CUDA(cudaMemcpyAsync(frames_out, c->seg_frames.p, nb, cudaMemcpyDeviceToDevice, st));
@@ -789,7 +789,7 @@ extern "C" int gat_segment(gat_ctx* c, const float* y, int64_t L, const gat_slic
     GatherParams g{y, (long long)L, n_onsets, c->seg_table.as<long long>(), (long long)sp->clip_len, sp->min_slice_rms_db,
                    c->seg_keep.as<unsigned char>(), c->seg_dest.as<int>(), n_clips, clips, (long long*)clip_table, max_onsets};
     LAUNCH(c, slice_loudness_kernel, (unsigned)max_onsets, 256, 0, st, g);
-    LAUNCH(c, slice_compact_kernel, 1, 32, 0, st, g);
+    LAUNCH(c, slice_compact_kernel, 1, 1024, 0, st, g);
     LAUNCH(c, slice_gather_kernel, (unsigned)max_onsets, 256, 0, st, g);
     return 0;
 }

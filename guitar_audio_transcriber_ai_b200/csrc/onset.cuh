@@ -197,53 +197,62 @@ struct PeakParams {
     int pre_max, post_max, pre_avg, post_avg, wait;
     double delta;              // float32(0.07) promoted
     double* envn;              // [T] normalised envelope
-    unsigned char* cand;       // [T]
+    unsigned* cand;            // [ceil(T/32)] bit t%32 of word t/32 = frame t passes both peak_pick tests
     int* n_peaks; int* peaks;  // outputs of peak_select_kernel
     int* any_nonzero;          // [1]
 };
 
 __global__ void peak_candidates_kernel(PeakParams p) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= p.T) return;
-    const double mn = -from_ordered_bits(p.env_minmax[0]);
-    const double mx = from_ordered_bits(p.env_minmax[1]);
-    const double den = __dadd_rn(__dsub_rn(mx, mn), 2.2250738585072014e-308);
-    auto x = [&](int i) { return __ddiv_rn(__dsub_rn(p.env[i], mn), den); };
-    const double xt = x(t);
-    p.envn[t] = xt;
-    if (xt != 0.0) atomicExch(p.any_nonzero, 1);
-    const int lo_m = t == 0 ? 0 : max(0, t - p.pre_max), hi_m = min(t + p.post_max, p.T);
-    double mxw = -1e300;
-    for (int i = lo_m; i < hi_m; ++i) { const double v = x(i); mxw = v > mxw ? v : mxw; }
-    bool ok = t == 0 ? (xt >= mxw) : (xt == mxw);
-    if (ok) {
-        const int lo_a = t == 0 ? 0 : max(0, t - p.pre_avg), hi_a = min(t + p.post_avg, p.T);
-        double acc = 0.0;
-        for (int i = lo_a; i < hi_a; ++i) acc = __dadd_rn(acc, x(i));
-        const double avg = __ddiv_rn(acc, (double)(hi_a - lo_a));
-        ok = xt >= __dadd_rn(avg, p.delta);
+    bool ok = false;
+    if (t < p.T) {
+        const double mn = -from_ordered_bits(p.env_minmax[0]);
+        const double mx = from_ordered_bits(p.env_minmax[1]);
+        const double den = __dadd_rn(__dsub_rn(mx, mn), 2.2250738585072014e-308);
+        auto x = [&](int i) { return __ddiv_rn(__dsub_rn(p.env[i], mn), den); };
+        const double xt = x(t);
+        p.envn[t] = xt;
+        if (xt != 0.0) atomicExch(p.any_nonzero, 1);
+        const int lo_m = t == 0 ? 0 : max(0, t - p.pre_max), hi_m = min(t + p.post_max, p.T);
+        double mxw = -1e300;
+        for (int i = lo_m; i < hi_m; ++i) { const double v = x(i); mxw = v > mxw ? v : mxw; }
+        ok = t == 0 ? (xt >= mxw) : (xt == mxw);
+        if (ok) {
+            const int lo_a = t == 0 ? 0 : max(0, t - p.pre_avg), hi_a = min(t + p.post_avg, p.T);
+            double acc = 0.0;
+            for (int i = lo_a; i < hi_a; ++i) acc = __dadd_rn(acc, x(i));
+            const double avg = __ddiv_rn(acc, (double)(hi_a - lo_a));
+            ok = xt >= __dadd_rn(avg, p.delta);
+        }
     }
-    p.cand[t] = ok ? 1 : 0;
+    const unsigned m = __ballot_sync(0xffffffffu, ok);       // blockDim is a multiple of 32: word t/32 belongs to this warp
+    if (lane_id() == 0 && t < p.T) p.cand[t >> 5] = m;
 }
 
-// Sequential `wait` rule: after a peak at n the next frame examined is n + wait + 1.  One warp walks the
-// candidate flags 32 at a time with a ballot; only set bits cost serial work.
-__global__ void peak_select_kernel(PeakParams p) {
+// Sequential `wait` rule: after a peak at n the next frame examined is n + wait + 1.  One warp: each lane
+// pulls one 32-frame mask word (1024 frames per coalesced load); words without candidates are skipped with a
+// ballot, set bits are walked in order.  Candidates are sparse (one per note), so this is a few microseconds.
+__global__ void __launch_bounds__(32) peak_select_kernel(PeakParams p) {
     const int lane = lane_id();
-    int count = 0;
-    int next_ok = 0;                       // first frame index that may be examined
     if (*p.any_nonzero == 0) { if (lane == 0) *p.n_peaks = 0; return; }
-    for (int base = 0; base < p.T; base += 32) {
-        const int t = base + lane;
-        unsigned m = __ballot_sync(0xffffffffu, t < p.T && p.cand[t]);
-        while (m) {
-            const int b = __ffs((int)m) - 1;
-            m &= m - 1;
-            const int n = base + b;
-            if (n >= next_ok) {
-                if (lane == 0) p.peaks[count] = n;
-                ++count;
-                next_ok = n + p.wait + 1;
+    const int n_words = (p.T + 31) >> 5;
+    int count = 0, next_ok = 0;
+    for (int w0 = 0; w0 < n_words; w0 += 32) {
+        const unsigned mine = w0 + lane < n_words ? p.cand[w0 + lane] : 0u;
+        unsigned live = __ballot_sync(0xffffffffu, mine != 0u);
+        while (live) {
+            const int src = __ffs((int)live) - 1;
+            live &= live - 1;
+            unsigned m = __shfl_sync(0xffffffffu, mine, src);
+            while (m) {
+                const int b = __ffs((int)m) - 1;
+                m &= m - 1;
+                const int n = ((w0 + src) << 5) + b;
+                if (n >= next_ok && n < p.T) {
+                    if (lane == 0) p.peaks[count] = n;
+                    ++count;
+                    next_ok = n + p.wait + 1;
+                }
             }
         }
     }
@@ -277,17 +286,37 @@ __global__ void backtrack_kernel(SliceParams p) {
     p.frames_bt[i] = f;
 }
 
-__global__ void minsep_table_kernel(SliceParams p) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// Greedy minimum separation is sequential in the kept onset, but cheap once the inputs sit in shared memory:
+// the CTA stages the backtracked frames tile by tile, thread 0 runs the greedy rule, then all threads build
+// the slice table in parallel.
+constexpr int kSepTile = 4096;
+
+__global__ void __launch_bounds__(1024) minsep_table_kernel(SliceParams p) {
+    __shared__ long long tile[kSepTile];
+    __shared__ int s_k;
+    __shared__ long long s_last;
     const int n = *p.n_peaks;
-    int k = 0;
-    long long last = -999999;
-    for (int i = 0; i < n; ++i) {
-        const long long s = p.frames_bt[i] * p.hop;
-        if (s - last >= p.min_sep_samples && k < p.max_onsets) { p.onsets[k++] = s; last = s; }
+    if (threadIdx.x == 0) { s_k = 0; s_last = -999999; }
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += kSepTile) {
+        const int nt = min(kSepTile, n - i0);
+        for (int i = threadIdx.x; i < nt; i += blockDim.x) tile[i] = p.frames_bt[i0 + i] * p.hop;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int k = s_k; long long last = s_last;
+            for (int i = 0; i < nt; ++i) {
+                const long long s = tile[i];
+                if (s - last >= p.min_sep_samples && k < p.max_onsets) { p.onsets[k++] = s; last = s; }
+            }
+            s_k = k; s_last = last;
+        }
+        __syncthreads();
     }
-    *p.n_onsets = k;
-    for (int i = 0; i < k; ++i) {
+    const int k = s_k;
+    if (threadIdx.x == 0) *p.n_onsets = k;
+    __threadfence_block();
+    __syncthreads();
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
         const long long next = i + 1 < k ? p.onsets[i + 1] : p.onsets[k - 1];
         const long long start = p.onsets[i] + p.skip;
         const long long end = (start + p.length < next) ? start + p.length : next;
@@ -337,20 +366,41 @@ __global__ void slice_loudness_kernel(GatherParams p) {
     }
 }
 
-__global__ void slice_compact_kernel(GatherParams p) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// Order-preserving compaction of the kept clips: one CTA, chunked block scan of the keep flags.
+__global__ void __launch_bounds__(1024) slice_compact_kernel(GatherParams p) {
+    __shared__ int warp_tot[32];
+    __shared__ int s_base;
     const int n = *p.n_onsets;
-    int k = 0;
-    for (int i = 0; i < n; ++i) {
-        p.dest[i] = p.keep[i] ? k : -1;
-        if (p.keep[i]) {
-            p.clip_table[3 * k + 0] = i;
-            p.clip_table[3 * k + 1] = p.table[3 * i];
-            p.clip_table[3 * k + 2] = p.table[3 * i + 1];
-            ++k;
+    const int lane = lane_id(), warp = warp_id();
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += (int)blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        const int keep = i < n ? (int)p.keep[i] : 0;
+        int incl = keep;                                    // inclusive scan inside the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
         }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < warp; ++w) before += warp_tot[w];
+        const int k = before + incl - keep;
+        if (i < n) {
+            p.dest[i] = keep ? k : -1;
+            if (keep) {
+                p.clip_table[3 * k + 0] = i;
+                p.clip_table[3 * k + 1] = p.table[3 * i];
+                p.clip_table[3 * k + 2] = p.table[3 * i + 1];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_base = before + incl;
+        __syncthreads();
     }
-    *p.n_clips = k;
+    if (threadIdx.x == 0) *p.n_clips = s_base;
 }
 
 __global__ void slice_gather_kernel(GatherParams p) {

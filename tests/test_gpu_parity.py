@@ -120,6 +120,43 @@ def test_segmentation_exact(tr22, golden_phrases):
         assert np.abs(r["rms_db"].cpu().numpy() - g[f"rms_db_{k}"]).max() <= 5e-5
 
 
+def test_long_audio_segmentation_exact(tr22):
+    """Two minutes of audio (24 phrases): global dB max / percentile / min-max dependencies at a non-trivial
+    scale, onsets and slice table still identical to the CPU oracle."""
+    import port
+    from guitar_audio_transcriber_ai_b200 import synth
+    y, _, _ = synth.long_audio(24, 22050, seed0=300)
+    want_onsets, want_clips, want_table = port.slice_in_memory(y, 22050, 0.5)
+    r = tr22.engine.segment(y, 0.5)
+    assert r["onsets"].cpu().numpy().tolist() == want_onsets
+    assert np.array_equal(r["table"].cpu().numpy(), want_table)
+    assert np.array_equal(r["clips"].cpu().numpy(), want_clips)          # gathered samples are copies: bit-exact
+
+
+def test_full_hour_segmentation_properties(tr22):
+    """BASELINE config 4 at full size (720 phrases = 1 h): invariants of slicing.py:106-161 that need no oracle."""
+    from guitar_audio_transcriber_ai_b200 import synth
+    y, _, _ = synth.long_audio(720, 22050, seed0=0)
+    yd = torch.from_numpy(y).cuda()
+    r1 = tr22.engine.segment(yd, 0.5)
+    r2 = tr22.engine.segment(yd, 0.5)
+    on = r1["onsets"].cpu().numpy()
+    tab = r1["table"].cpu().numpy()
+    assert np.array_equal(on, r2["onsets"].cpu().numpy()) and torch.equal(r1["clips"], r2["clips"])     # deterministic
+    assert len(on) > 5000 and np.all(on % 512 == 0)                      # frames_to_samples: multiples of the hop
+    assert np.all(np.diff(on) >= int(0.3 * 22050))                       # greedy minimum separation
+    assert len(tab) <= len(on) - 1                                       # the last onset never yields a clip
+    skip, length = int(0.1 * 22050), int(0.5 * 22050)
+    assert np.array_equal(tab[:, 1], on[tab[:, 0]] + skip)               # start = onset + attack skip
+    nxt = on[np.minimum(tab[:, 0] + 1, len(on) - 1)]
+    assert np.array_equal(tab[:, 2], np.minimum(tab[:, 1] + length, nxt))
+    clips = r1["clips"].cpu().numpy()
+    k = 1234
+    assert np.array_equal(clips[k, : tab[k, 2] - tab[k, 1]], y[tab[k, 1]: tab[k, 2]]) and not clips[k, tab[k, 2] - tab[k, 1]:].any()
+    rms_db = 20 * np.log10(np.sqrt((clips.astype(np.float64) ** 2).mean(1)) + 1e-10)
+    assert np.all(rms_db > -37.0 - 1e-3)                                 # every kept slice passed the loudness test
+
+
 def test_transcribe_audio_matches_reference_pipeline(tr22, golden_phrases):
     from guitar_audio_transcriber_ai_b200 import synth
     g = golden_phrases
