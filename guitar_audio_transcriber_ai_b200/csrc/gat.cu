@@ -476,7 +476,7 @@ int launch_yin(gat_ctx* c, const YinParams& p, void* stream) {
     const size_t smem = (size_t)(threads / 32) * yin_smem_per_warp<kLPT>() + 64;
     auto kfn = yin_kernel<kLPT>;
     GAT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long work = (long long)p.N * p.T;
+    const long long work = (long long)p.N * ((p.T + p.seg_frames - 1) / p.seg_frames);
     const long long ctas = (work + threads / 32 - 1) / (threads / 32);
     const unsigned grid = (unsigned)(ctas < c->num_sms ? ctas : c->num_sms);
     KNAME("yin_kernel");
@@ -499,6 +499,7 @@ int run_yin(gat_ctx* c, const float* audio, int64_t N, int64_t n, bool normalize
     p.max_period = mp < kYinFrame - kYinWin - 1 ? mp : kYinFrame - kYinWin - 1;
     if (p.min_period < 1 || p.max_period <= p.min_period + 1) return fail("yin: period range [%d, %d] unusable", p.min_period, p.max_period);
     p.trough_threshold = c->cfg.yin_trough_threshold; p.f0 = f0;
+    p.seg_frames = T < 11 ? T : 11;          // one extra block of work per segment: 12/11 blocks per frame instead of 2
     const int lags = p.max_period + 1;
     int rc;
     if (lags <= 7 * 32) rc = launch_yin<7>(c, p, stream);

@@ -2,12 +2,14 @@
 //
 // librosa builds the difference function from an FFT autocorrelation,
 //     d[tau] = E[0] + E[tau] - 2 acf[tau],  acf[tau] = sum_{j=1..W} x[j] x[j+tau],  E[tau] = sum_{j=tau+1..tau+W} x[j]^2
-// with W = 1024 inside frames of 2048 (hop 512, zero centre padding).  Here each warp owns one frame held
-// in shared memory and evaluates acf directly as a register-tiled sliding dot product: lane l owns the
-// kLPT consecutive lags [kLPT*l, kLPT*l + kLPT) and keeps the kLPT-sample window x[j+lag] in a register
-// ring, so one broadcast load + one window load feed kLPT FMAs.  The cumulative-mean normalisation,
-// trough search and parabolic refinement follow librosa's dtypes: d in float32, CMND and shifts in
-// float64 (float32 / int64 promotes), f0 = sr / period in float64.
+// with W = 1024 inside frames of 2048 (hop 512, zero centre padding).  Here acf is evaluated directly as a
+// register-tiled sliding dot product: lane l owns the kLPT consecutive lags [kLPT*l, kLPT*l + kLPT) and keeps
+// the kLPT-sample window x[j+lag] in a register ring, so one broadcast load + one window load feed kLPT FMAs.
+// Consecutive frames overlap by half a window (hop = W/2), so the sums are formed per 512-sample BLOCK and a
+// frame is the sum of two consecutive block partials: a warp walks a segment of frames of one clip and does
+// one block of work per frame instead of two.  The cumulative-mean normalisation, trough search and parabolic
+// refinement follow librosa's dtypes: d in float32, CMND and shifts in float64 (float32 / int64 promotes),
+// f0 = sr / period in float64.
 #pragma once
 #include "common.cuh"
 
@@ -19,20 +21,22 @@ struct YinParams {
     int N;
     const float* clip_scale;  // divide samples by this per-clip value first (memory path), or nullptr
     int T;                    // frames = 1 + n / 512
-    int hop;                  // 512
+    int hop;                  // 512 (= kYinWin / 2: the block decomposition relies on it)
     int sr;
     int min_period, max_period;
     double trough_threshold;  // 0.1
+    int seg_frames;           // frames per work item
     double* f0;               // [N][T]
 };
 
 constexpr int kYinFrame = 2048;
 constexpr int kYinWin = 1024;
-constexpr int kYinXs = 2240;          // frame + zero tail so the register ring can read ahead
+constexpr int kYinBlock = 512;
+constexpr int kYinBuf = 3072;         // floats of padded signal a warp keeps in shared memory
 
 template <int kLPT>
 __host__ __device__ inline size_t yin_smem_per_warp() {
-    return kYinXs * sizeof(float) + (size_t)32 * kLPT * sizeof(double);
+    return kYinBuf * sizeof(float) + (size_t)32 * kLPT * sizeof(double);
 }
 
 template <int kLPT>
@@ -41,116 +45,157 @@ __global__ void __launch_bounds__(384, 1) yin_kernel(YinParams p) {
     const int nwarps = blockDim.x >> 5;
     const int lane = lane_id(), warp = warp_id();
     unsigned char* base = smem_raw + (size_t)warp * yin_smem_per_warp<kLPT>();
-    float* xs = reinterpret_cast<float*>(base);
-    double* yv = reinterpret_cast<double*>(xs + kYinXs);            // CMND, index tau - min_period
+    float* buf = reinterpret_cast<float*>(base);
+    double* yv = reinterpret_cast<double*>(buf + kYinBuf);          // CMND, index tau - min_period
     const int nl = p.max_period - p.min_period + 1;
     const double tiny = 1.1754943508222875e-38;                    // np.finfo(float32).tiny
+    // samples a block needs, counted from the start of the PREVIOUS block (whose frame is finalised with it)
+    constexpr int kSpan = 2 * kYinBlock + 33 * kLPT + 1;
+    constexpr int kBlocksPerFill = (kYinBuf - kSpan) / kYinBlock + 1;
+    static_assert(kSpan <= kYinBuf, "kYinBuf too small for this lag tile");
 
-    const long long n_work = (long long)p.N * p.T;
+    const int n_seg = (p.T + p.seg_frames - 1) / p.seg_frames;
+    const long long n_work = (long long)p.N * n_seg;
     for (long long work = (long long)blockIdx.x * nwarps + warp; work < n_work; work += (long long)gridDim.x * nwarps) {
-        const int clip = (int)(work / p.T), t = (int)(work % p.T);
+        const int clip = (int)(work / n_seg);
+        const int f0 = (int)(work % n_seg) * p.seg_frames;
+        const int nf = min(p.seg_frames, p.T - f0);
         const float* src = p.audio + (long long)clip * p.n;
         const float c = p.clip_scale ? p.clip_scale[clip] : 1.0f;
-        for (int i = lane; i < kYinXs; i += 32) {
-            const long long s = (long long)t * p.hop + i - kYinFrame / 2;
-            float v = (i < kYinFrame && s >= 0 && s < p.n) ? src[s] : 0.0f;
+        auto padded = [&](long long i) {                            // centre-padded, normalised signal
+            const long long s = i - kYinFrame / 2;
+            float v = (s >= 0 && s < p.n) ? src[s] : 0.0f;
             if (p.clip_scale) v = __fdiv_rn(v, c);
-            xs[i] = v;
-        }
-        __syncwarp();
+            return v;
+        };
+        const int b = kLPT * lane;                                  // this lane's first lag
+        float prev_acc[kLPT], prev_e = 0.0f;
+#pragma unroll
+        for (int q = 0; q < kLPT; ++q) prev_acc[q] = 0.0f;
+        long long buf_base = 0;                                     // padded index of buf[0]
+        int fill_left = 0;
 
-        // ---- sliding dot products for this lane's lags b .. b+kLPT-1
-        const int b = kLPT * lane;
-        float ring[kLPT], acc[kLPT];
-#pragma unroll
-        for (int q = 0; q < kLPT; ++q) { ring[q] = xs[b + 1 + q]; acc[q] = 0.0f; }
-        float e_b = 0.0f;                                           // E[b] = sum_j x[j+b]^2
-        for (int j0 = 1; j0 <= kYinWin; j0 += kLPT) {
-#pragma unroll
-            for (int s = 0; s < kLPT; ++s) {
-                const int j = j0 + s;
-                const bool in = j <= kYinWin;
-                const float xj = in ? xs[j] : 0.0f;
-#pragma unroll
-                for (int i = 0; i < kLPT; ++i) acc[i] = fmaf(xj, ring[(s + i) % kLPT], acc[i]);
-                if (in) e_b = fmaf(ring[s], ring[s], e_b);
-                ring[s] = xs[b + j + kLPT];
+        for (int blk = f0; blk <= f0 + nf; ++blk) {
+            // ---- keep padded[512*(blk-1) .. +kSpan) resident
+            if (fill_left == 0) {
+                __syncwarp();
+                const long long nb = (long long)kYinBlock * (blk - 1);
+                if (blk == f0) {
+                    for (int i = lane; i < kYinBuf; i += 32) buf[i] = padded(nb + i);
+                } else {                                            // slide: keep the tail, load the rest
+                    // the shift is a multiple of 32, so every address is read and later overwritten by the SAME
+                    // lane: program order makes the in-place forward copy safe without a staging array
+                    const int keep = (int)(buf_base + kYinBuf - nb), off = kYinBuf - keep;
+                    for (int i = lane; i < keep; i += 32) buf[i] = buf[i + off];
+                    for (int i = keep + lane; i < kYinBuf; i += 32) buf[i] = padded(nb + i);
+                }
+                buf_base = nb;
+                fill_left = kBlocksPerFill;
+                __syncwarp();
             }
-        }
-        // ---- d[tau] = (E0 + E[tau]) - 2 acf[tau] in float32, with librosa's 1e-6 dead zones
-        float e0 = __shfl_sync(0xffffffffu, e_b, 0);
-        if (fabsf(e0) < 1e-6f) e0 = 0.0f;
-        float e_tau = e_b;
-        float dl[kLPT];
-#pragma unroll
-        for (int i = 0; i < kLPT; ++i) {
-            const int tau = b + i;
-            float a = acc[i];
-            if (fabsf(a) < 1e-6f) a = 0.0f;
-            float e = e_tau;
-            if (fabsf(e) < 1e-6f) e = 0.0f;
-            dl[i] = __fsub_rn(__fadd_rn(e0, e), __fmul_rn(2.0f, a));
-            // slide the energy window to the next lag: E[tau+1] = E[tau] + x[tau+1025]^2 - x[tau+1]^2
-            const float xin = xs[tau + kYinWin + 1], xout = xs[tau + 1];
-            e_tau = e_tau + xin * xin - xout * xout;
-        }
-        // ---- cumulative sum over tau = 1..max_period (blocked: in-lane sequential + warp scan of lane totals)
-        float run = 0.0f, cl[kLPT];
-#pragma unroll
-        for (int i = 0; i < kLPT; ++i) {
-            const int tau = b + i;
-            if (tau >= 1 && tau <= p.max_period) run += dl[i];
-            cl[i] = run;
-        }
-        float offs = run;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const float u = __shfl_up_sync(0xffffffffu, offs, o);
-            if (lane >= o) offs += u;
-        }
-        offs -= run;                                                // exclusive prefix of lane totals
-#pragma unroll
-        for (int i = 0; i < kLPT; ++i) {
-            const int tau = b + i;
-            if (tau >= p.min_period && tau <= p.max_period) {
-                const double cm = (double)(offs + cl[i]) / (double)tau;
-                yv[tau - p.min_period] = (double)dl[i] / (cm + tiny);
-            }
-        }
-        __syncwarp();
+            --fill_left;
+            const float* xs = buf + (int)((long long)kYinBlock * blk - buf_base);    // xs[j] = padded[512*blk + j]
 
-        // ---- first trough under the threshold, else the global minimum (first occurrence)
-        int first = 0x7fffffff;
-        double best = 1e300; int best_i = 0x7fffffff;
-        for (int i = lane; i < nl; i += 32) {
-            const double y0 = yv[i];
-            bool trough;
-            if (i == 0) trough = nl > 1 && y0 < yv[1];
-            else if (i == nl - 1) trough = y0 < yv[i - 1];
-            else trough = (y0 < yv[i - 1]) && (y0 <= yv[i + 1]);
-            if (trough && y0 < p.trough_threshold && i < first) first = i;
-            if (y0 < best) { best = y0; best_i = i; }
-        }
+            // ---- block partials: acc[i] = sum_{j=1..512} xs[j] xs[j + b + i],  e_blk = sum_j xs[j + b]^2
+            float ring[kLPT], acc[kLPT];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const int f2 = __shfl_xor_sync(0xffffffffu, first, o);
-            first = f2 < first ? f2 : first;
-            const double b2 = __shfl_xor_sync(0xffffffffu, best, o);
-            const int i2 = __shfl_xor_sync(0xffffffffu, best_i, o);
-            if (b2 < best || (b2 == best && i2 < best_i)) { best = b2; best_i = i2; }
-        }
-        if (lane == 0) {
-            const int idx = first != 0x7fffffff ? first : (best_i != 0x7fffffff ? best_i : 0);
-            double shift = 0.0;
-            if (idx > 0 && idx < nl - 1) {
-                const double ym = yv[idx - 1], y0 = yv[idx], yp = yv[idx + 1];
-                const double a = yp + ym - 2.0 * y0;
-                const double bb = (yp - ym) / 2.0;
-                if (!(fabs(bb) >= fabs(a))) shift = -bb / a;
+            for (int q = 0; q < kLPT; ++q) { ring[q] = xs[b + 1 + q]; acc[q] = 0.0f; }
+            float e_blk = 0.0f;
+            for (int j0 = 1; j0 <= kYinBlock; j0 += kLPT) {
+#pragma unroll
+                for (int s = 0; s < kLPT; ++s) {
+                    const int j = j0 + s;
+                    const bool in = j <= kYinBlock;
+                    const float xj = in ? xs[j] : 0.0f;
+#pragma unroll
+                    for (int i = 0; i < kLPT; ++i) acc[i] = fmaf(xj, ring[(s + i) % kLPT], acc[i]);
+                    if (in) e_blk = fmaf(ring[s], ring[s], e_blk);
+                    ring[s] = xs[b + j + kLPT];
+                }
             }
-            p.f0[(long long)clip * p.T + t] = (double)p.sr / ((double)(p.min_period + idx) + shift);
+            if (blk > f0) {
+                // ---- frame t = blk - 1: acf = previous block + this block
+                const int t = blk - 1;
+                const float* fx = xs - kYinBlock;                   // fx[j] = padded[512*t + j]
+                float e_b = prev_e + e_blk;                         // E[b] = sum_{j=1..1024} x[j+b]^2
+                // d[tau] = (E0 + E[tau]) - 2 acf[tau] in float32, with librosa's 1e-6 dead zones
+                float e0 = __shfl_sync(0xffffffffu, e_b, 0);
+                if (fabsf(e0) < 1e-6f) e0 = 0.0f;
+                float e_tau = e_b;
+                float dl[kLPT];
+#pragma unroll
+                for (int i = 0; i < kLPT; ++i) {
+                    const int tau = b + i;
+                    float a = prev_acc[i] + acc[i];
+                    if (fabsf(a) < 1e-6f) a = 0.0f;
+                    float e = e_tau;
+                    if (fabsf(e) < 1e-6f) e = 0.0f;
+                    dl[i] = __fsub_rn(__fadd_rn(e0, e), __fmul_rn(2.0f, a));
+                    // slide the energy window to the next lag: E[tau+1] = E[tau] + x[tau+1025]^2 - x[tau+1]^2
+                    const float xin = fx[tau + kYinWin + 1], xout = fx[tau + 1];
+                    e_tau = e_tau + xin * xin - xout * xout;
+                }
+                // cumulative sum over tau = 1..max_period (blocked: in-lane sequential + warp scan of lane totals)
+                float run = 0.0f, cl[kLPT];
+#pragma unroll
+                for (int i = 0; i < kLPT; ++i) {
+                    const int tau = b + i;
+                    if (tau >= 1 && tau <= p.max_period) run += dl[i];
+                    cl[i] = run;
+                }
+                float offs = run;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float u = __shfl_up_sync(0xffffffffu, offs, o);
+                    if (lane >= o) offs += u;
+                }
+                offs -= run;                                        // exclusive prefix of lane totals
+#pragma unroll
+                for (int i = 0; i < kLPT; ++i) {
+                    const int tau = b + i;
+                    if (tau >= p.min_period && tau <= p.max_period) {
+                        const double cm = (double)(offs + cl[i]) / (double)tau;
+                        yv[tau - p.min_period] = (double)dl[i] / (cm + tiny);
+                    }
+                }
+                __syncwarp();
+                // first trough under the threshold, else the global minimum (first occurrence)
+                int first = 0x7fffffff;
+                double best = 1e300; int best_i = 0x7fffffff;
+                for (int i = lane; i < nl; i += 32) {
+                    const double y0 = yv[i];
+                    bool trough;
+                    if (i == 0) trough = nl > 1 && y0 < yv[1];
+                    else if (i == nl - 1) trough = y0 < yv[i - 1];
+                    else trough = (y0 < yv[i - 1]) && (y0 <= yv[i + 1]);
+                    if (trough && y0 < p.trough_threshold && i < first) first = i;
+                    if (y0 < best) { best = y0; best_i = i; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const int f2 = __shfl_xor_sync(0xffffffffu, first, o);
+                    first = f2 < first ? f2 : first;
+                    const double b2 = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int i2 = __shfl_xor_sync(0xffffffffu, best_i, o);
+                    if (b2 < best || (b2 == best && i2 < best_i)) { best = b2; best_i = i2; }
+                }
+                if (lane == 0) {
+                    const int idx = first != 0x7fffffff ? first : (best_i != 0x7fffffff ? best_i : 0);
+                    double shift = 0.0;
+                    if (idx > 0 && idx < nl - 1) {
+                        const double ym = yv[idx - 1], y0 = yv[idx], yp = yv[idx + 1];
+                        const double aa = yp + ym - 2.0 * y0;
+                        const double bb = (yp - ym) / 2.0;
+                        if (!(fabs(bb) >= fabs(aa))) shift = -bb / aa;
+                    }
+                    p.f0[(long long)clip * p.T + t] = (double)p.sr / ((double)(p.min_period + idx) + shift);
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int q = 0; q < kLPT; ++q) prev_acc[q] = acc[q];
+            prev_e = e_blk;
         }
-        __syncwarp();
     }
 }
 
