@@ -161,6 +161,8 @@ struct gat_ctx {
     DevBuf conv_w_tc[3];   // conv2/conv3 weights in the tensor-core operand layout (hi/lo TF32 split)
     DevBuf fc1_w_tc, feat_planes, hid, tc_debug_buf;
     bool tc_debug = false;
+    int conv_pass_mult = 16;  // clips per conv pass = conv_pass_mult * num_sms; measured on B200: long passes win (5.84 ms at 1, 5.21 at 14,
+                              // 5.15 at 28 per 4096 clips) - per-launch head/tail costs outweigh keeping activations inside the L2
     int conv_ch[4] = {0, 0, 0, 0}; int hidden = 0, classes = 0; bool cnn_loaded = false;
     DevBuf scaler_mean, scaler_scale; int scaler_n = 0;
     float w_mlp = 0.2f, w_cnn = 0.8f;
@@ -211,6 +213,12 @@ extern "C" int gat_debug_tc_counters(gat_ctx* c, long long* out_host, int64_t n)
     }
     GAT_CUDA(cudaDeviceSynchronize());
     GAT_CUDA(cudaMemcpy(out_host, c->tc_debug_buf.p, (size_t)(n < 2 * 148 * 8 ? n : 2 * 148 * 8) * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int gat_set_conv_pass(gat_ctx* c, int32_t mult) {
+    if (!c || mult < 1 || mult > 64) return fail("gat_set_conv_pass: bad argument");
+    c->conv_pass_mult = mult;
     return 0;
 }
 
@@ -608,7 +616,8 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
     const size_t smem2 = conv_tc_smem_bytes<64>(W1 + 2, 3), smem3 = conv_tc_smem_bytes<128>(W2 + 2, 2);
     if (R2 < 2 || R3 < 2 || smem2 > 227 * 1024 || smem3 > 227 * 1024)
         return fail("infer: mel image of %d frames is too wide for the tensor-core conv tiling of this build", W0);
-    const long long chunk = N < c->num_sms ? N : c->num_sms;
+    const long long per_pass = (long long)c->num_sms * c->conv_pass_mult;
+    const long long chunk = N < per_pass ? N : per_pass;
     const size_t P1 = (size_t)(H1 + 2) * (W1 + 2), P2 = (size_t)(H2 + 2) * (W2 + 2);
     const size_t a1 = (size_t)chunk * 8 * P1 * 4 * 4, a2 = (size_t)chunk * 16 * P2 * 4 * 4;   // bytes of ONE of hi/lo
     const size_t a3 = (size_t)N * H3 * W3 * 128 * 4;

@@ -157,6 +157,9 @@ int gat_transcribe_clips_host(gat_ctx* ctx, const float* audio_host, int64_t N, 
 int gat_profile_begin(gat_ctx* ctx);
 int gat_profile_end(gat_ctx* ctx, char* buf, int64_t cap);
 
+/* Clips per CNN pass = mult * (number of SMs); default 16 (2368 clips, ~1.4 GB of activation planes at T = 87). */
+int gat_set_conv_pass(gat_ctx* ctx, int32_t mult);
+
 /* Diagnostics for the tensor-core conv pipeline: call with out_host = NULL to switch the in-kernel cycle
  * counters on; call again with a buffer of 2*148*8 int64 to read them (conv2 then conv3; per CTA:
  * MMA-thread total, wait acc_empty, wait a_full, wait w_full, epilogue total, epilogue wait acc_full). */
