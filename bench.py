@@ -108,7 +108,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_pass(clips: np.ndarray, cnn_ck) -> None:
+def cpu_reference_pass(clips: np.ndarray, cnn_ck):
     """The reference's path for this workload on the host: MelFeatureBuilder.extract_melspec_features' per-clip
     loop (features.py:307-331) followed by ONE batched CNN forward + softmax + argmax (note_predictor.py:102-123)."""
     sys.path.insert(0, str(ROOT / "oracle"))
@@ -117,7 +117,7 @@ def cpu_reference_pass(clips: np.ndarray, cnn_ck) -> None:
         specs = [port.melspec_image(c, SR) for c in clips]
         X = torch.stack(specs, dim=0)
         probs = torch.softmax(port.cnn_forward(cnn_ck["model"], X), dim=-1).numpy()
-    np.argmax(probs, axis=1)
+    return np.argmax(probs, axis=1)
 
 
 def run_reference(args):
@@ -285,10 +285,13 @@ def run_ours(args):
         sub = host[:sample].numpy()
         cpu_reference_pass(sub[:16], cnn_ck)
         t0 = time.perf_counter()
-        cpu_reference_pass(sub, cnn_ck)
+        cpu_labels = cpu_reference_pass(sub, cnn_ck)
         dt = time.perf_counter() - t0
+        # the same pass doubles as a parity guard: the CPU oracle's labels for these clips vs the timed CUDA path's
+        mismatches = int((cpu_labels != rec[:sample, 0].cpu().numpy()).sum())
         cpu_baseline = {"value": sample * CLIP_SECONDS / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"first {sample} of the 4096 clips, one pass, {dt:.1f} s (oracle port: per-clip torchaudio mel loop + one batched torch CNN forward)"}
+                        "sample": f"first {sample} of the 4096 clips, one pass, {dt:.1f} s (oracle port: per-clip torchaudio mel loop + one batched torch CNN forward)",
+                        "labels_compared": sample, "label_mismatches": mismatches}
 
     if rank == 0:
         print(json.dumps({

@@ -14,6 +14,9 @@
 //   every 2x2 pooling window is inside the group: the epilogue moves 32 channels at a time TMEM -> registers ->
 //   shared staging, pools, adds the BN-folded bias, applies LeakyReLU and writes the next layer's planes
 //   (already split hi/lo) or the dense NHWC tensor the classifier head reads.
+// * Wide images (long clips) are cut into column blocks of `cw` output columns: the group's rows are then staged
+//   as R+2 separate row segments of `seg` = cw+2 pixels and a tap is (ky*seg + kx) pixels further.  When one
+//   block spans the full width (seg = W+2) the rows are contiguous in HBM and each plane is ONE bulk copy.
 #pragma once
 #ifndef GAT_CPU_EMU
 #include "common.cuh"
@@ -31,19 +34,22 @@ struct ConvTcParams {
     const float* w;                               // [9 taps][CIN/32][hi|lo][8 chunks][COUT][4]
     const float* bias;                            // [COUT] (BatchNorm folded)
     int n_clips, H, W;                            // conv input size without the border; Hp = H+2, Wp = W+2
-    int R;                                        // image rows per group (even, R*Wp <= 384)
-    int groups_per_clip;
+    int R;                                        // image rows per group (even, R*seg <= 384)
+    int seg;                                      // staged pixels per row = cw + 2 (= W + 2 when one block spans the width)
+    int cw;                                       // output columns per column block (even unless there is one block)
+    int col_blocks;
+    int groups_per_clip;                          // row blocks * col_blocks
     int out_planes;                               // 1: write next layer's planes (hi/lo); 0: dense NHWC
     float* out_hi; float* out_lo;
     float slope;
     long long* debug;                             // optional [grid][8] cycle counters (profiling builds), else nullptr
 };
 
-__host__ __device__ inline int conv_tc_plane_pixels(int Wp) { return kTcGroupPix + 2 * Wp + 2; }
+__host__ __device__ inline int conv_tc_plane_pixels(int seg) { return kTcGroupPix + 2 * seg + 2; }
 
 template <int COUT>
-__host__ __device__ inline size_t conv_tc_smem_bytes(int Wp, int nstage) {
-    return (size_t)2 * 8 * conv_tc_plane_pixels(Wp) * 16          // A: hi|lo x 8 chunks x plane
+__host__ __device__ inline size_t conv_tc_smem_bytes(int seg, int nstage) {
+    return (size_t)2 * 8 * conv_tc_plane_pixels(seg) * 16          // A: hi|lo x 8 chunks x plane
          + (size_t)nstage * 2 * 8 * COUT * 16                      // weight ring
          + (size_t)kTcGroupPix * kTcStageStride * 4                // epilogue staging
          + 256;                                                    // barriers, tmem slot, alignment
@@ -58,7 +64,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
     constexpr uint32_t TMEM_COLS = ACC * kTcTiles * COUT <= 256 ? 256 : 512;
     extern __shared__ __align__(128) unsigned char smem[];
     const int Wp = p.W + 2, Hp = p.H + 2;
-    const int Pg = conv_tc_plane_pixels(Wp);
+    const int seg = p.seg;
+    const int Pg = conv_tc_plane_pixels(seg);
+    const bool contiguous = p.col_blocks == 1 && seg == Wp;
     const uint32_t plane = (uint32_t)Pg * 16;
     unsigned char* a_buf = smem;                                   // [part][chunk][Pg][16 B]
     unsigned char* w_buf = a_buf + (size_t)2 * 8 * plane;
@@ -90,15 +98,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
             uint32_t it = 0, use = 0;
             for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
                 const int clip = work / p.groups_per_clip, gi = work - clip * p.groups_per_clip;
-                const long long q_start = (long long)(gi * p.R) * Wp - 1;      // (y0-1)*Wp - 1 with y0 = 1 + gi*R
+                const int rb = gi / p.col_blocks, cb = gi - rb * p.col_blocks;
+                // first staged pixel: row y0-1, column xs-2 (one pixel of slack so tap offsets are never negative)
+                const long long q_start = (long long)(rb * p.R) * Wp + (long long)cb * p.cw - 1;
                 for (int kb = 0; kb < NKB; ++kb, ++it) {
                     mbar_wait(a_empty, (it & 1) ^ 1);
-                    mbar_expect_tx(a_full, 16 * plane);
-                    for (int part = 0; part < 2; ++part) {
-                        const float* src = part ? p.in_lo : p.in_hi;
-                        for (int c = 0; c < 8; ++c) {
-                            const long long pl = (long long)clip * (CIN / 4) + kb * 8 + c;
-                            bulk_g2s(a_buf + (size_t)(part * 8 + c) * plane, src + (pl * plane_pix + q_start) * 4, plane, a_full);
+                    if (contiguous) {
+                        mbar_expect_tx(a_full, 16 * plane);
+                        for (int part = 0; part < 2; ++part) {
+                            const float* src = part ? p.in_lo : p.in_hi;
+                            for (int c = 0; c < 8; ++c) {
+                                const long long pl = (long long)clip * (CIN / 4) + kb * 8 + c;
+                                bulk_g2s(a_buf + (size_t)(part * 8 + c) * plane, src + (pl * plane_pix + q_start) * 4, plane, a_full);
+                            }
+                        }
+                    } else {                                   // R+2 row segments per plane, each seg pixels from column xs-1;
+                        const uint32_t row_bytes = (uint32_t)seg * 16;   // slot 0 of the plane stays the unused slack pixel
+                        mbar_expect_tx(a_full, 16 * (uint32_t)(p.R + 2) * row_bytes);
+                        for (int part = 0; part < 2; ++part) {
+                            const float* src = part ? p.in_lo : p.in_hi;
+                            for (int c = 0; c < 8; ++c) {
+                                const long long pl = (long long)clip * (CIN / 4) + kb * 8 + c;
+                                for (int a = 0; a < p.R + 2; ++a)
+                                    bulk_g2s(a_buf + (size_t)(part * 8 + c) * plane + (size_t)(1 + a * seg) * 16,
+                                             src + (pl * plane_pix + q_start + 1 + (long long)a * Wp) * 4, row_bytes, a_full);
+                            }
                         }
                     }
                     for (int tap = 0; tap < 9; ++tap, ++use) {
@@ -142,7 +166,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
                         mbar_wait(w_full + st, (use / NSTAGE) & 1);
                         t_w += clock64() - t0;
                         fence_after_thread_sync();
-                        const uint32_t row_off = (uint32_t)((tap / 3) * Wp + (tap % 3));          // in 16-byte units
+                        const uint32_t row_off = (uint32_t)((tap / 3) * seg + (tap % 3));         // in 16-byte units
                         const uint32_t w_hi = ((smem_u32(w_buf) + st * W_STAGE) >> 4) | b_lbo, w_lo = w_hi + ((8 * COUT * 16) >> 4);
 #pragma unroll
                         for (int s = 0; s < 4; ++s) {
@@ -179,8 +203,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
         long long e_wait = 0, e_total = clock64();
         for (int work = blockIdx.x; work < n_work; work += gridDim.x, ++wi) {
             const int clip = work / p.groups_per_clip, gi = work - clip * p.groups_per_clip;
-            int prow = Hpool - gi * (p.R / 2);              // pooled rows produced by this group
+            const int rb = gi / p.col_blocks, colb = gi - rb * p.col_blocks;
+            int prow = Hpool - rb * (p.R / 2);              // pooled rows produced by this group
             prow = prow < p.R / 2 ? prow : p.R / 2;
+            int pcol = Wpool - colb * (p.cw / 2);             // pooled columns produced by this group
+            pcol = pcol < p.cw / 2 ? pcol : p.cw / 2;
             const uint32_t as = wi % ACC;
             const uint32_t t_acc = tmem + as * (uint32_t)(kTcTiles * COUT);
             const long long e0 = clock64();
@@ -202,13 +229,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
                     if (lane == 0) mbar_arrive(acc_empty + as);
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                const int n_items = prow * Wpool * 8;
+                const int n_items = prow * pcol * 8;
                 for (int item = et; item < n_items; item += 128) {
-                    const int px = item % Wpool;
-                    const int rest = item / Wpool;
+                    const int pxl = item % pcol;
+                    const int rest = item / pcol;
                     const int r = rest % prow, ch = rest / prow;
-                    const float* s00 = staging + (size_t)(2 * r * Wp + 1 + 2 * px) * kTcStageStride + ch * 4;
-                    const float* s10 = s00 + (size_t)Wp * kTcStageStride;
+                    const int px = colb * (p.cw / 2) + pxl;
+                    const float* s00 = staging + (size_t)(2 * r * seg + 1 + 2 * pxl) * kTcStageStride + ch * 4;
+                    const float* s10 = s00 + (size_t)seg * kTcStageStride;
                     float o[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -216,7 +244,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
                         const float z = m + __ldg(p.bias + cb * 32 + ch * 4 + e);
                         o[e] = z > 0.0f ? z : z * p.slope;
                     }
-                    const int Y = gi * (p.R / 2) + r;
+                    const int Y = rb * (p.R / 2) + r;
                     if (p.out_planes) {
                         const long long chunk_out = (long long)clip * (COUT / 4) + cb * 8 + ch;
                         const long long off = (chunk_out * Pout + (long long)(Y + 1) * Wp_out + px + 1) * 4;

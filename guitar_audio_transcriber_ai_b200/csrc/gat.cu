@@ -601,10 +601,28 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
 // and act1+act2 (hi/lo planes, ~0.6 MB per clip at T = 87) stay inside the 126 MB L2 between layers.
 constexpr size_t kActGuard = 65536;   // bytes before/after the plane buffers: halo reads of edge groups stay in bounds
 
-inline int conv_tc_rows(int H, int Wp) {
-    int R = 2 * (kTcGroupPix / (2 * Wp));
+// Tiling of one conv layer: column blocks of `cw` output columns (one block spanning the width when the staged
+// planes fit in shared memory), R image rows per group so that R * seg <= 384 tile pixels.
+struct ConvTiling { int seg, cw, col_blocks, R, groups_per_clip; size_t smem; };
+
+template <int COUT>
+ConvTiling conv_tc_tiling(int H, int W, int nstage) {
+    ConvTiling t{};
+    const size_t budget = 227 * 1024;
+    int seg = W + 2;
+    if (conv_tc_smem_bytes<COUT>(seg, nstage) <= budget && 2 * seg <= kTcGroupPix) {
+        t.seg = seg; t.cw = W; t.col_blocks = 1;
+    } else {
+        seg = 4;
+        while (conv_tc_smem_bytes<COUT>(seg + 2, nstage) <= budget && 2 * (seg + 2) <= kTcGroupPix) seg += 2;   // even
+        t.seg = seg; t.cw = seg - 2; t.col_blocks = (W + t.cw - 1) / t.cw;
+    }
+    int R = 2 * (kTcGroupPix / (2 * t.seg));
     const int hmax = 2 * (H / 2);
-    return R < hmax ? R : hmax;
+    t.R = R < hmax ? R : hmax;
+    t.groups_per_clip = t.R >= 2 ? ceil_div(H / 2, t.R / 2) * t.col_blocks : 0;
+    t.smem = conv_tc_smem_bytes<COUT>(t.seg, nstage);
+    return t;
 }
 
 int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, float* cnn_logits, void* stream) {
@@ -612,10 +630,10 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
     const int H0 = c->cfg.mel_n_mels, W0 = T;
     const int H1 = H0 / 2, W1 = W0 / 2, H2 = H1 / 2, W2 = W1 / 2, H3 = H2 / 2, W3 = W2 / 2;
     if (H3 < 1 || W3 < 1) return fail("infer: mel image %dx%d too small for three 2x2 pools", H0, W0);
-    const int R2 = conv_tc_rows(H1, W1 + 2), R3 = conv_tc_rows(H2, W2 + 2);
-    const size_t smem2 = conv_tc_smem_bytes<64>(W1 + 2, 3), smem3 = conv_tc_smem_bytes<128>(W2 + 2, 2);
-    if (R2 < 2 || R3 < 2 || smem2 > 227 * 1024 || smem3 > 227 * 1024)
-        return fail("infer: mel image of %d frames is too wide for the tensor-core conv tiling of this build", W0);
+    const ConvTiling t2 = conv_tc_tiling<64>(H1, W1, 3), t3 = conv_tc_tiling<128>(H2, W2, 2);
+    if (t2.R < 2 || t3.R < 2 || t2.smem > 227 * 1024 || t3.smem > 227 * 1024)
+        return fail("infer: no tensor-core conv tiling for a mel image of %d x %d", H0, W0);
+    const size_t smem2 = t2.smem, smem3 = t3.smem;
     const long long per_pass = (long long)c->num_sms * c->conv_pass_mult;
     const long long chunk = N < per_pass ? N : per_pass;
     const size_t P1 = (size_t)(H1 + 2) * (W1 + 2), P2 = (size_t)(H2 + 2) * (W2 + 2);
@@ -641,13 +659,13 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
         const int nc = (int)(N - c0 < chunk ? N - c0 : chunk);
         Conv1PlanesParams p1{mel + c0 * H0 * W0, nc, H0, W0, c->conv_w[0].as<float>(), c->conv_b[0].as<float>(), act1_hi, act1_lo, 0.01f};
         LAUNCH(c, conv1_pool_planes_kernel, (unsigned)(nc * ceil_div(H1 * W1, 256)), 256, 0, stream, p1);
-        ConvTcParams p2{act1_hi, act1_lo, c->conv_w_tc[1].as<float>(), c->conv_b[1].as<float>(), nc, H1, W1, R2,
-                        ceil_div(H1 / 2, R2 / 2), 1, act2_hi, act2_lo, 0.01f, c->tc_debug ? c->tc_debug_buf.as<long long>() : nullptr};
+        ConvTcParams p2{act1_hi, act1_lo, c->conv_w_tc[1].as<float>(), c->conv_b[1].as<float>(), nc, H1, W1, t2.R,
+                        t2.seg, t2.cw, t2.col_blocks, t2.groups_per_clip, 1, act2_hi, act2_lo, 0.01f, c->tc_debug ? c->tc_debug_buf.as<long long>() : nullptr};
         const int work2 = nc * p2.groups_per_clip;
         KNAME("conv2_tc_32_64");
         LAUNCH(c, k2, (unsigned)(work2 < c->num_sms ? work2 : c->num_sms), kTcThreads, smem2, stream, p2);
-        ConvTcParams p3{act2_hi, act2_lo, c->conv_w_tc[2].as<float>(), c->conv_b[2].as<float>(), nc, H2, W2, R3,
-                        ceil_div(H2 / 2, R3 / 2), 0, c->act3.as<float>() + (size_t)c0 * H3 * W3 * 128, nullptr, 0.01f,
+        ConvTcParams p3{act2_hi, act2_lo, c->conv_w_tc[2].as<float>(), c->conv_b[2].as<float>(), nc, H2, W2, t3.R,
+                        t3.seg, t3.cw, t3.col_blocks, t3.groups_per_clip, 0, c->act3.as<float>() + (size_t)c0 * H3 * W3 * 128, nullptr, 0.01f,
                         c->tc_debug ? c->tc_debug_buf.as<long long>() + 148 * 8 : nullptr};
         const int work3 = nc * p3.groups_per_clip;
         KNAME("conv3_tc_64_128");

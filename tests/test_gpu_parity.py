@@ -186,6 +186,27 @@ def test_live_oracle_on_fresh_inputs(tr22):
         assert np.abs(got["probs"][i] - want["probs"][0]).max() <= 5e-5
 
 
+@pytest.mark.parametrize("dur", [2.0, 4.0])
+def test_long_clips_against_oracle(dur, tr22):
+    """BASELINE config 5 durations: 2 s and 4 s clips (mel images 64x173 / 64x345) exercise the column-blocked conv
+    tiling, multi-chunk STFT staging and longer YIN / MFCC reductions."""
+    import port
+    from guitar_audio_transcriber_ai_b200 import synth
+    from guitar_audio_transcriber_ai_b200.checkpoint import load_checkpoint
+    mlp_ck, cnn_ck = load_checkpoint(CKPT / "mlp_synth_sr22050.ckpt"), load_checkpoint(CKPT / "cnn_synth_sr22050.ckpt")
+    clips, _ = synth.clip_batch(5, dur, 22050, seed0=int(dur * 1000))
+    got = tr22.transcribe_notes(clips, dur, 22050)
+    out = tr22.engine.transcribe_clips(clips, yin_on_normalized=True, return_features=True)
+    for i in range(len(clips)):
+        want = port.transcribe_note(mlp_ck, cnn_ck, clips[i], dur, 22050)
+        mf, ms = port.extract_inference_features_from_audio(clips[i], 22050)
+        assert mel_ok(out["mel"][i].cpu().numpy(), ms[0]) and mfcc_ok(out["mfcc"][i, :64].cpu().numpy(), mf[0, :64])
+        assert abs(float(out["mfcc"][i, 64]) - mf[0, 64]) <= 2e-6
+        assert str(got["labels"][i]) == str(want["labels"][0])
+        assert np.abs(got["per_model_probs"]["cnn"][i] - want["per_model_probs"]["cnn"][0]).max() <= 5e-5
+        assert np.abs(got["probs"][i] - want["probs"][0]).max() <= 5e-5
+
+
 def test_edge_cases_against_oracle(tr22):
     import port
     from guitar_audio_transcriber_ai_b200 import synth
