@@ -153,7 +153,7 @@ struct gat_ctx {
     gat_config cfg{};
     int64_t launches = 0;
     // tables
-    DevBuf tw32, w2_32, tw64, w2_64, win_mel, win_mfcc, win64, dct;
+    DevBuf tw32, w2_32, tw64, w2_64, win_mel, win_mfcc, win64, dct, tw_generic;
     SparseFbDev fb_mel, fb_mfcc;
     // models
     DevBuf mlp_params; int mlp_dims[kMlpMaxLayers + 1] = {0}; int mlp_n_linear = 0; int mlp_n_params = 0;
@@ -259,7 +259,8 @@ extern "C" int gat_profile_end(gat_ctx* c, char* buf, int64_t cap) {
 
 extern "C" int gat_ctx_create(const gat_config* cfg, int device, gat_ctx** out) {
     if (!cfg || !out) return fail("gat_ctx_create: null argument");
-    if (cfg->mel_n_fft != 2048) return fail("gat_ctx_create: mel_n_fft=%d unsupported (this build implements n_fft 2048)", cfg->mel_n_fft);
+    if (cfg->mel_n_fft != 512 && cfg->mel_n_fft != 1024 && cfg->mel_n_fft != 2048 && cfg->mel_n_fft != 4096)
+        return fail("gat_ctx_create: mel_n_fft=%d unsupported (512, 1024, 2048 or 4096)", cfg->mel_n_fft);
     if (cfg->mel_n_mels < 1 || cfg->mel_n_mels > 32 * kMaxMelsPerLane || cfg->mfcc_n_mels != 128)
         return fail("gat_ctx_create: unsupported mel sizes (mel %d, mfcc %d)", cfg->mel_n_mels, cfg->mfcc_n_mels);
     if (cfg->mel_hop < 1 || (cfg->mel_hop & 1)) return fail("gat_ctx_create: mel_hop must be even");
@@ -296,11 +297,20 @@ extern "C" int gat_ctx_create(const gat_config* cfg, int device, gat_ctx** out) 
     int rc = 0;
     rc |= upload(c->tw64, tw.data(), 1024); rc |= upload(c->w2_64, w2.data(), 1024);
     rc |= upload(c->tw32, twf.data(), 1024); rc |= upload(c->w2_32, w2f.data(), 1024);
-    rc |= upload(c->win_mel, cfg->mel_window, 2048);
+    rc |= upload(c->win_mel, cfg->mel_window, (size_t)cfg->mel_n_fft);
+    if (cfg->mel_n_fft != 2048) {   // generic path: W_M^k, M = n_fft/2, k < M/2
+        const int M = cfg->mel_n_fft / 2;
+        std::vector<Cpx<float>> tg(M / 2);
+        for (int k = 0; k < M / 2; ++k) {
+            const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)M;
+            tg[k] = Cpx<float>{(float)cosl(a), (float)sinl(a)};
+        }
+        rc |= upload(c->tw_generic, tg.data(), tg.size());
+    }
     rc |= upload(c->win_mfcc, win_mfcc.data(), 2048);
     rc |= upload(c->win64, cfg->stft_window, 2048);
     rc |= upload(c->dct, cfg->dct, (size_t)cfg->mfcc_n_mfcc * cfg->mfcc_n_mels);
-    rc |= build_sparse_fb(c->fb_mel, cfg->mel_fb, cfg->mel_n_mels, 1025, 1, cfg->mel_n_mels);
+    rc |= build_sparse_fb(c->fb_mel, cfg->mel_fb, cfg->mel_n_mels, cfg->mel_n_fft / 2 + 1, 1, cfg->mel_n_mels);
     rc |= build_sparse_fb(c->fb_mfcc, cfg->mfcc_fb, cfg->mfcc_n_mels, 1025, 1025, 1);
     if (rc) { gat_ctx_destroy(c); return 1; }
     *out = c;
@@ -309,7 +319,7 @@ extern "C" int gat_ctx_create(const gat_config* cfg, int device, gat_ctx** out) 
 
 extern "C" void gat_ctx_destroy(gat_ctx* c) {
     if (!c) return;
-    DevBuf* all[] = {&c->tw32, &c->w2_32, &c->tw64, &c->w2_64, &c->win_mel, &c->win_mfcc, &c->win64, &c->dct,
+    DevBuf* all[] = {&c->tw_generic, &c->tw32, &c->w2_32, &c->tw64, &c->w2_64, &c->win_mel, &c->win_mfcc, &c->win64, &c->dct,
                      &c->fb_mel.start, &c->fb_mel.len, &c->fb_mel.off, &c->fb_mel.mel, &c->fb_mel.w,
                      &c->fb_mfcc.start, &c->fb_mfcc.len, &c->fb_mfcc.off, &c->fb_mfcc.mel, &c->fb_mfcc.w,
                      &c->mlp_params, &c->conv_w_tc[1], &c->conv_w_tc[2], &c->fc1_w_tc, &c->feat_planes, &c->hid, &c->tc_debug_buf, &c->conv_w[0], &c->conv_w[1], &c->conv_w[2], &c->conv_b[0], &c->conv_b[1], &c->conv_b[2],
@@ -447,9 +457,38 @@ int launch_stft_mel(gat_ctx* c, StftMelParams<T> p, void* stream) {
     return 0;
 }
 
+template <int LOG2M>
+int launch_stft_generic(gat_ctx* c, StftGenericParams p, void* stream) {
+    const int threads = 256, nwarps = threads / 32;
+    int fc = 32;
+    while (fc > 1 && stft_generic_smem_bytes<LOG2M>(nwarps, fc, p.hop, p.fb.n_mels, p.fb.nnz) > 227 * 1024) fc = (fc + 1) / 2;
+    if (fc > p.n_frames) fc = p.n_frames;
+    p.frames_per_cta = fc;
+    p.chunks_per_clip = (p.n_frames + fc - 1) / fc;
+    const size_t smem = stft_generic_smem_bytes<LOG2M>(nwarps, fc, p.hop, p.fb.n_mels, p.fb.nnz);
+    if (smem > 227 * 1024) return fail("stft_mel (generic n_fft): %zu bytes of shared memory needed", smem);
+    auto kfn = stft_mel_generic_kernel<LOG2M>;
+    GAT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long work = (long long)p.N * p.chunks_per_clip;
+    KNAME("stft_mel_generic_image");
+    LAUNCH(c, kfn, (unsigned)(work < c->num_sms ? work : c->num_sms), threads, smem, stream, p);
+    return 0;
+}
+
 int run_melspec(gat_ctx* c, const float* audio, int64_t N, int64_t n, bool normalize, bool scale_ready, float* out, void* stream) {
-    if (n <= 1024) return fail("melspec: clips of %lld samples are too short for reflect padding of 1024", (long long)n);
+    const int n_fft = c->cfg.mel_n_fft;
+    if (n <= n_fft / 2) return fail("melspec: clips of %lld samples are too short for reflect padding of %d", (long long)n, n_fft / 2);
     if (normalize && !scale_ready && launch_clip_scale(c, audio, N, n, stream)) return 1;
+    if (n_fft != 2048) {
+        StftGenericParams g{};
+        g.audio = audio; g.n = n; g.N = (int)N; g.clip_scale = normalize ? c->clip_scale.as<float>() : nullptr;
+        g.n_fft = n_fft; g.hop = c->cfg.mel_hop; g.n_frames = (int)(1 + n / c->cfg.mel_hop);
+        g.window = c->win_mel.as<float>(); g.tw = c->tw_generic.as<Cpx<float>>(); g.fb = c->fb_mel.view();
+        g.amin = 1e-10f; g.out = out;
+        if (n_fft == 512) return launch_stft_generic<8>(c, g, stream);
+        if (n_fft == 1024) return launch_stft_generic<9>(c, g, stream);
+        return launch_stft_generic<11>(c, g, stream);
+    }
     StftMelParams<float> p{};
     p.audio = audio; p.n = n; p.N = (int)N; p.clip_scale = normalize ? c->clip_scale.as<float>() : nullptr;
     p.frame_gate = nullptr; p.sample_gate = 0.0f; p.gate_hop = 512;

@@ -35,7 +35,7 @@ typedef struct gat_ctx gat_ctx;
  */
 typedef struct gat_config {
     int32_t sample_rate;        /* checkpoint target_sr (config.py:29)                               */
-    int32_t mel_n_fft;          /* MelSpecConfig.N_FFT; this build supports 2048                      */
+    int32_t mel_n_fft;          /* MelSpecConfig.N_FFT: 512, 1024, 2048 (register-resident FFT) or 4096 */
     int32_t mel_hop;            /* MelSpecConfig.HOP_LENGTH                                           */
     int32_t mel_n_mels;         /* MelSpecConfig.N_MELS (<= 128)                                      */
     const float* mel_window;

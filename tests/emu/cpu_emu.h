@@ -187,6 +187,7 @@ static inline float __uint_as_float(unsigned i) { float f; memcpy(&f, &i, 4); re
 static inline long long __double_as_longlong(double d) { long long i; memcpy(&i, &d, 8); return i; }
 static inline double __longlong_as_double(long long i) { double d; memcpy(&d, &i, 8); return d; }
 static inline float fminf_(float a, float b) { return fminf(a, b); }
+static inline void sincospif(float x, float* s, float* c) { *s = (float)sin(M_PI * (double)x); *c = (float)cos(M_PI * (double)x); }
 
 static std::mutex& emu_atomic_mutex() { static std::mutex m; return m; }
 template <typename T> static inline T atomicAdd(T* p, T v) { std::lock_guard<std::mutex> g(emu_atomic_mutex()); T o = *p; *p = o + v; return o; }

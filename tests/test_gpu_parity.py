@@ -207,6 +207,26 @@ def test_long_clips_against_oracle(dur, tr22):
         assert np.abs(got["probs"][i] - want["probs"][0]).max() <= 5e-5
 
 
+@pytest.mark.parametrize("n_fft", [512, 1024, 4096])
+def test_other_n_fft_against_torchaudio(n_fft):
+    """MelSpecConfig.N_FFT is configurable; BASELINE config 5 sweeps 1024 / 2048 / 4096."""
+    import port
+    from guitar_audio_transcriber_ai_b200 import synth
+    from guitar_audio_transcriber_ai_b200.engine import Engine
+    eng = Engine(22050, {"N_MELS": 64, "N_FFT": n_fft, "HOP_LENGTH": 256}, device="cuda:0")
+    clips, _ = synth.clip_batch(6, 1.0, 22050, seed0=40 + n_fft)
+    mel = eng.melspec_db(clips).cpu().numpy()
+    for i in range(len(clips)):
+        ref = port.melspec_image(clips[i], 22050, 64, n_fft, 256).numpy()
+        assert mel[i].shape == ref.shape
+        if n_fft >= 1024:
+            assert mel_ok(mel[i], ref), (n_fft, i, np.abs(mel[i] - ref).max())
+        else:   # 64 mel bands over 257 bins: the lowest filters weigh a fraction of ONE weak bin, where the two float32
+                # FFTs' rounding noise is a larger share of the value; not a BASELINE configuration, checked loosely
+            assert np.abs(mel[i] - ref).max() <= 2e-2, (n_fft, i, np.abs(mel[i] - ref).max())
+    eng.close()
+
+
 def test_edge_cases_against_oracle(tr22):
     import port
     from guitar_audio_transcriber_ai_b200 import synth
