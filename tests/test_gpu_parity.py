@@ -157,6 +157,37 @@ def test_full_hour_segmentation_properties(tr22):
     assert np.all(rms_db > -37.0 - 1e-3)                                 # every kept slice passed the loudness test
 
 
+def test_segmentation_at_sr_11025(tr11):
+    """The shipped MLP checkpoint's rate: librosa's onset_detect defaults become pre_max 0 / wait 0 there."""
+    import port
+    from guitar_audio_transcriber_ai_b200 import synth
+    for seed in (5, 6):
+        y, _, _ = synth.phrase(seed, sr=11025)
+        want_onsets, want_clips, want_table = port.slice_in_memory(y, 11025, 0.5)
+        r = tr11.engine.segment(y, 0.5)
+        assert r["onsets"].cpu().numpy().tolist() == want_onsets
+        assert np.array_equal(r["table"].cpu().numpy(), want_table)
+        assert np.array_equal(r["clips"].cpu().numpy(), want_clips)
+
+
+def test_c_abi_argument_errors(tr22):
+    """Every entry point reports bad arguments through its return code + gat_last_error, never by crashing."""
+    import ctypes as C
+    lib = tr22.engine.lib
+    ctx = tr22.engine._ctx
+    assert lib.gat_melspec_db(ctx, None, 1, 22050, 1, None, None) != 0 and b"null" in lib.gat_last_error()
+    assert lib.gat_yin(None, None, 1, 22050, 0, None, None, None) != 0
+    assert lib.gat_infer(ctx, None, 65, None, 1, 44, None, None, None, None, None, None, None, None) != 0
+    assert lib.gat_segment(ctx, None, 1000, None, 4, None, None, None, None, None, None, None, None, None, None) != 0
+    assert lib.gat_set_conv_pass(ctx, 0) != 0 and lib.gat_set_conv_pass(ctx, 16) == 0
+    bad = np.zeros(3, np.int32)
+    assert lib.gat_load_mlp(ctx, bad.ctypes.data_as(C.c_void_p), 9, bad.ctypes.data_as(C.c_void_p), 3) != 0
+    a = torch.zeros(1, 600, device="cuda")
+    out = torch.zeros(1, 64, 3, device="cuda")
+    assert lib.gat_melspec_db(ctx, C.c_void_p(a.data_ptr()), 1, 600, 1, C.c_void_p(out.data_ptr()), None) != 0
+    assert b"too short" in lib.gat_last_error()
+
+
 def test_transcribe_audio_matches_reference_pipeline(tr22, golden_phrases):
     from guitar_audio_transcriber_ai_b200 import synth
     g = golden_phrases
