@@ -9,8 +9,11 @@
 //   (ky*Wp + kx) * 16 bytes further: im2col costs nothing and every load is a contiguous 1-D bulk (TMA) copy.
 // * 3xTF32: hi*hi + lo*hi + hi*lo accumulate in the FP32 TMEM accumulator, which keeps the logits
 //   float32-faithful (the reference runs the CNN in fp32); measured max error 5e-6 on |x| ~ 7.
-// * One CTA per SM, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2-5 =
-//   epilogue.  A work item is a GROUP of three consecutive 128-pixel tiles covering R whole image rows, so
+// * One CTA per SM, warp-specialised: warp 0 = weight producer, warp 1 = MMA issuer (one thread), warps 2-5 =
+//   epilogue, warp 6 = activation producer.  The 32 input channels of a K block are staged as two HALVES of
+//   16 channels with their own full/empty barriers and the MMAs run half-major (half 0: 9 taps, half 1: 9 taps),
+//   so the next group's half 0 streams in from HBM while this group's half 1 is being multiplied: the
+//   activation buffer is single (it fills shared memory) yet its load latency is hidden.  A work item is a GROUP of three consecutive 128-pixel tiles covering R whole image rows, so
 //   every 2x2 pooling window is inside the group: the epilogue moves 32 channels at a time TMEM -> registers ->
 //   shared staging, pools, adds the BN-folded bias, applies LeakyReLU and writes the next layer's planes
 //   (already split hi/lo) or the dense NHWC tensor the classifier head reads.
@@ -26,12 +29,12 @@ namespace gat {
 
 constexpr int kTcTiles = 3;                       // 128-pixel tiles per group
 constexpr int kTcGroupPix = 128 * kTcTiles;
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 224;
 constexpr int kTcStageStride = 33;                // floats per staged pixel (32 channels + 1 pad)
 
 struct ConvTcParams {
     const float* in_hi; const float* in_lo;       // [clip][CIN/4][Hp*Wp][4]
-    const float* w;                               // [9 taps][CIN/32][hi|lo][8 chunks][COUT][4]
+    const float* w;                               // [CIN/32][half][9 taps][hi|lo][4 chunks][COUT][4]
     const float* bias;                            // [COUT] (BatchNorm folded)
     int n_clips, H, W;                            // conv input size without the border; Hp = H+2, Wp = W+2
     int R;                                        // image rows per group (even, R*seg <= 384)
@@ -50,7 +53,7 @@ __host__ __device__ inline int conv_tc_plane_pixels(int seg) { return kTcGroupPi
 template <int COUT>
 __host__ __device__ inline size_t conv_tc_smem_bytes(int seg, int nstage) {
     return (size_t)2 * 8 * conv_tc_plane_pixels(seg) * 16          // A: hi|lo x 8 chunks x plane
-         + (size_t)nstage * 2 * 8 * COUT * 16                      // weight ring
+         + (size_t)nstage * 2 * 4 * COUT * 16                      // weight ring (one stage = one tap of one K half)
          + (size_t)kTcGroupPix * kTcStageStride * 4                // epilogue staging
          + 256;                                                    // barriers, tmem slot, alignment
 }
@@ -59,7 +62,7 @@ template <int CIN, int COUT, int NSTAGE>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) {
     using namespace tc;
     constexpr int NKB = CIN / 32;
-    constexpr uint32_t W_STAGE = 2 * 8 * COUT * 16;
+    constexpr uint32_t W_STAGE = 2 * 4 * COUT * 16;        // hi|lo x 4 chunks x COUT x 16 B
     constexpr int ACC = (2 * kTcTiles * COUT <= 512) ? 2 : 1;      // accumulator sets in TMEM (conv2: 2 x 192 columns)
     constexpr uint32_t TMEM_COLS = ACC * kTcTiles * COUT <= 256 ? 256 : 512;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -72,13 +75,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
     unsigned char* w_buf = a_buf + (size_t)2 * 8 * plane;
     float* staging = reinterpret_cast<float*>(w_buf + (size_t)NSTAGE * W_STAGE);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(staging) + (size_t)kTcGroupPix * kTcStageStride * 4);
-    uint64_t* a_full = bars + 0; uint64_t* a_empty = bars + 1; uint64_t* acc_full = bars + 2; uint64_t* acc_empty = bars + 4;
-    uint64_t* w_full = bars + 6; uint64_t* w_empty = bars + 6 + NSTAGE;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * NSTAGE);
+    uint64_t* a_full = bars + 0; uint64_t* a_empty = bars + 2; uint64_t* acc_full = bars + 4; uint64_t* acc_empty = bars + 6;
+    uint64_t* w_full = bars + 8; uint64_t* w_empty = bars + 8 + NSTAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * NSTAGE);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        mbar_init(a_full, 1); mbar_init(a_empty, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1); }
         fence_barrier_init();
@@ -93,43 +96,51 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
     const long long plane_pix = (long long)Hp * Wp;
 
     if (warp == 0) {
-        // ===================================================== TMA producer
+        // ===================================================== weight producer (one thread)
         if (lane == 0) {
-            uint32_t it = 0, use = 0;
-            for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
-                const int clip = work / p.groups_per_clip, gi = work - clip * p.groups_per_clip;
-                const int rb = gi / p.col_blocks, cb = gi - rb * p.col_blocks;
-                // first staged pixel: row y0-1, column xs-2 (one pixel of slack so tap offsets are never negative)
-                const long long q_start = (long long)(rb * p.R) * Wp + (long long)cb * p.cw - 1;
-                for (int kb = 0; kb < NKB; ++kb, ++it) {
-                    mbar_wait(a_empty, (it & 1) ^ 1);
-                    if (contiguous) {
-                        mbar_expect_tx(a_full, 16 * plane);
-                        for (int part = 0; part < 2; ++part) {
-                            const float* src = part ? p.in_lo : p.in_hi;
-                            for (int c = 0; c < 8; ++c) {
-                                const long long pl = (long long)clip * (CIN / 4) + kb * 8 + c;
-                                bulk_g2s(a_buf + (size_t)(part * 8 + c) * plane, src + (pl * plane_pix + q_start) * 4, plane, a_full);
-                            }
-                        }
-                    } else {                                   // R+2 row segments per plane, each seg pixels from column xs-1;
-                        const uint32_t row_bytes = (uint32_t)seg * 16;   // slot 0 of the plane stays the unused slack pixel
-                        mbar_expect_tx(a_full, 16 * (uint32_t)(p.R + 2) * row_bytes);
-                        for (int part = 0; part < 2; ++part) {
-                            const float* src = part ? p.in_lo : p.in_hi;
-                            for (int c = 0; c < 8; ++c) {
-                                const long long pl = (long long)clip * (CIN / 4) + kb * 8 + c;
-                                for (int a = 0; a < p.R + 2; ++a)
-                                    bulk_g2s(a_buf + (size_t)(part * 8 + c) * plane + (size_t)(1 + a * seg) * 16,
-                                             src + (pl * plane_pix + q_start + 1 + (long long)a * Wp) * 4, row_bytes, a_full);
-                            }
-                        }
-                    }
+            uint32_t use = 0;
+            for (int work = blockIdx.x; work < n_work; work += gridDim.x)
+                for (int kh = 0; kh < 2 * NKB; ++kh)
                     for (int tap = 0; tap < 9; ++tap, ++use) {
                         const uint32_t st = use % NSTAGE;
                         mbar_wait(w_empty + st, ((use / NSTAGE) & 1) ^ 1);
                         mbar_expect_tx(w_full + st, W_STAGE);
-                        bulk_g2s(w_buf + (size_t)st * W_STAGE, p.w + (size_t)(tap * NKB + kb) * (W_STAGE / 4), W_STAGE, w_full + st);
+                        bulk_g2s(w_buf + (size_t)st * W_STAGE, p.w + (size_t)(kh * 9 + tap) * (W_STAGE / 4), W_STAGE, w_full + st);
+                    }
+        }
+    } else if (warp == 6) {
+        // ===================================================== activation producer (32 lanes issue the copies)
+        uint32_t it = 0;
+        const uint32_t row_bytes = (uint32_t)seg * 16;
+        const int rows = p.R + 2;
+        for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
+            const int clip = work / p.groups_per_clip, gi = work - clip * p.groups_per_clip;
+            const int rb = gi / p.col_blocks, cb = gi - rb * p.col_blocks;
+            // first staged pixel: row y0-1, column xs-2 (one pixel of slack so tap offsets are never negative)
+            const long long q_start = (long long)(rb * p.R) * Wp + (long long)cb * p.cw - 1;
+            for (int kb = 0; kb < NKB; ++kb, ++it) {
+                for (int half = 0; half < 2; ++half) {
+                    if (lane == 0) {
+                        mbar_wait(a_empty + half, (it & 1) ^ 1);
+                        mbar_expect_tx(a_full + half, contiguous ? 8 * plane : 8 * (uint32_t)rows * row_bytes);
+                    }
+                    __syncwarp();
+                    if (contiguous) {
+                        if (lane < 8) {
+                            const int part = lane >> 2, c = half * 4 + (lane & 3);
+                            const float* src = part ? p.in_lo : p.in_hi;
+                            const long long pl = (long long)clip * (CIN / 4) + kb * 8 + c;
+                            bulk_g2s(a_buf + (size_t)(part * 8 + c) * plane, src + (pl * plane_pix + q_start) * 4, plane, a_full + half);
+                        }
+                    } else {                               // R+2 row segments per plane, each seg pixels from column xs-1;
+                        for (int i = lane; i < 8 * rows; i += 32) {        // slot 0 of the plane stays the unused slack pixel
+                            const int pc = i / rows, a = i - pc * rows;
+                            const int part = pc >> 2, c = half * 4 + (pc & 3);
+                            const float* src = part ? p.in_lo : p.in_hi;
+                            const long long pl = (long long)clip * (CIN / 4) + kb * 8 + c;
+                            bulk_g2s(a_buf + (size_t)(part * 8 + c) * plane + (size_t)(1 + a * seg) * 16,
+                                     src + (pl * plane_pix + q_start + 1 + (long long)a * Wp) * 4, row_bytes, a_full + half);
+                        }
                     }
                 }
             }
@@ -157,33 +168,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
                 const uint32_t d_base = tmem + as * (uint32_t)(kTcTiles * COUT);
                 uint32_t accumulate = 0;
                 for (int kb = 0; kb < NKB; ++kb, ++it) {
-                    t0 = clock64();
-                    mbar_wait(a_full, it & 1);
-                    t_a += clock64() - t0;
-                    for (int tap = 0; tap < 9; ++tap, ++use) {
-                        const uint32_t st = use % NSTAGE;
+                    for (int half = 0; half < 2; ++half) {
                         t0 = clock64();
-                        mbar_wait(w_full + st, (use / NSTAGE) & 1);
-                        t_w += clock64() - t0;
-                        fence_after_thread_sync();
-                        const uint32_t row_off = (uint32_t)((tap / 3) * seg + (tap % 3));         // in 16-byte units
-                        const uint32_t w_hi = ((smem_u32(w_buf) + st * W_STAGE) >> 4) | b_lbo, w_lo = w_hi + ((8 * COUT * 16) >> 4);
+                        mbar_wait(a_full + half, it & 1);
+                        t_a += clock64() - t0;
+                        for (int tap = 0; tap < 9; ++tap, ++use) {
+                            const uint32_t st = use % NSTAGE;
+                            t0 = clock64();
+                            mbar_wait(w_full + st, (use / NSTAGE) & 1);
+                            t_w += clock64() - t0;
+                            fence_after_thread_sync();
+                            const uint32_t row_off = (uint32_t)((tap / 3) * seg + (tap % 3));         // in 16-byte units
+                            const uint32_t w_hi = ((smem_u32(w_buf) + st * W_STAGE) >> 4) | b_lbo, w_lo = w_hi + ((4 * COUT * 16) >> 4);
 #pragma unroll
-                        for (int s = 0; s < 4; ++s) {
-                            const uint64_t dbh = desc(w_hi + s * b_step), dbl = desc(w_lo + s * b_step);
-                            const uint32_t ah = a_hi + row_off + s * a_step, al = a_lo + row_off + s * a_step;
+                            for (int sl = 0; sl < 2; ++sl) {
+                                const uint64_t dbh = desc(w_hi + sl * b_step), dbl = desc(w_lo + sl * b_step);
+                                const uint32_t s_off = row_off + (uint32_t)(2 * half + sl) * a_step;
+                                const uint32_t ah = a_hi + s_off, al = a_lo + s_off;
 #pragma unroll
-                            for (int g = 0; g < kTcTiles; ++g) {
-                                const uint32_t d = d_base + (uint32_t)(g * COUT);
-                                mma_tf32(d, desc(ah + g * 128), dbh, idesc, s == 0 ? accumulate : 1u);
-                                mma_tf32(d, desc(al + g * 128), dbh, idesc, 1u);
-                                mma_tf32(d, desc(ah + g * 128), dbl, idesc, 1u);
+                                for (int g = 0; g < kTcTiles; ++g) {
+                                    const uint32_t d = d_base + (uint32_t)(g * COUT);
+                                    mma_tf32(d, desc(ah + g * 128), dbh, idesc, sl == 0 ? accumulate : 1u);
+                                    mma_tf32(d, desc(al + g * 128), dbh, idesc, 1u);
+                                    mma_tf32(d, desc(ah + g * 128), dbl, idesc, 1u);
+                                }
                             }
+                            accumulate = 1;
+                            mma_commit(w_empty + st);       // weights of this stage are free once those MMAs retire
                         }
-                        accumulate = 1;
-                        mma_commit(w_empty + st);           // weights of this stage are free once those MMAs retire
+                        mma_commit(a_empty + half);         // ... and so is this half of the activation buffer
                     }
-                    mma_commit(a_empty);                    // ... and so is the activation buffer
                 }
                 mma_commit(acc_full + as);                  // accumulators of the group are complete
             }

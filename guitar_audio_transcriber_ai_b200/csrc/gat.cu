@@ -216,6 +216,47 @@ extern "C" int gat_debug_tc_counters(gat_ctx* c, long long* out_host, int64_t n)
     return 0;
 }
 
+// FP32-FMA peak of this device, measured: the denominator SURVEY.md 8(d) asks the FFT-bound stages to be reported
+// against (MEASURED_PEAKS.json has no FP32 figure).  16 independent FMA chains per thread, 1024 threads x 2 CTAs per SM.
+#ifndef GAT_CPU_EMU
+__global__ void __launch_bounds__(1024, 2) fma_peak_kernel(float* out, int iters, float a, float b) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (float)(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], a, b);
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += v[i];
+    if (s == 12345.678f) out[0] = s;     // keeps the chains alive
+}
+#endif
+extern "C" int gat_debug_fma_peak(gat_ctx* c, int32_t iters, float* tflops_host) {
+    if (!c || !tflops_host || iters < 1) return fail("gat_debug_fma_peak: bad argument");
+#ifdef GAT_CPU_EMU
+    return fail("gat_debug_fma_peak: needs the CUDA build");
+#else
+    if (c->tc_debug_buf.ensure(2 * 148 * 8 * 8)) return 1;
+    cudaEvent_t e0, e1;
+    GAT_CUDA(cudaEventCreate(&e0)); GAT_CUDA(cudaEventCreate(&e1));
+    const int grid = 2 * c->num_sms;
+    fma_peak_kernel<<<grid, 1024>>>((float*)c->tc_debug_buf.p, iters, 0.999f, 0.001f);   // warm-up
+    GAT_CUDA(cudaEventRecord(e0));
+    fma_peak_kernel<<<grid, 1024>>>((float*)c->tc_debug_buf.p, iters, 0.999f, 0.001f);
+    GAT_CUDA(cudaEventRecord(e1));
+    GAT_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.0f;
+    GAT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *tflops_host = (float)(2.0 * 128.0 * iters * 1024.0 * grid / (ms * 1e-3) * 1e-12);
+    return 0;
+#endif
+}
+
 extern "C" int gat_set_conv_pass(gat_ctx* c, int32_t mult) {
     if (!c || mult < 1 || mult > 64) return fail("gat_set_conv_pass: bad argument");
     c->conv_pass_mult = mult;
@@ -367,18 +408,19 @@ extern "C" int gat_load_cnn(gat_ctx* c, int32_t n_conv, const int32_t* ch, const
         if (upload(c->conv_b[i], conv_b[i], (size_t)ch[i + 1])) return 1;
     }
 #ifndef GAT_CPU_EMU
-    for (int i = 1; i < 3; ++i) {   // [tap][c_in/32][hi|lo][8 chunks][c_out][4]: one contiguous blob per (tap, K block)
-        const int cin = ch[i], cout = ch[i + 1], nkb = cin / 32;
-        std::vector<float> t((size_t)9 * nkb * 2 * 8 * cout * 4);
+    for (int i = 1; i < 3; ++i) {   // [c_in/32][half][tap][hi|lo][4 chunks][c_out][4]: one contiguous blob per pipeline stage
+        const int cin = ch[i], cout = ch[i + 1];
+        std::vector<float> t((size_t)9 * cin * cout * 2);
         for (int tap = 0; tap < 9; ++tap)
             for (int ci = 0; ci < cin; ++ci)
                 for (int oc = 0; oc < cout; ++oc) {
                     const float w = conv_w[i][((size_t)tap * cin + ci) * cout + oc];
                     const float hi = tc::tf32_hi(w);
-                    const size_t base = ((size_t)(tap * nkb + ci / 32) * 2) * 8 * cout * 4;
-                    const size_t idx = ((size_t)((ci % 32) / 4) * cout + oc) * 4 + (ci % 4);
+                    const int kh = ci / 16, chunk = (ci % 16) / 4;        // kh = K block * 2 + half
+                    const size_t base = ((size_t)(kh * 9 + tap) * 2) * 4 * cout * 4;
+                    const size_t idx = ((size_t)chunk * cout + oc) * 4 + (ci % 4);
                     t[base + idx] = hi;
-                    t[base + (size_t)8 * cout * 4 + idx] = w - hi;
+                    t[base + (size_t)4 * cout * 4 + idx] = w - hi;
                 }
         if (upload(c->conv_w_tc[i], t.data(), t.size())) return 1;
     }
@@ -644,24 +686,30 @@ constexpr size_t kActGuard = 65536;   // bytes before/after the plane buffers: h
 // planes fit in shared memory), R image rows per group so that R * seg <= 384 tile pixels.
 struct ConvTiling { int seg, cw, col_blocks, R, groups_per_clip; size_t smem; };
 
+// Picks the column blocking that needs the fewest 384-pixel groups per clip: nb column blocks of cw output
+// columns (cw even when nb > 1 so that 2x2 pool pairs stay inside a block), seg = cw + 2 staged pixels per row,
+// R rows per group.  Narrower blocks than shared memory allows often waste less of a group (W = 86: two blocks
+// of 44 columns x 8 rows fill 90 % of a group, one 64-column block x 6 rows + a 24-column remainder only 60 %).
 template <int COUT>
 ConvTiling conv_tc_tiling(int H, int W, int nstage) {
-    ConvTiling t{};
+    ConvTiling best{};
     const size_t budget = 227 * 1024;
-    int seg = W + 2;
-    if (conv_tc_smem_bytes<COUT>(seg, nstage) <= budget && 2 * seg <= kTcGroupPix) {
-        t.seg = seg; t.cw = W; t.col_blocks = 1;
-    } else {
-        seg = 4;
-        while (conv_tc_smem_bytes<COUT>(seg + 2, nstage) <= budget && 2 * (seg + 2) <= kTcGroupPix) seg += 2;   // even
-        t.seg = seg; t.cw = seg - 2; t.col_blocks = (W + t.cw - 1) / t.cw;
-    }
-    int R = 2 * (kTcGroupPix / (2 * t.seg));
     const int hmax = 2 * (H / 2);
-    t.R = R < hmax ? R : hmax;
-    t.groups_per_clip = t.R >= 2 ? ceil_div(H / 2, t.R / 2) * t.col_blocks : 0;
-    t.smem = conv_tc_smem_bytes<COUT>(t.seg, nstage);
-    return t;
+    for (int nb = 1; nb <= (W + 1) / 2; ++nb) {
+        int cw = (W + nb - 1) / nb;
+        if (nb > 1 && (cw & 1)) ++cw;
+        const int seg = cw + 2;
+        if (2 * seg > kTcGroupPix || conv_tc_smem_bytes<COUT>(seg, nstage) > budget) continue;
+        ConvTiling t{};
+        t.seg = seg; t.cw = cw; t.col_blocks = (W + cw - 1) / cw;
+        const int R = 2 * (kTcGroupPix / (2 * seg));
+        t.R = R < hmax ? R : hmax;
+        if (t.R < 2) continue;
+        t.groups_per_clip = ceil_div(H / 2, t.R / 2) * t.col_blocks;
+        t.smem = conv_tc_smem_bytes<COUT>(seg, nstage);
+        if (best.groups_per_clip == 0 || t.groups_per_clip < best.groups_per_clip) best = t;
+    }
+    return best;
 }
 
 int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, float* cnn_logits, void* stream) {
@@ -669,7 +717,7 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
     const int H0 = c->cfg.mel_n_mels, W0 = T;
     const int H1 = H0 / 2, W1 = W0 / 2, H2 = H1 / 2, W2 = W1 / 2, H3 = H2 / 2, W3 = W2 / 2;
     if (H3 < 1 || W3 < 1) return fail("infer: mel image %dx%d too small for three 2x2 pools", H0, W0);
-    const ConvTiling t2 = conv_tc_tiling<64>(H1, W1, 3), t3 = conv_tc_tiling<128>(H2, W2, 2);
+    const ConvTiling t2 = conv_tc_tiling<64>(H1, W1, 6), t3 = conv_tc_tiling<128>(H2, W2, 4);
     if (t2.R < 2 || t3.R < 2 || t2.smem > 227 * 1024 || t3.smem > 227 * 1024)
         return fail("infer: no tensor-core conv tiling for a mel image of %d x %d", H0, W0);
     const size_t smem2 = t2.smem, smem3 = t3.smem;
@@ -690,8 +738,8 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
     float* act1_lo = reinterpret_cast<float*>(c->act1.as<unsigned char>() + kActGuard + a1);
     float* act2_hi = reinterpret_cast<float*>(c->act2.as<unsigned char>() + kActGuard);
     float* act2_lo = reinterpret_cast<float*>(c->act2.as<unsigned char>() + kActGuard + a2);
-    auto k2 = conv_tc_kernel<32, 64, 3>;
-    auto k3 = conv_tc_kernel<64, 128, 2>;
+    auto k2 = conv_tc_kernel<32, 64, 6>;
+    auto k3 = conv_tc_kernel<64, 128, 4>;
     GAT_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     GAT_CUDA(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
     for (long long c0 = 0; c0 < N; c0 += chunk) {

@@ -104,6 +104,12 @@ class Engine:
             out[name] = (int(cnt), float(ms))
         return out
 
+    def fma_peak_tflops(self, iters: int = 4096) -> float:
+        """Measured FP32-FMA peak of this GPU (TFLOP/s): the roof the FFT-bound stages are reported against."""
+        v = C.c_float(0.0)
+        self.lib.check(self.lib.gat_debug_fma_peak(self._ctx, iters, C.byref(v)))
+        return float(v.value)
+
     def mel_frames(self, n: int) -> int:
         return 1 + n // self.hop
 

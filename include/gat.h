@@ -165,6 +165,10 @@ int gat_set_conv_pass(gat_ctx* ctx, int32_t mult);
  * MMA-thread total, wait acc_empty, wait a_full, wait w_full, epilogue total, epilogue wait acc_full). */
 int gat_debug_tc_counters(gat_ctx* ctx, long long* out_host, int64_t n);
 
+/* Measures this device's FP32-FMA peak (TFLOP/s, 2 flops per FMA) with a register-only FMA kernel: the
+ * denominator for the FFT-bound stages ("the builder must measure it").  Blocks. */
+int gat_debug_fma_peak(gat_ctx* ctx, int32_t iters, float* tflops_host);
+
 /* Number of kernels launched through this ctx so far (bench.py's gpu_launches). */
 int64_t gat_launch_count(const gat_ctx* ctx);
 /* classes of the loaded models, frames of the mel image for n samples. */
