@@ -54,9 +54,10 @@ struct StftMelParams {
     int hop;
     int n_frames;              // frames per clip = 1 + n / hop
     int pad_mode;
-    const T* window;           // [2048]
-    const Cpx<T>* tw;          // [1024]
-    const Cpx<T>* w2;          // [1024]
+    const T* window;           // [n_fft]
+    const T* window_half;      // [n_fft] 0.5 * window; only read when n_fft = 4096 (window stays in global/L1 there)
+    const Cpx<T>* tw;          // [n_fft/2]   W_C^(n1*k2), C = n_fft/2 (FftTables::tw)
+    const Cpx<T>* w2;          // [n_fft/4]   W_n_fft^k
     SparseFb fb;
     int frames_per_cta;
     int chunks_per_clip;
@@ -80,36 +81,41 @@ __device__ __forceinline__ double db10(double x) { return 10.0 * log10(x); }
 
 constexpr int kMaxMelsPerLane = 4;   // n_mels <= 128
 
-// Shared-memory footprint of stft_mel_kernel (bytes), mirrored by the host launcher.
-template <typename T>
+// Shared-memory footprint of stft_mel_kernel (bytes), mirrored by the host launcher.  P = n_fft / 64.
+template <typename T, int P>
 __host__ __device__ inline size_t stft_mel_smem_bytes(int nwarps, int frames_per_cta, int hop, int n_mels, int nnz, bool image, bool async) {
+    using G = FftGeom<P>;
+    const int fcr = (frames_per_cta + G::F - 1) / G::F * G::F;          // a warp always transforms F frames together
     size_t b = 0;
-    b += sizeof(FftTables<T>);
-    b += 2048 * sizeof(T);                                               // window
-    b += ((size_t)(frames_per_cta - 1) * hop + 2048) * sizeof(T);        // staged samples
-    if (async) b += ((size_t)(frames_per_cta - 1) * hop + 2048 + 8) * sizeof(float);   // raw landing zone (async path)
-    b += (size_t)nwarps * kXbufElems * sizeof(Cpx<T>);                   // per-warp transpose buffers
+    b += sizeof(FftTables<T, P>);
+    if (P < 64) b += G::N * sizeof(T);                                   // window (n_fft 4096 reads it through L1)
+    b += ((size_t)(fcr - 1) * hop + G::N) * sizeof(T);                   // staged samples
+    if (async) b += ((size_t)(fcr - 1) * hop + G::N + 8) * sizeof(float);   // raw landing zone (async path)
+    b += (size_t)nwarps * G::kXbufElems * sizeof(Cpx<T>);                // per-warp transpose buffers
     b += (size_t)4 * kMaxMelsPerLane * 32 * sizeof(int) + (size_t)nnz * sizeof(float); // sparse filterbank (lane slots)
     if (image) b += (size_t)n_mels * (frames_per_cta + 1) * sizeof(T);   // output tile
     return b + 64;
 }
 
-template <typename T, int kOut, int kThreads>
+template <typename T, int kOut, int kThreads, int P>
 __global__ void __launch_bounds__(kThreads, 1) stft_mel_kernel(StftMelParams<T> p) {
+    using G = FftGeom<P>;
+    constexpr int NFFT = G::N, HALF = G::N / 2, F = G::F, V = G::V;
     GAT_DYN_SMEM(smem_raw);
     const int nwarps = blockDim.x >> 5;
     const int lane = lane_id(), warp = warp_id();
     const int FC = p.frames_per_cta;
-    const int span_len = (FC - 1) * p.hop + 2048;
+    const int span_len = ((FC + F - 1) / F * F - 1) * p.hop + NFFT;
     const int n_mels = p.fb.n_mels;
 
     unsigned char* sp = smem_raw;
-    FftTables<T>* tab = reinterpret_cast<FftTables<T>*>(sp);  sp += sizeof(FftTables<T>);
-    T* win = reinterpret_cast<T*>(sp);                        sp += 2048 * sizeof(T);
+    FftTables<T, P>* tab = reinterpret_cast<FftTables<T, P>*>(sp);  sp += sizeof(FftTables<T, P>);
+    constexpr bool kWinSmem = P < 64;
+    T* win = reinterpret_cast<T*>(sp);                        if (kWinSmem) sp += NFFT * sizeof(T);
     T* span = reinterpret_cast<T*>(sp);                       sp += (size_t)span_len * sizeof(T);
     const bool kAsync = p.use_async != 0;     // prefetch the next chunk's samples with cp.async while this one is transformed
     float* raw = reinterpret_cast<float*>(sp);                if (kAsync) sp += (size_t)(span_len + 8) * sizeof(float);
-    Cpx<T>* xbuf_all = reinterpret_cast<Cpx<T>*>(sp);         sp += (size_t)nwarps * kXbufElems * sizeof(Cpx<T>);
+    Cpx<T>* xbuf_all = reinterpret_cast<Cpx<T>*>(sp);         sp += (size_t)nwarps * G::kXbufElems * sizeof(Cpx<T>);
     constexpr int kSlotEntries = kMaxMelsPerLane * 32;
     int* fb_start = reinterpret_cast<int*>(sp);               sp += kSlotEntries * sizeof(int);
     int* fb_len = reinterpret_cast<int*>(sp);                 sp += kSlotEntries * sizeof(int);
@@ -118,8 +124,10 @@ __global__ void __launch_bounds__(kThreads, 1) stft_mel_kernel(StftMelParams<T> 
     float* fb_w = reinterpret_cast<float*>(sp);               sp += (size_t)p.fb.nnz * sizeof(float);
     T* tile = reinterpret_cast<T*>(sp);                       // kOutImage only
 
-    fill_fft_tables<T>(tab, p.tw, p.w2);
-    for (int i = threadIdx.x; i < 2048; i += blockDim.x) win[i] = (T)0.5 * p.window[i];   // 1/2 of the Hermitian split, exact
+    fill_fft_tables<T, P>(tab, p.tw, p.w2);
+    if (kWinSmem)
+        for (int i = threadIdx.x; i < NFFT; i += blockDim.x) win[i] = (T)0.5 * p.window[i];   // 1/2 of the Hermitian split, exact
+    for (int i = threadIdx.x; i < span_len; i += blockDim.x) span[i] = (T)0;              // frames past a short chunk stay finite
     for (int i = threadIdx.x; i < kSlotEntries; i += blockDim.x) {
         const bool live = i < p.fb.n_slots * 32;
         fb_start[i] = live ? p.fb.start[i] : 0; fb_len[i] = live ? p.fb.len[i] : 0;
@@ -128,8 +136,8 @@ __global__ void __launch_bounds__(kThreads, 1) stft_mel_kernel(StftMelParams<T> 
     for (int i = threadIdx.x; i < p.fb.nnz; i += blockDim.x) fb_w[i] = p.fb.w[i];
     __syncthreads();
 
-    Cpx<T>* xbuf = xbuf_all + (size_t)warp * kXbufElems;
-    T* pbuf = reinterpret_cast<T*>(xbuf);   // 1025 power values alias the transpose buffer
+    Cpx<T>* xbuf = xbuf_all + (size_t)warp * G::kXbufElems;
+    T* pbuf = reinterpret_cast<T*>(xbuf);   // the power spectra alias the transpose buffer
 
     const long long n_work = (long long)p.N * p.chunks_per_clip;
     // Raw sample range a work item needs: padded index range [t0*hop, t0*hop + need) <-> samples s0 .. s0+need.
@@ -137,9 +145,9 @@ __global__ void __launch_bounds__(kThreads, 1) stft_mel_kernel(StftMelParams<T> 
         const int clip = (int)(work / p.chunks_per_clip);
         const int t0 = (int)(work % p.chunks_per_clip) * FC;
         const int nf = min(FC, p.n_frames - t0);
-        const long long s0 = (long long)t0 * p.hop - 1024;
+        const long long s0 = (long long)t0 * p.hop - HALF;
         const long long lo = s0 < 0 ? 0 : s0;
-        long long hi = s0 + (nf - 1) * p.hop + 2048;
+        long long hi = s0 + (nf - 1) * p.hop + NFFT;
         hi = hi > p.n ? p.n : hi;
         const float* src = p.audio + (long long)clip * p.n + lo;
         for (int i = threadIdx.x; i < (int)(hi - lo); i += blockDim.x) cp_async4(raw + i, src + i);
@@ -153,8 +161,8 @@ __global__ void __launch_bounds__(kThreads, 1) stft_mel_kernel(StftMelParams<T> 
         const int nf = min(FC, p.n_frames - t0);
         const float* src = p.audio + (long long)clip * p.n;
         const float c = p.clip_scale ? p.clip_scale[clip] : 1.0f;
-        const int need = (nf - 1) * p.hop + 2048;
-        const long long s0 = (long long)t0 * p.hop - 1024;
+        const int need = (nf - 1) * p.hop + NFFT;
+        const long long s0 = (long long)t0 * p.hop - HALF;
         const long long lo = s0 < 0 ? 0 : s0;
         long long hi = s0 + need;
         hi = hi > p.n ? p.n : hi;
@@ -178,42 +186,48 @@ __global__ void __launch_bounds__(kThreads, 1) stft_mel_kernel(StftMelParams<T> 
         if (kAsync && work + gridDim.x < n_work) issue_prefetch(work + gridDim.x);   // overlaps the FFT phase below
 
         T wmax = (T)-1e300;
-        for (int f = warp; f < nf; f += nwarps) {
-            const T* x = span + (size_t)f * p.hop;
-            Cpx<T> v[32];
-            const Cpx<T>* x2 = reinterpret_cast<const Cpx<T>*>(x);       // (x[2j], x[2j+1]) as one aligned vector
-            const Cpx<T>* w2v = reinterpret_cast<const Cpx<T>*>(win);
+        for (int f0 = warp * F; f0 < nf; f0 += nwarps * F) {       // this warp transforms frames f0 .. f0+F-1 together
+            Cpx<T> v[V];
+            const Cpx<T>* w2v = reinterpret_cast<const Cpx<T>*>(kWinSmem ? win : p.window_half);
 #pragma unroll
-            for (int n2 = 0; n2 < 32; ++n2) {
-                const int j = lane + 32 * n2;
+            for (int r = 0; r < V; ++r) {
+                const int j = lane + 32 * (r % P);
+                // (x[2j], x[2j+1]) of frame f0 + r/P as one aligned vector
+                const Cpx<T>* x2 = reinterpret_cast<const Cpx<T>*>(span + (size_t)(f0 + r / P) * p.hop);
                 const Cpx<T> xv = x2[j], wv = w2v[j];
-                v[n2] = Cpx<T>{xv.x * wv.x, xv.y * wv.y};
+                v[r] = Cpx<T>{xv.x * wv.x, xv.y * wv.y};
             }
-            warp_rfft2048_power<T>(v, xbuf, kPbufLead, tab);
+            warp_rfft_power<T, P>(v, xbuf, kPbufLead, tab);
             // banded-sparse mel, one filter per (lane, slot), four bins per step; bank-conflict free by construction
+#pragma unroll 1
+            for (int ff = 0; ff < F; ++ff) {
+                const int f = f0 + ff;
+                if (f >= nf) break;
+                const T* pf = pbuf + ff * G::kPbufStride + kPbufLead;
 #pragma unroll
-            for (int q = 0; q < kMaxMelsPerLane; ++q) {
-                const int e = q * 32 + lane;
-                const int m = fb_mel[e];
-                const int ln = fb_len[e];
-                const Vec4<T>* pb = reinterpret_cast<const Vec4<T>*>(pbuf + kPbufLead + fb_start[e]);
-                const float4* w = reinterpret_cast<const float4*>(fb_w + fb_off[e]);
-                T acc = (T)0;
-                for (int k = 0; k < ln; ++k) {
-                    const Vec4<T> pv = pb[k];
-                    const float4 wv = w[k];
-                    acc += pv.x * (T)wv.x;
-                    acc += pv.y * (T)wv.y;
-                    acc += pv.z * (T)wv.z;
-                    acc += pv.w * (T)wv.w;
-                }
-                if (m >= 0) {
-                    const T db = db10(acc > p.amin ? acc : p.amin);
-                    if (kOut == kOutImage) {
-                        tile[m * (FC + 1) + f] = db;
-                    } else {
-                        p.out[((long long)clip * p.n_frames + t0 + f) * n_mels + m] = db;
-                        wmax = db > wmax ? db : wmax;
+                for (int q = 0; q < kMaxMelsPerLane; ++q) {
+                    const int e = q * 32 + lane;
+                    const int m = fb_mel[e];
+                    const int ln = fb_len[e];
+                    const Vec4<T>* pb = reinterpret_cast<const Vec4<T>*>(pf + fb_start[e]);
+                    const float4* w = reinterpret_cast<const float4*>(fb_w + fb_off[e]);
+                    T acc = (T)0;
+                    for (int k = 0; k < ln; ++k) {
+                        const Vec4<T> pv = pb[k];
+                        const float4 wv = w[k];
+                        acc += pv.x * (T)wv.x;
+                        acc += pv.y * (T)wv.y;
+                        acc += pv.z * (T)wv.z;
+                        acc += pv.w * (T)wv.w;
+                    }
+                    if (m >= 0) {
+                        const T db = db10(acc > p.amin ? acc : p.amin);
+                        if (kOut == kOutImage) {
+                            tile[m * (FC + 1) + f] = db;
+                        } else {
+                            p.out[((long long)clip * p.n_frames + t0 + f) * n_mels + m] = db;
+                            wmax = db > wmax ? db : wmax;
+                        }
                     }
                 }
             }
@@ -221,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) stft_mel_kernel(StftMelParams<T> 
         }
         if (kOut == kOutSpec) {
             wmax = warp_max(wmax);
-            if (lane == 0 && nf > warp) atomicMax(p.spec_max + clip, ordered_bits((double)wmax));
+            if (lane == 0 && nf > warp * F) atomicMax(p.spec_max + clip, ordered_bits((double)wmax));
         }
         __syncthreads();
         if (kOut == kOutImage) {
@@ -231,166 +245,6 @@ __global__ void __launch_bounds__(kThreads, 1) stft_mel_kernel(StftMelParams<T> 
             }
             __syncthreads();
         }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// CNN chain for n_fft other than 2048 (MelSpecConfig.N_FFT is configurable: features.py:296-302; BASELINE
-// config 5 sweeps 1024 / 4096).  Same staging, mel and output code; the FFT is a generic warp-level radix-2
-// transform of the M = n_fft/2 folded complex points held in shared memory (bit-reversed load, log2(M)
-// butterfly passes separated by __syncwarp, Hermitian split in place).  It is slower per point than the
-// register-resident 32x32 transform above, which stays the path for the reference's default n_fft.
-struct StftGenericParams {
-    const float* audio; long long n; int N;
-    const float* clip_scale;
-    int n_fft, hop, n_frames;
-    const float* window;            // [n_fft]
-    const Cpx<float>* tw;           // [n_fft/4] : W_M^k, M = n_fft/2
-    SparseFb fb;
-    int frames_per_cta, chunks_per_clip;
-    float amin;
-    float* out;                     // [(clip*n_mels + m)*T + t]
-};
-
-template <int LOG2M>
-__host__ __device__ inline size_t stft_generic_smem_bytes(int nwarps, int frames_per_cta, int hop, int n_mels, int nnz) {
-    constexpr int M = 1 << LOG2M;
-    size_t b = 0;
-    b += (size_t)(M / 2) * sizeof(Cpx<float>);                          // twiddles
-    b += (size_t)2 * M * sizeof(float);                                 // window
-    b += ((size_t)(frames_per_cta - 1) * hop + 2 * M) * sizeof(float);  // staged samples
-    b += (size_t)nwarps * (M + 24) * sizeof(Cpx<float>);                // per-warp FFT buffer (also holds the power spectrum)
-    b += (size_t)4 * kMaxMelsPerLane * 32 * sizeof(int) + (size_t)nnz * sizeof(float);
-    b += (size_t)n_mels * (frames_per_cta + 1) * sizeof(float);
-    return b + 64;
-}
-
-template <int LOG2M>
-__global__ void __launch_bounds__(256, 1) stft_mel_generic_kernel(StftGenericParams p) {
-    constexpr int M = 1 << LOG2M;          // complex points per frame
-    constexpr int NFFT = 2 * M;
-    constexpr int PER_LANE = M / 32;
-    GAT_DYN_SMEM(smem_raw);
-    const int nwarps = blockDim.x >> 5;
-    const int lane = lane_id(), warp = warp_id();
-    const int FC = p.frames_per_cta;
-    const int span_len = (FC - 1) * p.hop + NFFT;
-    const int n_mels = p.fb.n_mels;
-    unsigned char* sp = smem_raw;
-    Cpx<float>* tw = reinterpret_cast<Cpx<float>*>(sp);       sp += (size_t)(M / 2) * sizeof(Cpx<float>);
-    float* win = reinterpret_cast<float*>(sp);                sp += (size_t)NFFT * sizeof(float);
-    float* span = reinterpret_cast<float*>(sp);               sp += (size_t)span_len * sizeof(float);
-    Cpx<float>* xbuf_all = reinterpret_cast<Cpx<float>*>(sp); sp += (size_t)nwarps * (M + 24) * sizeof(Cpx<float>);
-    constexpr int kSlotEntries = kMaxMelsPerLane * 32;
-    int* fb_start = reinterpret_cast<int*>(sp);               sp += kSlotEntries * sizeof(int);
-    int* fb_len = reinterpret_cast<int*>(sp);                 sp += kSlotEntries * sizeof(int);
-    int* fb_off = reinterpret_cast<int*>(sp);                 sp += kSlotEntries * sizeof(int);
-    int* fb_mel = reinterpret_cast<int*>(sp);                 sp += kSlotEntries * sizeof(int);
-    float* fb_w = reinterpret_cast<float*>(sp);               sp += (size_t)p.fb.nnz * sizeof(float);
-    float* tile = reinterpret_cast<float*>(sp);
-
-    for (int i = threadIdx.x; i < M / 2; i += blockDim.x) tw[i] = p.tw[i];
-    for (int i = threadIdx.x; i < NFFT; i += blockDim.x) win[i] = 0.5f * p.window[i];     // 1/2 of the Hermitian split
-    for (int i = threadIdx.x; i < kSlotEntries; i += blockDim.x) {
-        const bool live = i < p.fb.n_slots * 32;
-        fb_start[i] = live ? p.fb.start[i] : 0; fb_len[i] = live ? p.fb.len[i] : 0;
-        fb_off[i] = live ? p.fb.off[i] : 0;     fb_mel[i] = live ? p.fb.mel[i] : -1;
-    }
-    for (int i = threadIdx.x; i < p.fb.nnz; i += blockDim.x) fb_w[i] = p.fb.w[i];
-    __syncthreads();
-
-    Cpx<float>* buf = xbuf_all + (size_t)warp * (M + 24);
-    float* pbuf = reinterpret_cast<float*>(buf);              // kPbufLead zeros + (M + 1) bins + tail, 2M + 48 floats available
-    const long long n_work = (long long)p.N * p.chunks_per_clip;
-    for (long long work = blockIdx.x; work < n_work; work += gridDim.x) {
-        const int clip = (int)(work / p.chunks_per_clip);
-        const int t0 = (int)(work % p.chunks_per_clip) * FC;
-        const int nf = min(FC, p.n_frames - t0);
-        const float* src = p.audio + (long long)clip * p.n;
-        const float c = p.clip_scale ? p.clip_scale[clip] : 1.0f;
-        const int need = (nf - 1) * p.hop + NFFT;
-        for (int i = threadIdx.x; i < need; i += blockDim.x) {
-            long long s = (long long)t0 * p.hop + i - M;                 // centre padding of n_fft/2 = M, reflect
-            if (s < 0 || s >= p.n) s = reflect_index(s, p.n);
-            float v = src[s];
-            if (p.clip_scale) v = __fdiv_rn(v, c);
-            span[i] = v;
-        }
-        __syncthreads();
-        for (int f = warp; f < nf; f += nwarps) {
-            const float* x = span + (size_t)f * p.hop;
-            // bit-reversed load of the windowed, folded frame
-            for (int j = lane; j < M; j += 32) {
-                const int r = (int)(__brev((unsigned)j) >> (32 - LOG2M));
-                buf[r] = Cpx<float>{x[2 * j] * win[2 * j], x[2 * j + 1] * win[2 * j + 1]};
-            }
-            __syncwarp();
-            // radix-2 decimation-in-time passes
-            for (int half = 1; half < M; half <<= 1) {
-                const int tstep = (M / 2) / half;
-                for (int b = lane; b < M / 2; b += 32) {
-                    const int pos = b & (half - 1);
-                    const int i0 = ((b - pos) << 1) + pos, i1 = i0 + half;
-                    const Cpx<float> w = tw[pos * tstep];
-                    const Cpx<float> a = buf[i0], cc = cmul(buf[i1], w);
-                    buf[i0] = cadd(a, cc);
-                    buf[i1] = csub(a, cc);
-                }
-                __syncwarp();
-            }
-            // Hermitian split in place: the pair (k, M-k) is read and written by the same lane
-            float nyq = 0.0f;
-            for (int k = lane; k <= M / 2; k += 32) {
-                const int kp = (M - k) & (M - 1);
-                const Cpx<float> a = buf[k], bq = buf[kp];
-                float sn, cs;
-                sincospif(-2.0f * (float)k / (float)NFFT, &sn, &cs);   // W_NFFT^k = exp(-2 pi i k / NFFT)
-                const float er = a.x + bq.x, ei = a.y - bq.y;
-                const float orr = a.y + bq.y, oi = bq.x - a.x;
-                const float tr = orr * cs - oi * sn, ti = orr * sn + oi * cs;
-                if (k == 0) {
-                    buf[0] = Cpx<float>{er + tr, 0.0f};                  // X[0]; X[M] (Nyquist) kept in a register
-                    nyq = er - tr;
-                } else {
-                    buf[k] = Cpx<float>{er + tr, ei + ti};
-                    buf[kp] = Cpx<float>{er - tr, -(ei - ti)};           // X[M-k] = conj(E - T)
-                }
-            }
-            __syncwarp();
-            float pw[PER_LANE];
-#pragma unroll
-            for (int i = 0; i < PER_LANE; ++i) { const Cpx<float> v = buf[lane + 32 * i]; pw[i] = v.x * v.x + v.y * v.y; }
-            nyq = __shfl_sync(0xffffffffu, nyq, 0);
-            __syncwarp();
-            pbuf[lane] = 0.0f;                                           // kPbufLead zeros
-#pragma unroll
-            for (int i = 0; i < PER_LANE; ++i) pbuf[kPbufLead + lane + 32 * i] = pw[i];
-            if (lane == 0) pbuf[kPbufLead + M] = nyq * nyq;
-            if (lane < 4) pbuf[kPbufLead + M + 1 + lane] = 0.0f;
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < kMaxMelsPerLane; ++q) {
-                const int e = q * 32 + lane;
-                const int m = fb_mel[e];
-                const int ln = fb_len[e];
-                const Vec4<float>* pb = reinterpret_cast<const Vec4<float>*>(pbuf + kPbufLead + fb_start[e]);
-                const float4* w = reinterpret_cast<const float4*>(fb_w + fb_off[e]);
-                float acc = 0.0f;
-                for (int k = 0; k < ln; ++k) {
-                    const Vec4<float> pv = pb[k];
-                    const float4 wv = w[k];
-                    acc += pv.x * wv.x; acc += pv.y * wv.y; acc += pv.z * wv.z; acc += pv.w * wv.w;
-                }
-                if (m >= 0) tile[m * (FC + 1) + f] = db10(acc > p.amin ? acc : p.amin);
-            }
-            __syncwarp();
-        }
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < n_mels * nf; idx += blockDim.x) {
-            const int m = idx / nf, f = idx - m * nf;
-            p.out[((long long)clip * n_mels + m) * p.n_frames + t0 + f] = tile[m * (FC + 1) + f];
-        }
-        __syncthreads();
     }
 }
 

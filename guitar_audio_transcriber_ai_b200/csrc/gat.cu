@@ -153,7 +153,7 @@ struct gat_ctx {
     gat_config cfg{};
     int64_t launches = 0;
     // tables
-    DevBuf tw32, w2_32, tw64, w2_64, win_mel, win_mfcc, win64, dct, tw_generic;
+    DevBuf tw32, w2_32, tw64, w2_64, tw_mel, w2_mel, win_mel, win_mel_half, win_mfcc, win64, dct;
     SparseFbDev fb_mel, fb_mfcc;
     // models
     DevBuf mlp_params; int mlp_dims[kMlpMaxLayers + 1] = {0}; int mlp_n_linear = 0; int mlp_n_params = 0;
@@ -317,37 +317,40 @@ extern "C" int gat_ctx_create(const gat_config* cfg, int device, gat_ctx** out) 
 #else
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
 #endif
-    // FFT twiddles, computed in long double and rounded once
-    std::vector<Cpx<double>> tw(1024), w2(1024);
-    std::vector<Cpx<float>> twf(1024), w2f(1024);
-    for (int k2 = 0; k2 < 32; ++k2)
-        for (int n1 = 0; n1 < 32; ++n1) {
-            const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)(n1 * k2) / 1024.0L;
-            tw[k2 * 32 + n1] = Cpx<double>{(double)cosl(a), (double)sinl(a)};
+    // FFT twiddles (FftTables layout for an n_fft-point frame), computed in long double and rounded once
+    auto fft_tables = [](int n_fft, std::vector<Cpx<double>>& tw, std::vector<Cpx<double>>& w2) {
+        const int P = n_fft / 64, C = n_fft / 2;
+        const long double two_pi = 2.0L * 3.14159265358979323846264338327950288L;
+        tw.resize((size_t)P * 32); w2.resize((size_t)P * 16);
+        for (int k2 = 0; k2 < P; ++k2)
+            for (int n1 = 0; n1 < 32; ++n1) {
+                const long double a = -two_pi * (long double)(n1 * k2) / (long double)C;
+                tw[k2 * 32 + n1] = Cpx<double>{(double)cosl(a), (double)sinl(a)};
+            }
+        for (int k = 0; k < P * 16; ++k) {
+            const long double a = -two_pi * (long double)k / (long double)n_fft;
+            w2[k] = Cpx<double>{(double)cosl(a), (double)sinl(a)};
         }
-    for (int k = 0; k < 1024; ++k) {
-        const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / 2048.0L;
-        w2[k] = Cpx<double>{(double)cosl(a), (double)sinl(a)};
-    }
-    for (int i = 0; i < 1024; ++i) {
-        twf[i] = Cpx<float>{(float)tw[i].x, (float)tw[i].y};
-        w2f[i] = Cpx<float>{(float)w2[i].x, (float)w2[i].y};
-    }
+    };
+    auto to_float = [](const std::vector<Cpx<double>>& a) {
+        std::vector<Cpx<float>> f(a.size());
+        for (size_t i = 0; i < a.size(); ++i) f[i] = Cpx<float>{(float)a[i].x, (float)a[i].y};
+        return f;
+    };
+    std::vector<Cpx<double>> tw, w2, tw_m, w2_m;
+    fft_tables(2048, tw, w2);
+    fft_tables(cfg->mel_n_fft, tw_m, w2_m);
+    const std::vector<Cpx<float>> twf = to_float(tw), w2f = to_float(w2), twmf = to_float(tw_m), w2mf = to_float(w2_m);
     std::vector<float> win_mfcc(2048);
     for (int i = 0; i < 2048; ++i) win_mfcc[i] = (float)cfg->stft_window[i];
     int rc = 0;
-    rc |= upload(c->tw64, tw.data(), 1024); rc |= upload(c->w2_64, w2.data(), 1024);
-    rc |= upload(c->tw32, twf.data(), 1024); rc |= upload(c->w2_32, w2f.data(), 1024);
+    rc |= upload(c->tw64, tw.data(), tw.size()); rc |= upload(c->w2_64, w2.data(), w2.size());
+    rc |= upload(c->tw32, twf.data(), twf.size()); rc |= upload(c->w2_32, w2f.data(), w2f.size());
+    rc |= upload(c->tw_mel, twmf.data(), twmf.size()); rc |= upload(c->w2_mel, w2mf.data(), w2mf.size());
     rc |= upload(c->win_mel, cfg->mel_window, (size_t)cfg->mel_n_fft);
-    if (cfg->mel_n_fft != 2048) {   // generic path: W_M^k, M = n_fft/2, k < M/2
-        const int M = cfg->mel_n_fft / 2;
-        std::vector<Cpx<float>> tg(M / 2);
-        for (int k = 0; k < M / 2; ++k) {
-            const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)M;
-            tg[k] = Cpx<float>{(float)cosl(a), (float)sinl(a)};
-        }
-        rc |= upload(c->tw_generic, tg.data(), tg.size());
-    }
+    std::vector<float> win_half(cfg->mel_n_fft);
+    for (int i = 0; i < cfg->mel_n_fft; ++i) win_half[i] = 0.5f * cfg->mel_window[i];
+    rc |= upload(c->win_mel_half, win_half.data(), win_half.size());
     rc |= upload(c->win_mfcc, win_mfcc.data(), 2048);
     rc |= upload(c->win64, cfg->stft_window, 2048);
     rc |= upload(c->dct, cfg->dct, (size_t)cfg->mfcc_n_mfcc * cfg->mfcc_n_mels);
@@ -360,7 +363,7 @@ extern "C" int gat_ctx_create(const gat_config* cfg, int device, gat_ctx** out) 
 
 extern "C" void gat_ctx_destroy(gat_ctx* c) {
     if (!c) return;
-    DevBuf* all[] = {&c->tw_generic, &c->tw32, &c->w2_32, &c->tw64, &c->w2_64, &c->win_mel, &c->win_mfcc, &c->win64, &c->dct,
+    DevBuf* all[] = {&c->tw_mel, &c->w2_mel, &c->win_mel_half, &c->tw32, &c->w2_32, &c->tw64, &c->w2_64, &c->win_mel, &c->win_mfcc, &c->win64, &c->dct,
                      &c->fb_mel.start, &c->fb_mel.len, &c->fb_mel.off, &c->fb_mel.mel, &c->fb_mel.w,
                      &c->fb_mfcc.start, &c->fb_mfcc.len, &c->fb_mfcc.off, &c->fb_mfcc.mel, &c->fb_mfcc.w,
                      &c->mlp_params, &c->conv_w_tc[1], &c->conv_w_tc[2], &c->fc1_w_tc, &c->feat_planes, &c->hid, &c->tc_debug_buf, &c->conv_w[0], &c->conv_w[1], &c->conv_w[2], &c->conv_b[0], &c->conv_b[1], &c->conv_b[2],
@@ -470,27 +473,34 @@ int launch_clip_scale(gat_ctx* c, const float* audio, int64_t N, int64_t n, void
     return 0;
 }
 
-template <typename T, int kOut, int kThreads>
+template <typename T, int kOut, int kThreads, int P>
 int launch_stft_mel(gat_ctx* c, StftMelParams<T> p, void* stream) {
+    using G = FftGeom<P>;
     const int nwarps = kThreads / 32;
+    const int per_round = nwarps * G::F;                     // frames one pass of the CTA's warps transforms
+    auto smem_for = [&](int fc, bool async) { return stft_mel_smem_bytes<T, P>(nwarps, fc, p.hop, p.fb.n_mels, p.fb.nnz, kOut == kOutImage, async); };
     int fc = (int)(8192 / p.hop) + 1;
     fc = fc > 32 ? 32 : fc;
     if (sizeof(T) == 8) fc = fc > 8 ? 8 : fc;
-    // Asynchronous prefetch needs a second (raw) copy of the chunk in shared memory: use it when at least one frame
-    // per warp still fits (CNN chain at hop 256: 16 frames), otherwise stage synchronously with the larger chunk.
+    if (fc > per_round) fc = fc / per_round * per_round;     // whole rounds
+    else if (sizeof(T) == 4) fc = per_round;                 // at least one frame group per warp
+    while (fc > per_round && smem_for(fc, false) > 227 * 1024) fc -= per_round;
+    while (fc > 1 && smem_for(fc, false) > 227 * 1024) fc = (fc + 1) / 2;
+    // Asynchronous prefetch needs a second (raw) copy of the chunk in shared memory: use it when at least one round
+    // of frames still fits (CNN chain at hop 256: 16 frames), otherwise stage synchronously with the larger chunk.
     bool async = false;
     if (sizeof(T) == 4) {
         int fa = fc;
-        while (fa > nwarps && stft_mel_smem_bytes<T>(nwarps, fa, p.hop, p.fb.n_mels, p.fb.nnz, kOut == kOutImage, true) > 227 * 1024) fa = (fa + 1) / 2;
-        if (fa >= nwarps && stft_mel_smem_bytes<T>(nwarps, fa, p.hop, p.fb.n_mels, p.fb.nnz, kOut == kOutImage, true) <= 227 * 1024) { async = true; fc = fa; }
+        while (fa > per_round && smem_for(fa, true) > 227 * 1024) fa -= per_round;
+        if (fa >= per_round && smem_for(fa, true) <= 227 * 1024) { async = true; fc = fa; }
     }
     p.use_async = async ? 1 : 0;
     if (fc > p.n_frames) fc = p.n_frames;
     p.frames_per_cta = fc;
     p.chunks_per_clip = (p.n_frames + fc - 1) / fc;
-    const size_t smem = stft_mel_smem_bytes<T>(nwarps, fc, p.hop, p.fb.n_mels, p.fb.nnz, kOut == kOutImage, async);
-    if (smem > 227 * 1024) return fail("stft_mel: %zu bytes of shared memory needed (hop %d)", smem, p.hop);
-    auto kfn = stft_mel_kernel<T, kOut, kThreads>;
+    const size_t smem = smem_for(fc, async);
+    if (smem > 227 * 1024) return fail("stft_mel: %zu bytes of shared memory needed (n_fft %d, hop %d)", smem, G::N, p.hop);
+    auto kfn = stft_mel_kernel<T, kOut, kThreads, P>;
     GAT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long work = (long long)p.N * p.chunks_per_clip;
     const unsigned grid = (unsigned)(work < c->num_sms ? work : c->num_sms);
@@ -499,45 +509,24 @@ int launch_stft_mel(gat_ctx* c, StftMelParams<T> p, void* stream) {
     return 0;
 }
 
-template <int LOG2M>
-int launch_stft_generic(gat_ctx* c, StftGenericParams p, void* stream) {
-    const int threads = 256, nwarps = threads / 32;
-    int fc = 32;
-    while (fc > 1 && stft_generic_smem_bytes<LOG2M>(nwarps, fc, p.hop, p.fb.n_mels, p.fb.nnz) > 227 * 1024) fc = (fc + 1) / 2;
-    if (fc > p.n_frames) fc = p.n_frames;
-    p.frames_per_cta = fc;
-    p.chunks_per_clip = (p.n_frames + fc - 1) / fc;
-    const size_t smem = stft_generic_smem_bytes<LOG2M>(nwarps, fc, p.hop, p.fb.n_mels, p.fb.nnz);
-    if (smem > 227 * 1024) return fail("stft_mel (generic n_fft): %zu bytes of shared memory needed", smem);
-    auto kfn = stft_mel_generic_kernel<LOG2M>;
-    GAT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long work = (long long)p.N * p.chunks_per_clip;
-    KNAME("stft_mel_generic_image");
-    LAUNCH(c, kfn, (unsigned)(work < c->num_sms ? work : c->num_sms), threads, smem, stream, p);
-    return 0;
-}
-
 int run_melspec(gat_ctx* c, const float* audio, int64_t N, int64_t n, bool normalize, bool scale_ready, float* out, void* stream) {
     const int n_fft = c->cfg.mel_n_fft;
     if (n <= n_fft / 2) return fail("melspec: clips of %lld samples are too short for reflect padding of %d", (long long)n, n_fft / 2);
     if (normalize && !scale_ready && launch_clip_scale(c, audio, N, n, stream)) return 1;
-    if (n_fft != 2048) {
-        StftGenericParams g{};
-        g.audio = audio; g.n = n; g.N = (int)N; g.clip_scale = normalize ? c->clip_scale.as<float>() : nullptr;
-        g.n_fft = n_fft; g.hop = c->cfg.mel_hop; g.n_frames = (int)(1 + n / c->cfg.mel_hop);
-        g.window = c->win_mel.as<float>(); g.tw = c->tw_generic.as<Cpx<float>>(); g.fb = c->fb_mel.view();
-        g.amin = 1e-10f; g.out = out;
-        if (n_fft == 512) return launch_stft_generic<8>(c, g, stream);
-        if (n_fft == 1024) return launch_stft_generic<9>(c, g, stream);
-        return launch_stft_generic<11>(c, g, stream);
-    }
     StftMelParams<float> p{};
     p.audio = audio; p.n = n; p.N = (int)N; p.clip_scale = normalize ? c->clip_scale.as<float>() : nullptr;
     p.frame_gate = nullptr; p.sample_gate = 0.0f; p.gate_hop = 512;
     p.hop = c->cfg.mel_hop; p.n_frames = (int)(1 + n / c->cfg.mel_hop); p.pad_mode = kPadReflect;
-    p.window = c->win_mel.as<float>(); p.tw = c->tw32.as<Cpx<float>>(); p.w2 = c->w2_32.as<Cpx<float>>();
+    p.window = c->win_mel.as<float>(); p.window_half = c->win_mel_half.as<float>();
+    p.tw = c->tw_mel.as<Cpx<float>>(); p.w2 = c->w2_mel.as<Cpx<float>>();
     p.fb = c->fb_mel.view(); p.amin = 1e-10f; p.out = out; p.spec_max = nullptr;
-    return launch_stft_mel<float, kOutImage, 512>(c, p, stream);
+    switch (n_fft) {     // MelSpecConfig.N_FFT is configurable (features.py:296-302; BASELINE config 5 sweeps it)
+        case 512:  return launch_stft_mel<float, kOutImage, 512, 8>(c, p, stream);
+        case 1024: return launch_stft_mel<float, kOutImage, 512, 16>(c, p, stream);
+        case 2048: return launch_stft_mel<float, kOutImage, 512, 32>(c, p, stream);
+        case 4096: return launch_stft_mel<float, kOutImage, 256, 64>(c, p, stream);
+    }
+    return fail("melspec: n_fft %d unsupported", n_fft);
 }
 
 int run_mfcc(gat_ctx* c, const float* audio, int64_t N, int64_t n, bool normalize, bool scale_ready, float* out, int ld, void* stream) {
@@ -551,7 +540,7 @@ int run_mfcc(gat_ctx* c, const float* audio, int64_t N, int64_t n, bool normaliz
     p.hop = 512; p.n_frames = T; p.pad_mode = kPadZero;
     p.window = c->win_mfcc.as<float>(); p.tw = c->tw32.as<Cpx<float>>(); p.w2 = c->w2_32.as<Cpx<float>>();
     p.fb = c->fb_mfcc.view(); p.amin = 1e-10f; p.out = c->spec.as<float>(); p.spec_max = c->spec_max.as<long long>();
-    if (launch_stft_mel<float, kOutSpec, 512>(c, p, stream)) return 1;
+    if (launch_stft_mel<float, kOutSpec, 512, 32>(c, p, stream)) return 1;
     MfccFinishParams f{};
     f.spec = c->spec.as<float>(); f.spec_max = c->spec_max.as<long long>(); f.T = T; f.n_mels = 128;
     f.n_mfcc = c->cfg.mfcc_n_mfcc; f.dct = c->dct.as<float>(); f.top_db = 80.0f; f.out = out; f.ld = ld;
@@ -877,7 +866,7 @@ extern "C" int gat_segment(gat_ctx* c, const float* y, int64_t L, const gat_slic
     p.hop = sp->onset_hop; p.n_frames = To; p.pad_mode = kPadZero;
     p.window = c->win64.as<double>(); p.tw = c->tw64.as<Cpx<double>>(); p.w2 = c->w2_64.as<Cpx<double>>();
     p.fb = c->fb_mfcc.view(); p.amin = 1e-10; p.out = c->spec.as<double>(); p.spec_max = spec_max;
-    if (launch_stft_mel<double, kOutSpec, 192>(c, p, st)) return 1;
+    if (launch_stft_mel<double, kOutSpec, 192, 32>(c, p, st)) return 1;
 
     // 5-7: flux envelope -> normalise + candidate peaks -> sequential wait rule
     FluxParams fp{c->spec.as<double>(), spec_max, To, 128, 1 + 2048 / (2 * sp->onset_hop), 80.0, c->seg_env.as<double>(), env_minmax};
