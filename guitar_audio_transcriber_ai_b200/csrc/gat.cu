@@ -12,6 +12,7 @@ using std::min;
 #include "fc_tc.cuh"
 #include "features.cuh"
 #include "fft.cuh"
+#include "frontend.cuh"
 #include "infer.cuh"
 #include "onset.cuh"
 #include "yin.cuh"
@@ -822,6 +823,43 @@ extern "C" int gat_infer(gat_ctx* c, const float* mfcc, int32_t ld, const float*
     if (!ml) { if (c->logits_mlp.ensure((size_t)N * classes * sizeof(float))) return 1; ml = c->logits_mlp.as<float>(); }
     if (run_cnn(c, mel, N, T, cnn_probs, cl, stream)) return 1;
     return run_mlp_ensemble(c, mfcc, ld, N, cnn_probs, probs, mlp_probs, ml, index, conf, stream);
+}
+
+// ------------------------------------------------------------------------------------------------- file front end
+extern "C" int gat_pcm16_roundtrip(gat_ctx* c, float* audio, int64_t count, void* stream) {
+    if (!c || (!audio && count > 0) || count < 0) return fail("gat_pcm16_roundtrip: bad argument");
+    if (count == 0) return 0;
+    const long long blocks = (count + 255) / 256;
+    const unsigned grid = (unsigned)(blocks < 8LL * c->num_sms ? blocks : 8LL * c->num_sms);
+    LAUNCH(c, pcm16_roundtrip_kernel, grid, 256, 0, stream, audio, (long long)count);
+    return 0;
+}
+
+extern "C" int gat_decode_mono(gat_ctx* c, const void* frames_dev, int32_t sample_format, int64_t frames, int32_t channels,
+                               float* out, void* stream) {
+    if (!c || !frames_dev || !out || frames < 1 || channels < 1) return fail("gat_decode_mono: bad argument");
+    const long long blocks = (frames + 255) / 256;
+    const unsigned grid = (unsigned)(blocks < 8LL * c->num_sms ? blocks : 8LL * c->num_sms);
+    if (sample_format == GAT_SAMPLE_PCM16) {
+        LAUNCH(c, pcm16_to_mono_kernel, grid, 256, 0, stream, (const short*)frames_dev, (long long)frames, (int)channels, out);
+    } else if (sample_format == GAT_SAMPLE_FLOAT32) {
+        LAUNCH(c, f32_to_mono_kernel, grid, 256, 0, stream, (const float*)frames_dev, (long long)frames, (int)channels, out);
+    } else {
+        return fail("gat_decode_mono: sample_format %d unknown", sample_format);
+    }
+    return 0;
+}
+
+extern "C" int gat_resample(gat_ctx* c, const float* in, int64_t N, int64_t n_in, int32_t up, int32_t down,
+                            const double* taps_dev, int32_t half_len, float* out, int64_t n_out, void* stream) {
+    if (!c || !in || !out || !taps_dev || N < 1 || n_in < 1 || up < 1 || down < 1 || half_len < 0)
+        return fail("gat_resample: bad argument");
+    if (n_out != (n_in * up + down - 1) / down) return fail("gat_resample: n_out must be ceil(n_in*up/down) = %lld", (long long)((n_in * up + down - 1) / down));
+    if (N > 65535) return fail("gat_resample: at most 65535 signals per call");
+    ResampleParams p{in, (long long)n_in, out, (long long)n_out, taps_dev, (int)half_len, (int)up, (int)down};
+    dim3 grid((unsigned)((n_out + 255) / 256), (unsigned)N);
+    LAUNCH(c, resample_poly_kernel, grid, 256, 0, stream, p);
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------- segmentation

@@ -55,6 +55,7 @@ class Engine:
         with self._on_device():
             self.lib.check(self.lib.gat_ctx_create(C.byref(cfg), self.device.index or 0, C.byref(handle)), ValueError)
         self._ctx = handle
+        self._resample_cache = {}
 
     # ------------------------------------------------------------------ plumbing
     def _on_device(self):
@@ -264,6 +265,53 @@ class Engine:
                 "h2d_bytes": N * n * 4, "d2h_bytes": N * 12 + (N * K * 4 if want_probs else 0)}
 
     # ------------------------------------------------------------------ segmentation
+    # ------------------------------------------------------------------ file front end
+    def decode_mono(self, frames) -> torch.Tensor:
+        """librosa.load's decode + to_mono on the device: interleaved [frames, channels] int16 or float32."""
+        a = torch.as_tensor(np.array(frames, copy=True) if isinstance(frames, np.ndarray) and not frames.flags.writeable else frames)
+        if a.dim() == 1:
+            a = a.unsqueeze(1)
+        if a.dtype == torch.int16:
+            fmt = 0
+        elif a.dtype == torch.float32:
+            fmt = 1
+        else:
+            raise ValueError("decode_mono: int16 or float32 frames expected")
+        a = a.to(self.device).contiguous()
+        out = self._empty((a.shape[0],), torch.float32)
+        with self._on_device():
+            self.lib.check(self.lib.gat_decode_mono(self._ctx, _lib.ptr(a), fmt, a.shape[0], a.shape[1], _lib.ptr(out), self._stream()))
+        return out
+
+    def pcm16_roundtrip_(self, audio: torch.Tensor) -> torch.Tensor:
+        """sf.write(PCM_16) followed by librosa.load, in place on a float32 device tensor."""
+        if audio.dtype != torch.float32 or not audio.is_contiguous() or audio.device != self.device:
+            raise ValueError("pcm16_roundtrip_: contiguous float32 tensor on the engine's device expected")
+        with self._on_device():
+            self.lib.check(self.lib.gat_pcm16_roundtrip(self._ctx, _lib.ptr(audio), audio.numel(), self._stream()))
+        return audio
+
+    def resample(self, audio, orig_sr: int, target_sr: int) -> torch.Tensor:
+        """librosa.load(sr=target_sr) / librosa.resample for [n] or [N, n] signals; output length ceil(n*ratio)."""
+        x = self._clips(audio)
+        squeeze = torch.as_tensor(audio).dim() == 1
+        if int(orig_sr) == int(target_sr):
+            return x[0] if squeeze else x
+        key = (int(orig_sr), int(target_sr))
+        if key not in self._resample_cache:
+            up, down, taps, half = tables.resample_filter(*key)
+            self._resample_cache[key] = (up, down, torch.from_numpy(taps).to(self.device), half)
+        up, down, taps, half = self._resample_cache[key]
+        n_in = x.shape[1]
+        n_out = (n_in * up + down - 1) // down
+        out = self._empty((x.shape[0], n_out), torch.float32)
+        with self._on_device():
+            for i in range(0, x.shape[0], 65535):
+                xi = x[i:i + 65535]
+                self.lib.check(self.lib.gat_resample(self._ctx, _lib.ptr(xi), xi.shape[0], n_in, up, down, _lib.ptr(taps), half,
+                                                     _lib.ptr(out[i:i + 65535]), n_out, self._stream()))
+        return out[0] if squeeze else out
+
     def slicer_params(self, L: int, length_sec: float, cfg=None) -> _lib.GatSlicerParams:
         cfg = cfg or SLICER_CONFIG
         sr = self.sample_rate

@@ -93,3 +93,23 @@ def long_audio(n_phrases: int, sr: int = 22050, seed0: int = 0):
         starts.append(s + off)
         off += len(y)
     return np.concatenate(parts), np.concatenate(midis), np.concatenate(starts)
+
+
+def wav_case(name: str):
+    """Deterministic WAV-file test inputs for the file pipeline (Transcriber.transcribe): returns
+    (int16 frames [n] or [n, channels], sample rate).  The same arrays are written to disk by the golden-vector
+    generator and by the tests, so no audio needs to be stored.
+
+      mono22050   : config-1 phrase (seed 0), mono PCM_16 at 22 050 Hz - no resampling anywhere
+      stereo32000 : config-1 phrase (seed 5) synthesised at 32 000 Hz, two channels with different gains,
+                    PCM_16 - exercises the channel mean and both resampling steps (32 000 -> 22 050 -> 11 025)
+    """
+    def q16(x):
+        return np.clip(np.rint(x * 32767.0), -32768, 32767).astype(np.int16)
+    if name == "mono22050":
+        y, _, _ = phrase(0, sr=22050)
+        return q16(y), 22050
+    if name == "stereo32000":
+        y, _, _ = phrase(5, sr=32000)
+        return np.stack([q16(0.9 * y), q16(0.7 * y)], axis=1), 32000
+    raise KeyError(name)

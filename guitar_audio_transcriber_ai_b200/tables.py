@@ -129,3 +129,24 @@ def onset_detect_params(sr: int, hop: int) -> dict:
     out = {k: int(np.ceil(v)) for k, v in vals.items()}
     out["delta"] = np.float32(0.07)
     return out
+
+
+def resample_filter(orig_sr: int, target_sr: int, attenuation_db: float = 120.0, passband: float = 0.913):
+    """Polyphase low-pass for gat_resample: (up, down, taps float64 [2*half+1] scaled by up, half).
+
+    The reference resamples with soxr's HQ recipe through ``librosa.load`` / ``librosa.resample``
+    (audio/loading.py:85, transcribe.py:173): linear phase, pass band kept to 0.913 of the lower Nyquist
+    frequency, stop band from that Nyquist frequency on, about 20 bits of rejection.  soxr is not available, so
+    this designs a Kaiser-windowed sinc to the same specification; the arithmetic that applies it restates
+    scipy.signal.resample_poly.  Not bit-identical to soxr (file front end)."""
+    g = math.gcd(int(orig_sr), int(target_sr))
+    up, down = int(target_sr) // g, int(orig_sr) // g
+    q = max(up, down)
+    width = (1.0 - passband) / q                       # transition band, in units of the up-sampled grid's Nyquist
+    cutoff = (1.0 + passband) / (2.0 * q)              # centre of the transition band
+    beta = 0.1102 * (attenuation_db - 8.7)
+    half = int(math.ceil((attenuation_db - 8.0) / (2.285 * math.pi * width) / 2.0))
+    n = np.arange(-half, half + 1, dtype=np.float64)
+    h = cutoff * np.sinc(cutoff * n) * np.kaiser(2 * half + 1, beta)
+    h /= h.sum()
+    return up, down, np.ascontiguousarray(h * up), half

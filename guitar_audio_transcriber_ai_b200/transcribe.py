@@ -2,11 +2,13 @@
 
 ``transcribe_note`` keeps the reference signature and result dict; ``transcribe_notes`` (batch of clips)
 and ``transcribe_audio`` (whole signal in memory: segmentation + features + ensemble + YIN) are the
-batched additions.  ``transcribe(audio_path)`` needs the file front end (decode, soxr resample, PCM_16
-round trip) that SURVEY 8f-1 leaves for later and raises NotImplementedError.
+batched additions.  ``transcribe(audio_path)`` is the file pipeline: WAV decode, channel mean and
+resampling on the GPU, slicing, the PCM_16 round trip the reference's clip files go through, features with the
+checkpoint's scaler, ensemble, per-clip YIN.  Resampling restates soxr_hq's specification, not its bits.
 """
 from __future__ import annotations
 
+from datetime import datetime
 from pathlib import Path
 
 import numpy as np
@@ -15,7 +17,7 @@ import torch
 from .audio.features import MelFeatureBuilder
 from .audio.slicing import AudioSlicer
 from .checkpoint import load_checkpoint
-from .config import CLIP_DURATION, CNN_CONFIG, MLP_CONFIG, SLICER_CONFIG, TARGET_SR
+from .config import CLIP_DURATION, CNN_CONFIG, INFERENCE_OUTPUT_ROOT, MLP_CONFIG, SLICER_CONFIG, TARGET_SR
 from .dsp.yin import YinDsp
 from .engine import Engine
 from .note_predictor import NotePredictor
@@ -69,10 +71,54 @@ class Transcriber:
         """transcribe.py:147-199 for one clip."""
         return self.transcribe_notes(np.asarray(audio)[None, :], clip_duration, sr_in)
 
-    def transcribe(self, audio_path, out_root=None, audio_name="transcribe_audio", target_sr=TARGET_SR,
-                   clip_duration=CLIP_DURATION) -> dict:
-        raise NotImplementedError("file front end (decode / soxr resample / PCM_16 clips) is not part of the "
-                                  "accelerated hot path yet; load the audio and call transcribe_audio(y, sr)")
+    def transcribe(self, audio_path, out_root=INFERENCE_OUTPUT_ROOT, audio_name: str = "transcribe_audio",
+                   target_sr: int = TARGET_SR, clip_duration: float = CLIP_DURATION, save_clips: bool = True) -> dict:
+        """transcribe.py:77-144: slice the file at ``target_sr``, pass every clip through PCM_16 (the reference
+        writes clip .wav files and loads them back), bring the clips to the checkpoint's rate, extract features
+        WITH the checkpoint's scaler, predict, and run YIN on the raw clips (``dsp_info``).
+
+        ``save_clips`` keeps the reference's side effect (``out_root/<name>_<timestamp>/<name>/NNNN_clip__T.TTTs.wav``);
+        the clips are never read back, the device copy is already what a reload would return.  Clips come back in
+        onset order (the reference's order is whatever ``os.listdir`` yields)."""
+        ckpt_sr = self._target_sr()
+        self._feature_flags()
+        slicer_engine = self.engine if int(target_sr) == int(ckpt_sr) else self.slicer.engine(target_sr)
+        y, _ = self.slicer.load_wav(audio_path, target_sr)
+        seg = slicer_engine.segment(y, clip_duration, SLICER_CONFIG)
+        clips = seg["clips"]
+        if save_clips:                                            # float clips -> PCM_16 files, as save_clip does
+            out_dir = Path(out_root) / f"{audio_name}_{datetime.now().strftime('%m-%d_%H-%M-%S')}" / audio_name
+            out_dir.mkdir(exist_ok=True, parents=True)
+            table = seg["table"].cpu().numpy()
+            onsets = seg["onsets"].cpu().numpy()
+            for clip, row in zip(clips.cpu().numpy(), table):
+                self.slicer.save_clip(clip, target_sr, out_dir, int(row[0]), float(onsets[int(row[0])]) / target_sr)
+        if clips.shape[0]:
+            slicer_engine.pcm16_roundtrip_(clips)                 # what loading those files back returns
+        if clips.shape[0] == 0:
+            raise FileNotFoundError("load_audio_dataset: No audio files found.")
+        if int(target_sr) != int(ckpt_sr):                       # AudioDatasetLoader: librosa.load(sr=ckpt_sr) + fix_len
+            clips = self.engine.resample(clips.to(self.engine.device), target_sr, ckpt_sr)
+        fixed = int(ckpt_sr * clip_duration)
+        if clips.shape[1] > fixed:
+            clips = clips[:, :fixed].contiguous()
+        elif clips.shape[1] < fixed:
+            clips = torch.nn.functional.pad(clips, (0, fixed - clips.shape[1]))
+        return self._predict_sliced(clips, seg)
+
+    def _predict_sliced(self, clips, seg) -> dict:
+        self.engine.set_ensemble_weights(self.predictor.mlp_weight, self.predictor.cnn_weight)
+        out = self.engine.transcribe_clips(clips, yin_on_normalized=False, apply_scaler=self.engine.has_scaler,
+                                           return_features=True)
+        result = self.predictor._result(out)
+        hz = out["yin_hz"].cpu().numpy()
+        result["dsp_info"] = []
+        for v in hz:
+            m, name, mf = YinDsp.round_to_nearest_pitch(float(v))
+            result["dsp_info"].append((float(v), {"midi": m, "note_name": name, "midi_float": mf}))
+        result["onsets"] = [int(v) for v in seg["onsets"].cpu().numpy()]
+        result["slice_table"] = seg["table"].cpu().numpy()
+        return result
 
     # ------------------------------------------------------------------ batched additions
     def transcribe_notes(self, audio, clip_duration: float = CLIP_DURATION, sr_in: int = TARGET_SR) -> dict:
@@ -80,11 +126,10 @@ class Transcriber:
         pad/trim to int(clip_duration*target_sr), features WITHOUT the scaler, YIN on the normalised audio."""
         target_sr = self._target_sr()
         self._feature_flags()
-        if sr_in != target_sr:
-            raise NotImplementedError("resampling (librosa.resample, soxr_hq) is out of scope: pass audio at "
-                                      f"the checkpoint rate {target_sr}")
         target_len = int(clip_duration * target_sr)
         a = self.engine._clips(audio if torch.is_tensor(audio) else np.asarray(audio, dtype=np.float32))
+        if sr_in != target_sr:                                   # transcribe.py:172-173
+            a = self.engine.resample(a, sr_in, target_sr)
         if a.shape[1] < target_len:
             a = torch.nn.functional.pad(a, (0, target_len - a.shape[1]))
         elif a.shape[1] > target_len:
@@ -98,21 +143,11 @@ class Transcriber:
         per-clip YIN ``dsp_info``; plus ``onsets`` and ``slice_table``."""
         target_sr = self._target_sr()
         self._feature_flags()
+        yt = torch.as_tensor(np.asarray(y, dtype=np.float32) if not torch.is_tensor(y) else y)
         if sr is not None and sr != target_sr:
-            raise NotImplementedError(f"resampling is out of scope: pass audio at {target_sr} Hz")
-        seg = self.engine.segment(np.asarray(y, dtype=np.float32) if not torch.is_tensor(y) else y, clip_duration, SLICER_CONFIG)
+            yt = self.engine.resample(yt.reshape(-1), sr, target_sr)
+        seg = self.engine.segment(yt, clip_duration, SLICER_CONFIG)
         clips = seg["clips"]
         if clips.shape[0] == 0:
             raise FileNotFoundError("load_audio_dataset: No audio files found.")
-        self.engine.set_ensemble_weights(self.predictor.mlp_weight, self.predictor.cnn_weight)
-        out = self.engine.transcribe_clips(clips, yin_on_normalized=False, apply_scaler=self.engine.has_scaler,
-                                           return_features=True)
-        result = self.predictor._result(out)
-        hz = out["yin_hz"].cpu().numpy()
-        result["dsp_info"] = []
-        for v in hz:
-            m, name, mf = YinDsp.round_to_nearest_pitch(float(v))
-            result["dsp_info"].append((float(v), {"midi": m, "note_name": name, "midi_float": mf}))
-        result["onsets"] = [int(v) for v in seg["onsets"].cpu().numpy()]
-        result["slice_table"] = seg["table"].cpu().numpy()
-        return result
+        return self._predict_sliced(clips, seg)

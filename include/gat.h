@@ -133,6 +133,27 @@ int gat_segment(gat_ctx* ctx, const float* y_dev, int64_t L, const gat_slicer_pa
                 int32_t* n_clips_dev, float* rms_db_dev, double* env_dev, int64_t* frames_dev,
                 int32_t* n_frames_dev, void* stream);
 
+/* ---- file front end (Transcriber.transcribe) ---------------------------------------- */
+
+#define GAT_SAMPLE_PCM16   0
+#define GAT_SAMPLE_FLOAT32 1
+
+/* sf.write(.wav) + librosa.load of a clip (audio/slicing.py:144 then audio/loading.py:85): every sample goes
+ * through PCM_16 once, x <- rint(x * 32767) / 32768, in place on `count` device floats. */
+int gat_pcm16_roundtrip(gat_ctx* ctx, float* audio_dev, int64_t count, void* stream);
+
+/* librosa.load's decode + to_mono (audio/slicing.py:25): interleaved frames of `channels` samples
+ * (PCM_16 scaled by 1/32768 as libsndfile does, or float32) -> float32 channel mean, `frames` outputs. */
+int gat_decode_mono(gat_ctx* ctx, const void* frames_dev, int32_t sample_format, int64_t frames, int32_t channels,
+                    float* out_dev, void* stream);
+
+/* librosa.load(sr=...) / librosa.resample (audio/loading.py:85, transcribe.py:173) for N signals of n_in
+ * samples: polyphase FIR by up/down with the caller's taps (float64, length 2*half_len+1, already scaled by
+ * `up`), scipy.signal.resample_poly alignment, n_out = ceil(n_in*up/down).  The reference resamples with
+ * soxr_hq, which is not reproducible here: same length convention, equivalent quality, not bit-identical. */
+int gat_resample(gat_ctx* ctx, const float* in_dev, int64_t N, int64_t n_in, int32_t up, int32_t down,
+                 const double* taps_dev, int32_t half_len, float* out_dev, int64_t n_out, void* stream);
+
 /* ---- end to end --------------------------------------------------------------------------------- */
 
 #define GAT_FLAG_YIN_ON_NORMALIZED 1   /* transcribe_note path (features.py:473)                    */

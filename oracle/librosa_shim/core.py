@@ -249,24 +249,47 @@ def yin(y, *, fmin, fmax, sr=22050, frame_length=2048, win_length=None, hop_leng
     return sr / yin_period
 
 
-# --------------------------------------------------------------------------- file front end (8f: out of scope)
+# --------------------------------------------------------------------------- file front end
+def _soxr_hq_like_filter(up, down, attenuation_db=120.0, passband=0.913):
+    """Kaiser-windowed sinc to soxr HQ's published specification (pass band to 0.913 of the lower Nyquist,
+    stop band from that Nyquist on, ~20 bits of rejection).  soxr is absent: NOT its coefficients."""
+    import scipy.signal
+    q = max(up, down)
+    width = (1.0 - passband) / q
+    cutoff = (1.0 + passband) / (2.0 * q)
+    beta = 0.1102 * (attenuation_db - 8.7)
+    half = int(np.ceil((attenuation_db - 8.0) / (2.285 * np.pi * width) / 2.0))
+    return scipy.signal.firwin(2 * half + 1, cutoff, window=("kaiser", beta))
+
+
+def resample(y, *, orig_sr, target_sr, res_type="soxr_hq", **_):
+    """librosa.resample: output length ceil(n * target/orig), float32 in -> float32 out.  The filter is the
+    soxr-HQ-like design above applied with scipy.signal.resample_poly (unpinned against soxr)."""
+    if orig_sr == target_sr:
+        return y
+    import math
+    import scipy.signal
+    g = math.gcd(int(orig_sr), int(target_sr))
+    up, down = int(target_sr) // g, int(orig_sr) // g
+    h = _soxr_hq_like_filter(up, down)
+    out = scipy.signal.resample_poly(np.asarray(y), up, down, axis=-1, window=h)
+    n_out = int(np.ceil(np.asarray(y).shape[-1] * float(target_sr) / float(orig_sr)))
+    assert out.shape[-1] == n_out
+    return np.ascontiguousarray(out, dtype=np.float32)
+
+
 def load(path, *, sr=22050, mono=True, **_):
-    """librosa.load needs soundfile + soxr, neither available; 16-bit/float WAV at the target rate only."""
+    """librosa.load: libsndfile decode to float32 (16/32-bit PCM, float WAV), channel mean, resample."""
     import scipy.io.wavfile
     sr_in, data = scipy.io.wavfile.read(path)
     if data.dtype == np.int16:
-        data = data.astype(np.float32) / 32768.0
+        data = data.astype(np.float32) / np.float32(32768.0)
     elif data.dtype == np.int32:
-        data = data.astype(np.float32) / 2147483648.0
+        data = (data.astype(np.float64) / 2147483648.0).astype(np.float32)
     data = data.astype(np.float32)
     if data.ndim == 2 and mono:
-        data = data.mean(axis=1)
+        data = np.mean(data.T, axis=0)          # librosa.to_mono on (channels, n)
     if sr is not None and sr_in != sr:
-        raise NotImplementedError("librosa_shim.load: soxr_hq resampling is out of scope (SURVEY 8f-1)")
+        data = resample(data, orig_sr=sr_in, target_sr=sr)
+        sr_in = sr
     return data, sr_in
-
-
-def resample(y, *, orig_sr, target_sr, **_):
-    if orig_sr == target_sr:
-        return y
-    raise NotImplementedError("librosa_shim.resample: soxr_hq resampling is out of scope (SURVEY 8f-1)")

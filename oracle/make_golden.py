@@ -173,12 +173,64 @@ def phrase_cases(ns):
     print("[make_golden] wrote phrases_sr22050.npz")
 
 
+FILE_CASES = {
+    # name: (wav case, mlp ckpt, cnn ckpt, slicing target_sr)
+    "mono22050": ("mono22050", "mlp_synth_sr22050.ckpt", "cnn_synth_sr22050.ckpt", 22050),
+    "stereo32000_ckpt11025": ("stereo32000", "mlp_v1.0.0.ckpt", "cnn_synth_sr11025.ckpt", 22050),
+}
+
+
+def file_cases(ns):
+    """Transcriber.transcribe(audio_path) (transcribe.py:77-144) run VERBATIM on WAV files: librosa.load ->
+    shim (decode + restated resampler), sf.write -> oracle/soundfile_standin (libsndfile PCM_16 restated).
+    os.listdir is sorted for the run (the reference iterates clips in directory order, which is arbitrary)."""
+    import os
+    import tempfile
+    import scipy.io.wavfile
+    out = {}
+    for name, (wav, mlp_name, cnn_name, target_sr) in FILE_CASES.items():
+        frames, sr_file = synth.wav_case(wav)
+        mlp_ck = ref_env.load_ckpt(CKPT / mlp_name)
+        cnn_ck = ref_env.load_ckpt(CKPT / cnn_name)
+        with tempfile.TemporaryDirectory() as tmp:
+            path = pathlib.Path(tmp) / "in.wav"
+            scipy.io.wavfile.write(str(path), sr_file, frames)
+            orig_listdir = os.listdir
+            os.listdir = lambda p=".": sorted(orig_listdir(p))
+            try:
+                with posix_safe_torch_load(), contextlib.redirect_stdout(None):
+                    tr = ns.transcribe.Transcriber(mlp_ckpt=mlp_name, cnn_ckpt=cnn_name, mlp_root=CKPT, cnn_root=CKPT)
+                    res = tr.transcribe(path, out_root=pathlib.Path(tmp) / "out", audio_name="t", target_sr=target_sr,
+                                        clip_duration=0.5)
+            finally:
+                os.listdir = orig_listdir
+            pres = port.transcribe_file(mlp_ck, cnn_ck, path, target_sr, 0.5)
+        same(res["probs"], pres["probs"], f"file[{name}] probs")
+        same(res["indices"], pres["indices"], f"file[{name}] indices")
+        assert list(res["labels"]) == list(pres["labels"])
+        ref_hz = np.array([np.nan if d[0] is None else d[0] for d in res["dsp_info"]], dtype=np.float64)
+        port_hz = np.array([np.nan if d[0] is None else d[0] for d in pres["dsp_info"]], dtype=np.float64)
+        same(ref_hz, port_hz, f"file[{name}] yin")
+        out[f"{name}_probs"] = res["probs"]
+        out[f"{name}_indices"] = res["indices"]
+        out[f"{name}_labels"] = np.array(res["labels"], dtype=str)
+        out[f"{name}_yin_hz"] = ref_hz
+        out[f"{name}_onsets"] = np.asarray(pres["onsets"], dtype=np.int64)
+        out[f"{name}_table"] = pres["slice_table"]
+        out[f"{name}_clips"] = pres["clips"]
+        print(f"[make_golden] file case {name}: {len(pres['onsets'])} onsets -> {len(res['labels'])} clips; labels {list(res['labels'])}")
+    np.savez_compressed(GOLD / "files.npz", **out)
+    print("[make_golden] wrote files.npz")
+
+
 def main():
     warnings.simplefilter("ignore")
     torch.set_num_threads(1)  # single-threaded reductions: the vectors do not depend on the core count
     ns = ref_env.install()
-    clip_cases(ns)
-    phrase_cases(ns)
+    if "--files-only" not in sys.argv:
+        clip_cases(ns)
+        phrase_cases(ns)
+    file_cases(ns)
 
 
 if __name__ == "__main__":

@@ -327,3 +327,38 @@ def transcribe_audio(mlp_ckpt, cnn_ckpt, y, sr=TARGET_SR, clip_duration=CLIP_DUR
     result["onsets"] = onsets
     result["slice_table"] = table
     return result
+
+
+# ----------------------------------------------------------------------------- file pipeline
+def pcm16_roundtrip(clip):
+    """sf.write(.wav) (slicing.py:144, libsndfile PCM_16: rint(x * 0x7FFF)) then librosa.load (loading.py:85,
+    libsndfile read: / 0x8000), restated in oracle/soundfile_standin.py and librosa_shim.load."""
+    q = np.clip(np.rint(np.asarray(clip, dtype=np.float32) * np.float32(32767.0)), -32768, 32767).astype(np.int16)
+    return q.astype(np.float32) / np.float32(32768.0)
+
+
+def transcribe_file(mlp_ckpt, cnn_ckpt, audio_path, target_sr=TARGET_SR, clip_duration=CLIP_DURATION):
+    """transcribe.py:77-144: load at ``target_sr`` -> slice -> clip files (PCM_16) -> AudioDatasetLoader at the
+    checkpoint's rate (resample + fix_len) -> features with the scaler -> predict -> YIN on the loaded clips.
+    Clips in onset order (the reference iterates os.listdir order)."""
+    ckpt_sr = mlp_ckpt["config"]["target_sr"]
+    if ckpt_sr != cnn_ckpt["config"]["target_sr"]:
+        raise ValueError("[Transcriber] Target SR mismatch.")
+    y, sr = librosa.load(str(audio_path), sr=target_sr, mono=True)          # slicing.py:25
+    onsets, clips, table = slice_in_memory(y, sr, clip_duration)
+    if len(clips) == 0:
+        raise FileNotFoundError("load_audio_dataset: No audio files found.")
+    fixed = int(ckpt_sr * clip_duration)
+    wavs = []
+    for c in clips:
+        w = pcm16_roundtrip(c)
+        w = librosa.resample(w, orig_sr=sr, target_sr=ckpt_sr)            # librosa.load(path, sr=ckpt_sr), loading.py:85
+        wavs.append(fix_len(w, fixed))                                      # loading.py:86
+    X, M = extract_inference_features(wavs, ckpt_sr, mlp_ckpt["config"]["features"]["params"],
+                                      cnn_ckpt["config"]["features"]["params"], mlp_ckpt.get("scaler"))
+    result = predict(mlp_ckpt, cnn_ckpt, X, M)
+    result["dsp_info"] = [yin_estimate_pitch(w, ckpt_sr) for w in wavs]
+    result["onsets"] = onsets
+    result["slice_table"] = table
+    result["clips"] = np.stack(wavs)
+    return result

@@ -341,3 +341,51 @@ def test_error_behaviour(tr22):
         tr22.predictor.predict(np.zeros((1, 65), np.float32), None)
     with pytest.raises(ValueError):
         tr22.engine.melspec_db(np.zeros((1, 512), np.float32))     # too short for reflect padding
+
+
+# ---------------------------------------------------------------------------------------- file front end (8f-1)
+@pytest.mark.gpu
+def test_front_end_kernels_against_oracle(tr22):
+    """decode + channel mean and the PCM_16 round trip bit-exact; the resampler within one float32 ulp."""
+    import librosa_shim
+    import port
+    import file_cases
+    eng = tr22.engine
+    rng = np.random.default_rng(3)
+    st = rng.integers(-32768, 32767, (100_001, 2)).astype(np.int16)
+    assert np.array_equal(eng.decode_mono(st).cpu().numpy(), np.mean((st.astype(np.float32) / np.float32(32768.0)).T, axis=0))
+    x = (0.9 * rng.uniform(-1, 1, (5, 11025))).astype(np.float32)
+    x[0, :5] = [1.0, -1.0, 0.5 / 32767, 1.5 / 32767, 2.5 / 32767]
+    t = torch.from_numpy(x.copy()).cuda()
+    eng.pcm16_roundtrip_(t)
+    assert np.array_equal(t.cpu().numpy(), np.stack([port.pcm16_roundtrip(r) for r in x]))
+    for a, b in ((22050, 11025), (32000, 22050), (11025, 22050), (44100, 22050), (48000, 22050)):
+        out = eng.resample(x, a, b).cpu().numpy()
+        want = np.stack([librosa_shim.resample(r, orig_sr=a, target_sr=b) for r in x])
+        assert out.shape == want.shape and np.abs(out - want).max() <= file_cases.RESAMPLE_ABS
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["mono22050", "stereo32000_ckpt11025"])
+def test_transcribe_file_matches_reference(name, tmp_path):
+    """Transcriber.transcribe(path) against vectors from the reference's own transcribe() (oracle/make_golden.py)."""
+    import file_cases
+    file_cases.check_transcribe_file("cuda:0", tmp_path, name)
+
+
+@pytest.mark.gpu
+def test_transcribe_notes_resamples_like_the_reference(tr22):
+    """transcribe_note with sr_in != target_sr (transcribe.py:172-173): resample, then the usual path."""
+    import port
+    import ref_env
+    from guitar_audio_transcriber_ai_b200 import synth
+    mlp_ck, cnn_ck = ref_env.load_ckpt(CKPT / "mlp_synth_sr22050.ckpt"), ref_env.load_ckpt(CKPT / "cnn_synth_sr22050.ckpt")
+    # 16 kHz input leaves the mel bins above 8 kHz at the float32 rounding floor of the FFT (about -140 dB re the
+    # peak): there the dB image is implementation noise in ANY float32 FFT, and the CNN sees it -> looser bound.
+    for seed, sr_in, tol in ((3, 44100, 5e-5), (5, 32000, 5e-5), (4, 16000, 1e-2)):
+        a = synth.note(float(synth.midi_to_hz(synth.random_midi(seed))), 0.5, sr_in, seed)
+        want = port.transcribe_note(mlp_ck, cnn_ck, a, 0.5, sr_in)
+        got = tr22.transcribe_note(a, 0.5, sr_in)
+        assert [str(s) for s in got["labels"]] == [str(s) for s in want["labels"]]
+        assert np.abs(got["per_model_probs"]["mlp"] - want["per_model_probs"]["mlp"]).max() <= 5e-5
+        assert np.abs(got["probs"] - want["probs"]).max() <= tol
