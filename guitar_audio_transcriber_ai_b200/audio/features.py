@@ -1,13 +1,17 @@
-"""``MelFeatureBuilder`` - drop-in for the inference half of the reference's audio/features.py.
+"""``MelFeatureBuilder`` - drop-in for the reference's audio/features.py.
 
-Same signatures and return types as features.py:130-158 (``extract_inference_features``) and :441-508
-(``extract_inference_features_from_audio``); the arithmetic runs in csrc/features.cuh + csrc/yin.cuh.
-Training-set builders and reports (features.py:24-102, :221-272, :343-435) are out of scope.
+Same signatures and return types as features.py:130-158 (``extract_inference_features``), :441-508
+(``extract_inference_features_from_audio``) and the training-set builders: :162-219
+``extract_mfcc_features``, :275-341 ``extract_melspec_features``, :221-272 / :343-435 the train/val DataLoader
+builders.  The arithmetic runs batched in csrc/features.cuh + csrc/yin.cuh (the reference loops clip by clip);
+label encoding, the stratified split and ``StandardScaler.fit`` are the same sklearn calls on the host.
+``generate_feature_report`` (:24-102, a JSON summary) is not mirrored.
 """
 from __future__ import annotations
 
 import numpy as np
 import torch
+from torch.utils.data import DataLoader, TensorDataset
 
 from ..config import MFCCConfig, MelSpecConfig, TARGET_SR, asdict
 from ..dsp.yin import shared_engine
@@ -26,6 +30,99 @@ class MelFeatureBuilder:
         """features.py:124-126 (host helper kept for API parity; the device path fuses it into the loads)."""
         rms = np.sqrt(np.mean(y ** 2))
         return y / (rms + eps)
+
+    # ---- shared helpers (features.py:107-122)
+    def _encode_labels_to_ints(self, labels):
+        classes = sorted(set(labels))
+        label_to_idx = {c: i for i, c in enumerate(classes)}
+        idx_to_label = {i: c for i, c in enumerate(classes)}
+        return [label_to_idx[l] for l in labels], len(classes), idx_to_label
+
+    def _create_tensor_dataset(self, X, y):
+        X_tensor = X if isinstance(X, torch.Tensor) else torch.tensor(X, dtype=torch.float32)
+        return TensorDataset(X_tensor, torch.tensor(y, dtype=torch.long))
+
+    def _labels(self, labels):
+        y = np.array(labels, dtype=str)
+        y_encoded, num_classes, reverse_map = self._encode_labels_to_ints(y)
+        return np.array(y_encoded, dtype=int), num_classes, reverse_map
+
+    # ---- training-set feature extraction (features.py:162-219, :275-341), one batched pass each
+    def extract_mfcc_features(self, audio_loader, n_mfcc=13, normalize_audio_volume: bool = False,
+                              add_pitch_features: bool = True):
+        """-> (X float32 (N, n_mfcc [+1 = log10(YIN Hz)]), y_encoded int (N,), num_classes, reverse_map).
+        YIN runs on the raw clip even when the MFCCs use the normalised one (features.py:201)."""
+        wavs, _, labels, _ = audio_loader.load_audio_dataset(pad_to_max=True)
+        clips = np.stack([np.asarray(w, dtype=np.float32) for w in wavs])
+        eng = self._engine(audio_loader.target_sr, {"N_MFCC": n_mfcc}, asdict(MelSpecConfig()))
+        feats, hz = eng.mfcc_features(eng._clips(clips), normalize_audio_volume, add_pitch_features,
+                                      yin_on_normalized=False, apply_scaler=False)
+        X = feats.cpu().numpy()
+        if add_pitch_features and bool(torch.isnan(hz).any()):
+            # the reference appends the pitch feature only when YIN returns one, then np.vstack fails on ragged rows
+            raise ValueError("all the input array dimensions except for the concatenation axis must match exactly "
+                             "(YIN found no pitch for at least one clip)")
+        y_encoded, num_classes, reverse_map = self._labels(labels)
+        print(f"Extracted MFCC features for {len(X)} samples.")
+        return X, y_encoded, num_classes, reverse_map
+
+    def extract_melspec_features(self, audio_loader, n_mels: int = 128, n_fft: int = 1024, hop_length: int = 256,
+                                 normalize_audio_volume: bool = False, to_db: bool = True):
+        """-> (X torch float32 (N, 1, n_mels, T), y_encoded, num_classes, reverse_map)."""
+        if not to_db:
+            raise NotImplementedError("to_db=False is not implemented (every caller in the reference keeps the default)")
+        wavs, _, labels, _ = audio_loader.load_audio_dataset(pad_to_max=True)
+        clips = np.stack([np.asarray(w, dtype=np.float32) for w in wavs])
+        eng = self._engine(audio_loader.target_sr, asdict(MFCCConfig()), {"N_MELS": n_mels, "N_FFT": n_fft, "HOP_LENGTH": hop_length})
+        X = eng.melspec_db(eng._clips(clips), normalize_audio_volume).cpu()
+        y_encoded, num_classes, reverse_map = self._labels(labels)
+        print(f"Extracted Mel-spectrogram features for {X.shape[0]} samples. X shape: {tuple(X.shape)}")
+        return X, y_encoded, num_classes, reverse_map
+
+    def build_mfcc_train_val_dataloaders(self, audio_loader, n_mfcc=13, batch_size: int = 32, val_size: float = 0.2,
+                                         shuffle_train: bool = True, shuffle_val: bool = False, normalize_audio_volume=False,
+                                         standard_scaler: bool = True, seed: int = 42, num_workers: int = 0,
+                                         pin_memory: bool = True, drop_last: bool = False):
+        """features.py:221-272: stratified split, StandardScaler fitted on the training part."""
+        from sklearn.model_selection import train_test_split
+        from sklearn.preprocessing import StandardScaler
+        X, y_encoded, num_classes, reverse_map = self.extract_mfcc_features(audio_loader, n_mfcc, normalize_audio_volume)
+        X_tr, X_val, y_tr, y_val = train_test_split(X, y_encoded, test_size=val_size, stratify=y_encoded, random_state=seed)
+        scaler = None
+        if standard_scaler:
+            scaler = StandardScaler().fit(X_tr)
+            X_tr, X_val = scaler.transform(X_tr), scaler.transform(X_val)
+            self.scaler = scaler
+        dl_tr = DataLoader(self._create_tensor_dataset(X_tr, y_tr), batch_size=batch_size, shuffle=shuffle_train,
+                           num_workers=num_workers, pin_memory=pin_memory, drop_last=drop_last)
+        dl_val = DataLoader(self._create_tensor_dataset(X_val, y_val), batch_size=batch_size, shuffle=shuffle_val,
+                            num_workers=num_workers, pin_memory=pin_memory, drop_last=False)
+        return dl_tr, dl_val, X, y_encoded, num_classes, reverse_map, scaler
+
+    def build_melspec_dataloader(self, audio_loader, n_mels: int = 128, n_fft: int = 1024, hop_length: int = 256,
+                                 batch_size: int = 32, shuffle: bool = True, normalize_audio_volume: bool = False):
+        """features.py:343-364."""
+        X, y_encoded, num_classes, reverse_map = self.extract_melspec_features(
+            audio_loader=audio_loader, n_mels=n_mels, n_fft=n_fft, hop_length=hop_length,
+            normalize_audio_volume=normalize_audio_volume)
+        return DataLoader(self._create_tensor_dataset(X, y_encoded), batch_size=batch_size, shuffle=shuffle), num_classes, reverse_map
+
+    def build_melspec_train_val_dataloaders(self, audio_loader, n_mels: int = 128, n_fft: int = 1024, hop_length: int = 256,
+                                            batch_size: int = 32, val_size: float = 0.2, shuffle_train: bool = True,
+                                            shuffle_val: bool = False, normalize_audio_volume: bool = False, seed: int = 42,
+                                            num_workers: int = 0, pin_memory: bool = True, drop_last: bool = False):
+        """features.py:366-435: stratified split by index, no scaler."""
+        from sklearn.model_selection import train_test_split
+        X, y_encoded, num_classes, reverse_map = self.extract_melspec_features(
+            audio_loader=audio_loader, n_mels=n_mels, n_fft=n_fft, hop_length=hop_length,
+            normalize_audio_volume=normalize_audio_volume)
+        idx_tr, idx_val, y_tr, y_val = train_test_split(np.arange(len(y_encoded)), y_encoded, test_size=val_size,
+                                                        stratify=y_encoded, random_state=seed)
+        dl_tr = DataLoader(self._create_tensor_dataset(X[idx_tr], y_tr), batch_size=batch_size, shuffle=shuffle_train,
+                           num_workers=num_workers, pin_memory=pin_memory, drop_last=drop_last)
+        dl_val = DataLoader(self._create_tensor_dataset(X[idx_val], y_val), batch_size=batch_size, shuffle=shuffle_val,
+                            num_workers=num_workers, pin_memory=pin_memory, drop_last=False)
+        return dl_tr, dl_val, X, y_encoded, num_classes, reverse_map
 
     # ---- batched device entry points (additions; the reference loops clip by clip in Python)
     def extract_mfcc_features_batch(self, clips, sr, n_mfcc=64, normalize_audio_volume=True, add_pitch_features=True,

@@ -145,3 +145,30 @@ def test_emu_front_end_kernels(emu_lib):
 @pytest.mark.parametrize("name", list(file_cases.CASES))
 def test_emu_transcribe_file(emu_lib, name, tmp_path):
     file_cases.check_transcribe_file("cpu", tmp_path, name, prob_tol=5e-5)
+
+
+def test_emu_cli(emu_lib, tmp_path, capsys):
+    """transcribe_cli.py:96-114: console table and the txt dump, through the emulated kernels."""
+    from guitar_audio_transcriber_ai_b200 import transcribe_cli
+    path = file_cases.write_case(tmp_path, "mono22050")
+    g = np.load(GOLD / "files.npz")
+    res = transcribe_cli.main(["--audio", str(path), "--out", str(tmp_path / "o"), "--save_results", "--device", "cpu",
+                               "--mlp_ckpt", "mlp_synth_sr22050.ckpt", "--cnn_ckpt", "cnn_synth_sr22050.ckpt",
+                               "--mlp_root", str(CKPT), "--cnn_root", str(CKPT)])
+    out = capsys.readouterr().out
+    labels = [str(s) for s in g["mono22050_labels"]]
+    assert "Idx |  Label |  Confidence | (YIN Note Estimate)" in out
+    assert f"000  {labels[0]:>4}  (conf=" in out
+    txt = (tmp_path / "o" / "mono22050_transcription.txt").read_text(encoding="utf-8")
+    rows = txt.split("\n\nFull result dict:\n")[0].splitlines()
+    assert [r.split(",")[1] for r in rows] == labels and rows[0].startswith("0,")
+    assert "'dsp_info'" in txt
+    assert not list((tmp_path / "o").glob("*/*/*.wav"))       # clips are only kept with --save_clips
+    with pytest.raises(ValueError):
+        transcribe_cli.main(["--audio", str(tmp_path / "o" / "mono22050_transcription.txt"), "--device", "cpu"])
+
+
+def test_emu_training_feature_builders(emu_lib):
+    """features.py:162-435 through the emulated kernels, against the oracle port per clip."""
+    import train_cases
+    train_cases.check_training_builders("cpu")

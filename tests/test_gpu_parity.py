@@ -389,3 +389,10 @@ def test_transcribe_notes_resamples_like_the_reference(tr22):
         assert [str(s) for s in got["labels"]] == [str(s) for s in want["labels"]]
         assert np.abs(got["per_model_probs"]["mlp"] - want["per_model_probs"]["mlp"]).max() <= 5e-5
         assert np.abs(got["probs"] - want["probs"]).max() <= tol
+
+
+@pytest.mark.gpu
+def test_training_feature_builders(tr22):
+    """features.py:162-435: batched dataset features == the oracle's per-clip loop; loaders/splits."""
+    import train_cases
+    train_cases.check_training_builders("cuda:0", n_classes=6, per_class=4)
