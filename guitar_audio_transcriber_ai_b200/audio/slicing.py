@@ -62,6 +62,11 @@ class AudioSlicer:
             self.save_clip(clip, sr, out_dir, int(row[0]), onsets[int(row[0])] / sr)
         return onsets
 
+    def detect_onsets(self, y, sr=11025, hop_len=512, min_sep=0.25) -> list[int]:
+        """slicing.py:106-122: onset strength -> peak picking with backtracking -> minimum separation, on ``y``
+        as given (no gates).  The live prototype calls it with hop 1024 on the microphone buffer."""
+        return [int(v) for v in self.engine(sr).detect_onsets(y, hop_len, min_sep).cpu().numpy()]
+
     def detect_onsets_gated(self, y, sr=TARGET_SR, cfg=None) -> list[int]:
         """apply_db_threshold -> apply_rms_threshold -> detect_onsets as sliceNsave chains them
         (slicing.py:148-151): onset sample positions of the raw signal ``y``."""

@@ -863,6 +863,81 @@ extern "C" int gat_resample(gat_ctx* c, const float* in, int64_t N, int64_t n_in
 }
 
 // ------------------------------------------------------------------------------------------------- segmentation
+namespace {
+
+// Scalars shared by the segmentation kernels, in seg_small: spec max (8 B) | env min, max (16 B) | n_peaks |
+// any_nonzero | gate value.
+struct SegScalars { long long* spec_max; long long* env_minmax; int* n_peaks; int* any_nonzero; float* gate_val; };
+
+int seg_scalars(gat_ctx* c, cudaStream_t st, SegScalars* s) {
+    if (c->seg_small.ensure(64)) return 1;
+    unsigned char* small = c->seg_small.as<unsigned char>();
+    s->spec_max = reinterpret_cast<long long*>(small);
+    s->env_minmax = reinterpret_cast<long long*>(small + 8);
+    s->n_peaks = reinterpret_cast<int*>(small + 24);
+    s->any_nonzero = reinterpret_cast<int*>(small + 28);
+    s->gate_val = reinterpret_cast<float*>(small + 32);
+    GAT_CUDA(cudaMemsetAsync(small, 0x80, 24, st));
+    GAT_CUDA(cudaMemsetAsync(small + 24, 0, 40, st));
+    return 0;
+}
+
+// AudioSlicer.detect_onsets (slicing.py:106-122) on y[L]: float64 STFT -> Slaney mel-128 -> dB -> flux envelope ->
+// normalise, pick peaks -> backtrack -> frames * hop -> greedy minimum separation.  `gated` applies the sample
+// gate and the frame gate (seg_gate) of sliceNsave while the samples are staged.  Also fills the slice table.
+int onset_chain(gat_ctx* c, const float* y, int64_t L, const gat_slicer_params* sp, bool gated, const SegScalars& sc,
+                int32_t max_onsets, int64_t* onsets, int32_t* n_onsets, double* env_out, int64_t* frames_out,
+                int32_t* n_frames_out, cudaStream_t st) {
+    const int To = (int)(1 + L / sp->onset_hop);      // onset frames
+    if (c->spec.ensure((size_t)To * 128 * sizeof(double)) || c->seg_env.ensure((size_t)To * 8) || c->seg_envn.ensure((size_t)To * 8) ||
+        c->seg_cand.ensure((size_t)(To / 32 + 2) * 4) || c->seg_peaks.ensure((size_t)To * 4) || c->seg_frames.ensure((size_t)To * 8) ||
+        c->seg_table.ensure((size_t)max_onsets * 3 * 8)) return 1;
+    StftMelParams<double> p{};
+    p.audio = y; p.n = L; p.N = 1; p.clip_scale = nullptr;
+    p.frame_gate = gated ? c->seg_gate.as<unsigned char>() : nullptr;
+    p.sample_gate = gated ? sp->sample_gate : 0.0f; p.gate_hop = sp->rms_hop;
+    p.hop = sp->onset_hop; p.n_frames = To; p.pad_mode = kPadZero;
+    p.window = c->win64.as<double>(); p.tw = c->tw64.as<Cpx<double>>(); p.w2 = c->w2_64.as<Cpx<double>>();
+    p.fb = c->fb_mfcc.view(); p.amin = 1e-10; p.out = c->spec.as<double>(); p.spec_max = sc.spec_max;
+    if (launch_stft_mel<double, kOutSpec, 192, 32>(c, p, st)) return 1;
+
+    // flux envelope -> normalise + candidate peaks -> sequential wait rule
+    FluxParams fp{c->spec.as<double>(), sc.spec_max, To, 128, 1 + 2048 / (2 * sp->onset_hop), 80.0, c->seg_env.as<double>(), sc.env_minmax};
+    LAUNCH(c, onset_flux_kernel, (unsigned)ceil_div(To, 128), 128, 0, st, fp);
+    PeakParams pp{c->seg_env.as<double>(), sc.env_minmax, To, sp->pre_max, sp->post_max, sp->pre_avg, sp->post_avg, sp->wait,
+                  (double)sp->delta, c->seg_envn.as<double>(), c->seg_cand.as<unsigned>(), sc.n_peaks, c->seg_peaks.as<int>(), sc.any_nonzero};
+    LAUNCH(c, peak_candidates_kernel, (unsigned)ceil_div(To, 128), 128, 0, st, pp);
+    LAUNCH(c, peak_select_kernel, 1, 32, 0, st, pp);
+    if (env_out) GAT_CUDA(cudaMemcpyAsync(env_out, c->seg_envn.p, (size_t)To * 8, cudaMemcpyDeviceToDevice, st));
+
+    // backtrack, min separation, slice table
+    SliceParams s{c->seg_envn.as<double>(), To, sc.n_peaks, c->seg_peaks.as<int>(), sp->onset_hop, (long long)L,
+                  (long long)sp->min_sep_samples, (long long)sp->attack_skip, (long long)sp->clip_len, max_onsets,
+                  n_onsets, (long long*)onsets, c->seg_frames.as<long long>(), c->seg_table.as<long long>()};
+    LAUNCH(c, backtrack_kernel, (unsigned)ceil_div(To, 128), 128, 0, st, s);
+    LAUNCH(c, minsep_table_kernel, 1, 1024, 0, st, s);
+    if (frames_out && n_frames_out) {
+        const size_t nb = (size_t)(max_onsets < To ? max_onsets : To) * 8;
+        GAT_CUDA(cudaMemcpyAsync(frames_out, c->seg_frames.p, nb, cudaMemcpyDeviceToDevice, st));
+        GAT_CUDA(cudaMemcpyAsync(n_frames_out, sc.n_peaks, 4, cudaMemcpyDeviceToDevice, st));
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int gat_detect_onsets(gat_ctx* c, const float* y, int64_t L, const gat_slicer_params* sp, int32_t max_onsets,
+                                 int64_t* onsets, int32_t* n_onsets, void* stream) {
+    if (!c || !y || !sp || !onsets || !n_onsets) return fail("gat_detect_onsets: null argument");
+    if (L < 1) return fail("gat_detect_onsets: empty signal");
+    if (max_onsets < 1) return fail("gat_detect_onsets: max_onsets must be positive");
+    if (sp->onset_hop < 2 || (sp->onset_hop & 1) || sp->onset_hop > 2048) return fail("gat_detect_onsets: hop %d unsupported (even, 2..2048)", sp->onset_hop);
+    cudaStream_t st = (cudaStream_t)stream;
+    SegScalars sc{};
+    if (seg_scalars(c, st, &sc)) return 1;
+    return onset_chain(c, y, L, sp, false, sc, max_onsets, onsets, n_onsets, nullptr, nullptr, nullptr, st);
+}
+
 extern "C" int gat_segment(gat_ctx* c, const float* y, int64_t L, const gat_slicer_params* sp, int32_t max_onsets,
                            int64_t* onsets, int32_t* n_onsets, float* clips, int64_t* clip_table, int32_t* n_clips,
                            float* rms_db_out, double* env_out, int64_t* frames_out, int32_t* n_frames_out, void* stream) {
@@ -872,60 +947,21 @@ extern "C" int gat_segment(gat_ctx* c, const float* y, int64_t L, const gat_slic
     if (sp->rms_hop < 1 || sp->onset_hop != 512) return fail("gat_segment: onset hop %d unsupported (the reference always uses 512)", sp->onset_hop);
     cudaStream_t st = (cudaStream_t)stream;
     const int T = (int)(1 + L / sp->rms_hop);         // rms frames
-    const int To = (int)(1 + L / sp->onset_hop);      // onset frames
-    // small scalars: [0..1] spec max (8B) | [2..3] env min/max (16B) | n_peaks | any_nonzero | gate
-    if (c->seg_small.ensure(64) || c->seg_rms.ensure((size_t)T * 4) || c->seg_rms_med.ensure((size_t)T * 4) ||
-        c->seg_gate.ensure((size_t)T) || c->spec.ensure((size_t)To * 128 * sizeof(double)) ||
-        c->seg_env.ensure((size_t)To * 8) || c->seg_envn.ensure((size_t)To * 8) || c->seg_cand.ensure((size_t)(To / 32 + 2) * 4) ||
-        c->seg_peaks.ensure((size_t)To * 4) || c->seg_frames.ensure((size_t)To * 8) ||
-        c->seg_table.ensure((size_t)max_onsets * 3 * 8) || c->seg_keep.ensure((size_t)max_onsets) ||
-        c->seg_dest.ensure((size_t)max_onsets * 4)) return 1;
-    unsigned char* small = c->seg_small.as<unsigned char>();
-    long long* spec_max = reinterpret_cast<long long*>(small);
-    long long* env_minmax = reinterpret_cast<long long*>(small + 8);
-    int* n_peaks = reinterpret_cast<int*>(small + 24);
-    int* any_nonzero = reinterpret_cast<int*>(small + 28);
-    float* gate_val = reinterpret_cast<float*>(small + 32);
-    GAT_CUDA(cudaMemsetAsync(small, 0x80, 24, st));
-    GAT_CUDA(cudaMemsetAsync(small + 24, 0, 40, st));
+    if (c->seg_rms.ensure((size_t)T * 4) || c->seg_rms_med.ensure((size_t)T * 4) || c->seg_gate.ensure((size_t)T) ||
+        c->seg_keep.ensure((size_t)max_onsets) || c->seg_dest.ensure((size_t)max_onsets * 4)) return 1;
+    SegScalars sc{};
+    if (seg_scalars(c, st, &sc)) return 1;
 
     // 1-3: sample gate (fused into the loads) -> frame RMS dB -> median-5 -> p20 + 6 dB frame gate
     RmsParams rp{y, (long long)L, T, sp->rms_hop, sp->sample_gate, c->seg_rms.as<float>()};
     LAUNCH(c, rms_db_kernel, (unsigned)ceil_div(T, 128), 128, 0, st, rp);
     LAUNCH(c, median5_kernel, (unsigned)ceil_div(T, 256), 256, 0, st, c->seg_rms.as<float>(), c->seg_rms_med.as<float>(), T);
-    GateParams gp{c->seg_rms_med.as<float>(), T, sp->p20_k, sp->p20_gamma, sp->gate_offset_db, c->seg_gate.as<unsigned char>(), gate_val};
+    GateParams gp{c->seg_rms_med.as<float>(), T, sp->p20_k, sp->p20_gamma, sp->gate_offset_db, c->seg_gate.as<unsigned char>(), sc.gate_val};
     LAUNCH(c, rms_gate_kernel, 1, 1024, 0, st, gp);
     if (rms_db_out) GAT_CUDA(cudaMemcpyAsync(rms_db_out, c->seg_rms_med.p, (size_t)T * 4, cudaMemcpyDeviceToDevice, st));
 
-    // 4: float64 STFT -> Slaney mel-128 -> dB of the doubly gated signal
-    StftMelParams<double> p{};
-    p.audio = y; p.n = L; p.N = 1; p.clip_scale = nullptr;
-    p.frame_gate = c->seg_gate.as<unsigned char>(); p.sample_gate = sp->sample_gate; p.gate_hop = sp->rms_hop;
-    p.hop = sp->onset_hop; p.n_frames = To; p.pad_mode = kPadZero;
-    p.window = c->win64.as<double>(); p.tw = c->tw64.as<Cpx<double>>(); p.w2 = c->w2_64.as<Cpx<double>>();
-    p.fb = c->fb_mfcc.view(); p.amin = 1e-10; p.out = c->spec.as<double>(); p.spec_max = spec_max;
-    if (launch_stft_mel<double, kOutSpec, 192, 32>(c, p, st)) return 1;
-
-    // 5-7: flux envelope -> normalise + candidate peaks -> sequential wait rule
-    FluxParams fp{c->spec.as<double>(), spec_max, To, 128, 1 + 2048 / (2 * sp->onset_hop), 80.0, c->seg_env.as<double>(), env_minmax};
-    LAUNCH(c, onset_flux_kernel, (unsigned)ceil_div(To, 128), 128, 0, st, fp);
-    PeakParams pp{c->seg_env.as<double>(), env_minmax, To, sp->pre_max, sp->post_max, sp->pre_avg, sp->post_avg, sp->wait,
-                  (double)sp->delta, c->seg_envn.as<double>(), c->seg_cand.as<unsigned>(), n_peaks, c->seg_peaks.as<int>(), any_nonzero};
-    LAUNCH(c, peak_candidates_kernel, (unsigned)ceil_div(To, 128), 128, 0, st, pp);
-    LAUNCH(c, peak_select_kernel, 1, 32, 0, st, pp);
-    if (env_out) GAT_CUDA(cudaMemcpyAsync(env_out, c->seg_envn.p, (size_t)To * 8, cudaMemcpyDeviceToDevice, st));
-
-    // 8-9: backtrack, min separation, slice table
-    SliceParams s{c->seg_envn.as<double>(), To, n_peaks, c->seg_peaks.as<int>(), sp->onset_hop, (long long)L,
-                  (long long)sp->min_sep_samples, (long long)sp->attack_skip, (long long)sp->clip_len, max_onsets,
-                  n_onsets, (long long*)onsets, c->seg_frames.as<long long>(), c->seg_table.as<long long>()};
-    LAUNCH(c, backtrack_kernel, (unsigned)ceil_div(To, 128), 128, 0, st, s);
-    LAUNCH(c, minsep_table_kernel, 1, 1024, 0, st, s);
-    if (frames_out && n_frames_out) {
-        const size_t nb = (size_t)(max_onsets < To ? max_onsets : To) * 8;
-        GAT_CUDA(cudaMemcpyAsync(frames_out, c->seg_frames.p, nb, cudaMemcpyDeviceToDevice, st));
-        GAT_CUDA(cudaMemcpyAsync(n_frames_out, n_peaks, 4, cudaMemcpyDeviceToDevice, st));
-    }
+    // 4-9: onsets of the doubly gated signal
+    if (onset_chain(c, y, L, sp, true, sc, max_onsets, onsets, n_onsets, env_out, frames_out, n_frames_out, st)) return 1;
 
     // 10-11: loudness test, compaction, gather
     GatherParams g{y, (long long)L, n_onsets, c->seg_table.as<long long>(), (long long)sp->clip_len, sp->min_slice_rms_db,

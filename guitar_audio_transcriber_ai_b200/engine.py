@@ -328,6 +328,24 @@ class Engine:
             min_sep_samples=int(cfg.MIN_SEP * sr), attack_skip=int(cfg.ATTACK_SKIP_SEC * sr),
             clip_len=int(length_sec * sr), min_slice_rms_db=float(cfg.MIN_SLICE_RMS_DB))
 
+    def detect_onsets(self, y, hop_len: int = 512, min_sep: float = 0.25) -> torch.Tensor:
+        """AudioSlicer.detect_onsets(y, sr, hop_len, min_sep) (slicing.py:106-122) on an un-gated signal:
+        int64 onset sample positions on the device."""
+        yt = torch.as_tensor(y).to(device=self.device, dtype=torch.float32).contiguous().reshape(-1)
+        L = yt.numel()
+        od = tables.onset_detect_params(self.sample_rate, int(hop_len))
+        sp = _lib.GatSlicerParams(
+            min_db_threshold=0.0, sample_gate=0.0, rms_hop=512, p20_k=0, p20_gamma=0.0, gate_offset_db=0.0, onset_hop=int(hop_len),
+            pre_max=od["pre_max"], post_max=od["post_max"], pre_avg=od["pre_avg"], post_avg=od["post_avg"],
+            wait=od["wait"], delta=float(od["delta"]), min_sep_samples=int(min_sep * self.sample_rate),
+            attack_skip=0, clip_len=1, min_slice_rms_db=0.0)
+        max_onsets = max(2, 1 + L // int(hop_len))
+        onsets, n = self._empty((max_onsets,), torch.int64), self._empty((1,), torch.int32)
+        with self._on_device():
+            self.lib.check(self.lib.gat_detect_onsets(self._ctx, _lib.ptr(yt), L, C.byref(sp), max_onsets, _lib.ptr(onsets),
+                                                      _lib.ptr(n), self._stream()), ValueError)
+        return onsets[: int(n.item())]
+
     def segment(self, y, length_sec: float, cfg=None, diagnostics: bool = False) -> dict:
         """AudioSlicer.sliceNsave without file I/O (slicing.py:147-165) on one mono signal at the target rate."""
         yt = torch.as_tensor(y).to(device=self.device, dtype=torch.float32).contiguous().reshape(-1)

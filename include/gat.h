@@ -133,6 +133,14 @@ int gat_segment(gat_ctx* ctx, const float* y_dev, int64_t L, const gat_slicer_pa
                 int32_t* n_clips_dev, float* rms_db_dev, double* env_dev, int64_t* frames_dev,
                 int32_t* n_frames_dev, void* stream);
 
+/* AudioSlicer.detect_onsets(y, sr, hop_len, min_sep) on its own (slicing.py:106-122; the live prototype calls it
+ * with hop 1024 on the un-gated microphone buffer, prototyping/source/transcribe_live.py:94-96): no gates, any even
+ * hop.  Uses sp->onset_hop, the peak-pick fields and min_sep_samples; the signal is processed in float64 (a float32
+ * signal handed to librosa would be processed in float32 - same onsets unless an envelope value ties a threshold).
+ * Outputs (device): onsets_dev int64[max_onsets], n_onsets_dev int32[1]. */
+int gat_detect_onsets(gat_ctx* ctx, const float* y_dev, int64_t L, const gat_slicer_params* sp, int32_t max_onsets,
+                      int64_t* onsets_dev, int32_t* n_onsets_dev, void* stream);
+
 /* ---- file front end (Transcriber.transcribe) ---------------------------------------- */
 
 #define GAT_SAMPLE_PCM16   0

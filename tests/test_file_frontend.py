@@ -172,3 +172,9 @@ def test_emu_training_feature_builders(emu_lib):
     """features.py:162-435 through the emulated kernels, against the oracle port per clip."""
     import train_cases
     train_cases.check_training_builders("cpu")
+
+
+def test_emu_live_transcriber(emu_lib):
+    """Streaming path: feed()/step() against the prototype's loop restated on the oracle."""
+    import live_cases
+    live_cases.check_live("cpu")

@@ -396,3 +396,23 @@ def test_training_feature_builders(tr22):
     """features.py:162-435: batched dataset features == the oracle's per-clip loop; loaders/splits."""
     import train_cases
     train_cases.check_training_builders("cuda:0", n_classes=6, per_class=4)
+
+
+@pytest.mark.gpu
+def test_detect_onsets_ungated_any_hop(tr22):
+    """AudioSlicer.detect_onsets(y, sr, hop_len, min_sep) on raw signals (slicing.py:106-122), hops 256 / 512 / 1024."""
+    import port
+    from guitar_audio_transcriber_ai_b200 import synth
+    for seed in range(4):
+        y, _, _ = synth.phrase(seed, sr=22050)
+        for hop, min_sep in ((512, 0.25), (1024, 0.3), (256, 0.3)):
+            assert tr22.slicer.detect_onsets(y, 22050, hop, min_sep) == port.detect_onsets(y.astype(np.float64), 22050, hop, min_sep)
+    yl, _, _ = synth.long_audio(6, 22050, 40)
+    assert tr22.slicer.detect_onsets(yl, 22050, 1024, 0.3) == port.detect_onsets(yl.astype(np.float64), 22050, 1024, 0.3)
+
+
+@pytest.mark.gpu
+def test_live_transcriber():
+    """Streaming path on the GPU: same notes, labels and probabilities as the prototype's loop on the oracle."""
+    import live_cases
+    live_cases.check_live("cuda:0")
