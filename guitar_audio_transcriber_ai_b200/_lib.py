@@ -63,6 +63,7 @@ _PROTOTYPES = {
                               _P, _P, _P]),
     "gat_transcribe_clips": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gat_transcribe_clips_host": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int32, _P, _P, _P]),
+    "gat_transcribe_clips_host_pcm16": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int32, _P, _P, _P]),
     "gat_detect_onsets": (C.c_int, [_P, _P, C.c_int64, C.POINTER(GatSlicerParams), C.c_int32, _P, _P, _P]),
     "gat_pcm16_roundtrip": (C.c_int, [_P, _P, C.c_int64, _P]),
     "gat_decode_mono": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int32, _P, _P]),

@@ -173,7 +173,7 @@ struct gat_ctx {
     DevBuf seg_small, seg_rms, seg_rms_med, seg_gate, seg_env, seg_envn, seg_cand, seg_peaks, seg_frames, seg_table,
            seg_keep, seg_dest;
     // end-to-end staging
-    DevBuf e2e_audio[2], e2e_mel, e2e_mfcc, e2e_probs, e2e_mlp_probs, e2e_cnn_probs, e2e_index, e2e_conf;
+    DevBuf e2e_audio[2], e2e_pcm[2], e2e_mel, e2e_mfcc, e2e_probs, e2e_mlp_probs, e2e_cnn_probs, e2e_index, e2e_conf;
     cudaStream_t e2e_stream[2] = {nullptr, nullptr};
     bool e2e_streams = false;
 };
@@ -372,7 +372,7 @@ extern "C" void gat_ctx_destroy(gat_ctx* c) {
                      &c->clip_scale, &c->spec, &c->spec_max, &c->f0, &c->act1, &c->act2, &c->act3, &c->hz_tmp, &c->logits_cnn, &c->logits_mlp,
                      &c->seg_small, &c->seg_rms, &c->seg_rms_med, &c->seg_gate, &c->seg_env, &c->seg_envn, &c->seg_cand,
                      &c->seg_peaks, &c->seg_frames, &c->seg_table, &c->seg_keep, &c->seg_dest,
-                     &c->e2e_audio[0], &c->e2e_audio[1], &c->e2e_mel, &c->e2e_mfcc, &c->e2e_probs, &c->e2e_mlp_probs,
+                     &c->e2e_audio[0], &c->e2e_audio[1], &c->e2e_pcm[0], &c->e2e_pcm[1], &c->e2e_mel, &c->e2e_mfcc, &c->e2e_probs, &c->e2e_mlp_probs,
                      &c->e2e_cnn_probs, &c->e2e_index, &c->e2e_conf};
     for (DevBuf* b : all) b->release();
     if (c->e2e_streams) { cudaStreamDestroy(c->e2e_stream[0]); cudaStreamDestroy(c->e2e_stream[1]); }
@@ -1011,18 +1011,24 @@ extern "C" int gat_transcribe_clips(gat_ctx* c, const float* audio, int64_t N, i
     return run_mlp_ensemble(c, mfcc, F, N, cnn_probs, probs, mlp_probs, mlp_logits, index, conf, stream);
 }
 
-extern "C" int gat_transcribe_clips_host(gat_ctx* c, const float* audio_host, int64_t N, int64_t n, int32_t flags,
-                                         int64_t* index_host, float* conf_host, float* probs_host) {
-    if (!c || !audio_host || !index_host || !conf_host) return fail("gat_transcribe_clips_host: null argument");
-    if (N <= 0) return 0;
+namespace {
+// Host clips -> labels.  sample_bytes = 4: float32 clips; 2: PCM_16 clips (x / 32768 on the device, libsndfile's
+// scaling), which halves the bytes that cross the host link - the link is what bounds this call.
+int transcribe_host(gat_ctx* c, const void* audio_host_v, int sample_bytes, int64_t N, int64_t n, int32_t flags,
+                    int64_t* index_host, float* conf_host, float* probs_host) {
+    const unsigned char* audio_host = static_cast<const unsigned char*>(audio_host_v);
     if (!c->e2e_streams) {
         GAT_CUDA(cudaStreamCreateWithFlags(&c->e2e_stream[0], cudaStreamNonBlocking));
         GAT_CUDA(cudaStreamCreateWithFlags(&c->e2e_stream[1], cudaStreamNonBlocking));
         c->e2e_streams = true;
     }
     const int classes = c->classes;
-    const int64_t want = 4 * (int64_t)c->num_sms;   // a multiple of the conv kernels' num_sms-clip passes (592 clips = 52 MB at 1 s)
+    // 4 x num_sms clips per chunk (592 clips = 52 MB at 1 s), measured on B200 at 4096 x 1 s clips: 1x 11.6 ms, 2x 8.6, 3x 8.1,
+    // 4x 7.6, 6x 7.9 - smaller chunks pay ~0.25 ms of fixed kernel cost each and stop hiding behind the copies, larger
+    // ones lengthen the un-overlapped tail.  At 4x the step is copy-bound: 361 MB at the 53 GB/s this host link sustains.
+    const int64_t want = 4 * (int64_t)c->num_sms;
     const int64_t chunk = N < want ? N : want;
+    if (sample_bytes == 2 && (c->e2e_pcm[0].ensure((size_t)chunk * n * 2) || c->e2e_pcm[1].ensure((size_t)chunk * n * 2))) return 1;
     if (c->e2e_audio[0].ensure((size_t)chunk * n * 4) || c->e2e_audio[1].ensure((size_t)chunk * n * 4) ||
         c->e2e_probs.ensure((size_t)N * classes * 4) || c->e2e_mlp_probs.ensure((size_t)N * classes * 4) ||
         c->e2e_cnn_probs.ensure((size_t)N * classes * 4) || c->e2e_index.ensure((size_t)N * 8) || c->e2e_conf.ensure((size_t)N * 4)) return 1;
@@ -1039,9 +1045,16 @@ extern "C" int gat_transcribe_clips_host(gat_ctx* c, const float* audio_host, in
         const int b = (int)(k & 1);
         const int64_t nc = N - c0 < chunk ? N - c0 : chunk;
         if (k >= 2) GAT_CUDA(cudaStreamWaitEvent(c->e2e_stream[1], consumed[b], 0));
-        GAT_CUDA(cudaMemcpyAsync(c->e2e_audio[b].p, audio_host + c0 * n, (size_t)nc * n * 4, cudaMemcpyHostToDevice, c->e2e_stream[1]));
+        void* landing = sample_bytes == 2 ? c->e2e_pcm[b].p : c->e2e_audio[b].p;
+        GAT_CUDA(cudaMemcpyAsync(landing, audio_host + (size_t)c0 * n * sample_bytes, (size_t)nc * n * sample_bytes, cudaMemcpyHostToDevice, c->e2e_stream[1]));
         GAT_CUDA(cudaEventRecord(copied[b], c->e2e_stream[1]));
         GAT_CUDA(cudaStreamWaitEvent(c->e2e_stream[0], copied[b], 0));
+        if (sample_bytes == 2) {
+            const long long count = (long long)nc * n;
+            const long long blocks = (count + 255) / 256;
+            LAUNCH(c, pcm16_to_mono_kernel, (unsigned)(blocks < 16LL * c->num_sms ? blocks : 16LL * c->num_sms), 256, 0, c->e2e_stream[0],
+                   c->e2e_pcm[b].as<short>(), count, 1, c->e2e_audio[b].as<float>());
+        }
         rc = gat_transcribe_clips(c, c->e2e_audio[b].as<float>(), nc, n, flags, c->e2e_probs.as<float>() + c0 * classes,
                                   c->e2e_mlp_probs.as<float>() + c0 * classes, c->e2e_cnn_probs.as<float>() + c0 * classes,
                                   c->e2e_index.as<int64_t>() + c0, c->e2e_conf.as<float>() + c0, nullptr, nullptr, nullptr,
@@ -1057,4 +1070,19 @@ extern "C" int gat_transcribe_clips_host(gat_ctx* c, const float* audio_host, in
     GAT_CUDA(cudaStreamSynchronize(c->e2e_stream[0]));
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(copied[i]); cudaEventDestroy(consumed[i]); }
     return rc;
+}
+}  // namespace
+
+extern "C" int gat_transcribe_clips_host(gat_ctx* c, const float* audio_host, int64_t N, int64_t n, int32_t flags,
+                                         int64_t* index_host, float* conf_host, float* probs_host) {
+    if (!c || !audio_host || !index_host || !conf_host) return fail("gat_transcribe_clips_host: null argument");
+    if (N <= 0) return 0;
+    return transcribe_host(c, audio_host, 4, N, n, flags, index_host, conf_host, probs_host);
+}
+
+extern "C" int gat_transcribe_clips_host_pcm16(gat_ctx* c, const int16_t* audio_host, int64_t N, int64_t n, int32_t flags,
+                                               int64_t* index_host, float* conf_host, float* probs_host) {
+    if (!c || !audio_host || !index_host || !conf_host) return fail("gat_transcribe_clips_host_pcm16: null argument");
+    if (N <= 0) return 0;
+    return transcribe_host(c, audio_host, 2, N, n, flags, index_host, conf_host, probs_host);
 }

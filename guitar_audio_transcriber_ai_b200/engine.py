@@ -237,16 +237,18 @@ class Engine:
 
     def transcribe_clips_host(self, audio_host, yin_on_normalized=True, apply_scaler=False, skip_mlp=False,
                               want_probs=True) -> dict:
-        """Host buffers in, host buffers out: H2D (chunked, overlapped), kernels, D2H inside the call."""
+        """Host buffers in (float32 clips, or int16 = PCM_16 clips scaled by 1/32768 on the device), host buffers
+        out: H2D (chunked, overlapped), kernels, D2H inside the call."""
         if isinstance(audio_host, torch.Tensor):
-            if audio_host.device.type != "cpu" or audio_host.dtype != torch.float32 or not audio_host.is_contiguous():
-                raise ValueError("audio_host must be a contiguous float32 CPU tensor (pinned for overlap)")
-            N, n = audio_host.shape
-            src = _lib.ptr(audio_host)
+            if audio_host.device.type != "cpu" or audio_host.dtype not in (torch.float32, torch.int16) or not audio_host.is_contiguous():
+                raise ValueError("audio_host must be a contiguous float32 or int16 (PCM_16) CPU tensor (pinned for overlap)")
+            pcm16 = audio_host.dtype == torch.int16
         else:
-            audio_host = np.ascontiguousarray(audio_host, dtype=np.float32)
-            N, n = audio_host.shape
-            src = _lib.ptr(audio_host)
+            pcm16 = isinstance(audio_host, np.ndarray) and audio_host.dtype == np.int16
+            audio_host = np.ascontiguousarray(audio_host, dtype=np.int16 if pcm16 else np.float32)
+        N, n = audio_host.shape
+        src = _lib.ptr(audio_host)
+        entry = self.lib.gat_transcribe_clips_host_pcm16 if pcm16 else self.lib.gat_transcribe_clips_host
         K = self.num_classes
         flags = (_lib.GAT_FLAG_YIN_ON_NORMALIZED if yin_on_normalized else 0) | \
                 (_lib.GAT_FLAG_APPLY_SCALER if apply_scaler else 0) | (_lib.GAT_FLAG_SKIP_MLP if skip_mlp else 0)
@@ -257,12 +259,12 @@ class Engine:
                               "probs": torch.empty((N, K), dtype=torch.float32, pin_memory=pin)}
         ho = self._host_out
         with self._on_device():
-            self.lib.check(self.lib.gat_transcribe_clips_host(
+            self.lib.check(entry(
                 self._ctx, src, N, n, flags, _lib.ptr(ho["indices"]), _lib.ptr(ho["confidences"]),
                 _lib.ptr(ho["probs"]) if want_probs else None), ValueError)
         return {"indices": ho["indices"].numpy(), "confidences": ho["confidences"].numpy(),
                 "probs": ho["probs"].numpy() if want_probs else None,
-                "h2d_bytes": N * n * 4, "d2h_bytes": N * 12 + (N * K * 4 if want_probs else 0)}
+                "h2d_bytes": N * n * (2 if pcm16 else 4), "d2h_bytes": N * 12 + (N * K * 4 if want_probs else 0)}
 
     # ------------------------------------------------------------------ segmentation
     # ------------------------------------------------------------------ file front end

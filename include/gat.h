@@ -181,6 +181,12 @@ int gat_transcribe_clips(gat_ctx* ctx, const float* audio_dev, int64_t N, int64_
 int gat_transcribe_clips_host(gat_ctx* ctx, const float* audio_host, int64_t N, int64_t n, int32_t flags,
                               int64_t* index_host, float* conf_host, float* probs_host);
 
+/* Same with PCM_16 host clips (what .wav files and audio interfaces deliver): samples are scaled by 1/32768 on the
+ * device exactly as libsndfile / librosa.load would on the host (audio/loading.py:85), and half as many bytes cross
+ * the host link, which is the bound of the float32 variant. */
+int gat_transcribe_clips_host_pcm16(gat_ctx* ctx, const int16_t* audio_host, int64_t N, int64_t n, int32_t flags,
+                                    int64_t* index_host, float* conf_host, float* probs_host);
+
 /* Per-kernel timing with CUDA events on the launching stream (bench.py's roofline figures).
  * gat_profile_end writes one line per kernel: "<kernel> <launches> <total ms>\n". */
 int gat_profile_begin(gat_ctx* ctx);

@@ -416,3 +416,16 @@ def test_live_transcriber():
     """Streaming path on the GPU: same notes, labels and probabilities as the prototype's loop on the oracle."""
     import live_cases
     live_cases.check_live("cuda:0")
+
+
+@pytest.mark.gpu
+def test_host_entry_point_pcm16(tr22):
+    """gat_transcribe_clips_host_pcm16 == the float32 entry fed x/32768 (libsndfile's read scaling), bit for bit."""
+    from guitar_audio_transcriber_ai_b200 import synth
+    clips, _ = synth.clip_batch(700, 0.5, 22050, 900)           # more than one 592-clip chunk
+    q = np.clip(np.rint(clips * 32767.0), -32768, 32767).astype(np.int16)
+    a = tr22.engine.transcribe_clips_host(torch.from_numpy(q).pin_memory())
+    ia, pa = a["indices"].copy(), a["probs"].copy()
+    b = tr22.engine.transcribe_clips_host(torch.from_numpy(q.astype(np.float32) / np.float32(32768.0)).pin_memory())
+    assert np.array_equal(ia, b["indices"]) and np.array_equal(pa, b["probs"])
+    assert a["h2d_bytes"] * 2 == b["h2d_bytes"]
