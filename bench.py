@@ -288,6 +288,15 @@ def run_ours(args):
     roofline = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
                 "frac": top["frac"], "traffic": traffic, "peak_source": peaks["source"] + (" (sustained bf16)" if top["bound"] == "tensor" else " (copy)"),
                 "share_of_step": top["share"]}
+    if top["kernel"].startswith("stft_mel"):
+        # The STFT chain is nominally HBM-bound (the contract's roof, above) but at n_fft 2048 / hop 256 it does 148 FLOP
+        # per algorithmic byte: its real roof is FP32 issue.  Report that too, against the FP32-FMA peak MEASURED on
+        # this device (gat_debug_fma_peak; MEASURED_PEAKS.json has no FP32 figure) - SURVEY 8(d) "reporting rule".
+        fma_peak = eng.fma_peak_tflops()
+        flops = (hi - lo) * T * (2.5 * 2048 * 11 + 2.0 * 1025 * 64)        # rFFT 2.5 N log2 N + dense-equivalent mel GEMM
+        ach = flops / (top["ms_per_step"] * 1e-3) / 1e12
+        roofline["fp32"] = {"achieved": ach, "peak": fma_peak, "unit": "TFLOP/s", "frac": ach / fma_peak,
+                            "peak_source": "measured live (register-only FMA kernel)", "flops_per_frame": 2.5 * 2048 * 11 + 2.0 * 1025 * 64}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
