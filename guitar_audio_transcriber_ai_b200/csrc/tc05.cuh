@@ -85,6 +85,18 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Same with BF16 operands (kind::f16, a/b format 1 = BF16, FP32 accumulate): K = 16 per MMA, i.e. two 16-byte chunks
+// of eight channels.  Used for the two correction passes of the split product (see conv_tc.cuh).
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // Arrive on `bar` once every tcgen05 operation issued so far by this thread has completed.
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -115,6 +127,25 @@ __host__ __device__ inline float tf32_hi(float x) {
 #else
     uint32_t u; memcpy(&u, &x, 4); u &= 0xffffe000u; float r; memcpy(&r, &u, 4); return r;
 #endif
+}
+
+// BF16 (round to nearest even) of an fp32 value, as raw bits; host and device give identical results.
+__host__ __device__ inline unsigned short bf16_bits(float x) {
+#ifdef __CUDA_ARCH__
+    uint32_t u = __float_as_uint(x);
+#else
+    uint32_t u; memcpy(&u, &x, 4);
+#endif
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (unsigned short)(u >> 16);
+}
+// Eight channels -> the 16-byte BF16 chunk of the hi parts and of the remainders.
+__device__ __forceinline__ void split_bf16x8(const float (&o)[8], uint4& hb, uint4& lb) {
+    unsigned short h[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const float hi = tf32_hi(o[e]); h[e] = bf16_bits(hi); l[e] = bf16_bits(o[e] - hi); }
+    hb = make_uint4(h[0] | (uint32_t)h[1] << 16, h[2] | (uint32_t)h[3] << 16, h[4] | (uint32_t)h[5] << 16, h[6] | (uint32_t)h[7] << 16);
+    lb = make_uint4(l[0] | (uint32_t)l[1] << 16, l[2] | (uint32_t)l[3] << 16, l[4] | (uint32_t)l[5] << 16, l[6] | (uint32_t)l[7] << 16);
 }
 
 }  // namespace tc
