@@ -5,6 +5,7 @@
 #ifndef GAT_CPU_EMU
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 
 namespace gat {
 namespace tc {
@@ -141,11 +142,16 @@ __host__ __device__ inline unsigned short bf16_bits(float x) {
 }
 // Eight channels -> the 16-byte BF16 chunk of the hi parts and of the remainders.
 __device__ __forceinline__ void split_bf16x8(const float (&o)[8], uint4& hb, uint4& lb) {
-    unsigned short h[8], l[8];
+    uint32_t h[4], l[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { const float hi = tf32_hi(o[e]); h[e] = bf16_bits(hi); l[e] = bf16_bits(o[e] - hi); }
-    hb = make_uint4(h[0] | (uint32_t)h[1] << 16, h[2] | (uint32_t)h[3] << 16, h[4] | (uint32_t)h[5] << 16, h[6] | (uint32_t)h[7] << 16);
-    lb = make_uint4(l[0] | (uint32_t)l[1] << 16, l[2] | (uint32_t)l[3] << 16, l[4] | (uint32_t)l[5] << 16, l[6] | (uint32_t)l[7] << 16);
+    for (int e = 0; e < 4; ++e) {       // cvt.rn.bf16x2.f32: two conversions per instruction, same rounding as bf16_bits
+        const float h0 = tf32_hi(o[2 * e]), h1 = tf32_hi(o[2 * e + 1]);
+        const __nv_bfloat162 hp = __floats2bfloat162_rn(h0, h1), lp = __floats2bfloat162_rn(o[2 * e] - h0, o[2 * e + 1] - h1);
+        h[e] = *reinterpret_cast<const uint32_t*>(&hp);
+        l[e] = *reinterpret_cast<const uint32_t*>(&lp);
+    }
+    hb = make_uint4(h[0], h[1], h[2], h[3]);
+    lb = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 }  // namespace tc
