@@ -180,6 +180,28 @@ def kernel_table(prof: dict, steps: int, n_clips: int, T: int, peaks: dict):
     return rows
 
 
+def bind_to_gpu_numa_node(local_rank: int) -> str:
+    """One process per GPU: pin this rank to the CPUs NVML reports as local to its GPU BEFORE the pinned host buffers
+    are allocated (first-touch places them on that NUMA node), so the host->device copies of different ranks do not
+    all cross the same socket link.  Best effort: returns what happened for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() or 64) // 64 + 16)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = sorted(cpus & allowed)
+        if not use:
+            return f"gpu-local cpus not in this process's cpuset ({len(allowed)} cpus allowed)"
+        os.sched_setaffinity(0, use)
+        return f"bound to {len(use)} gpu-local cpus"
+    except Exception as e:          # NVML missing, old driver, ...
+        return f"not bound ({type(e).__name__})"
+
+
 def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -190,6 +212,7 @@ def run_ours(args):
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     from guitar_audio_transcriber_ai_b200 import parallel
@@ -320,7 +343,7 @@ def run_ours(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "clips_per_gpu": CLIPS_PER_GPU, "clip_seconds": CLIP_SECONDS, "sample_rate": SR,
-                       "parallelism": f"clip-sharded x{world}, label all-gather", "l2": "inputs (361 MB per GPU) exceed the 126 MB L2",
+                       "parallelism": f"clip-sharded x{world}, label all-gather", "host_affinity_rank0": numa, "l2": "inputs (361 MB per GPU) exceed the 126 MB L2",
                        "labels_checksum": labels_checksum},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ho["h2d_bytes"] * world, "d2h_bytes_per_step": ho["d2h_bytes"] * world,
                     "ms_per_step": 1e3 * e2e_s / args.steps},

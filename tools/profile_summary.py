@@ -1,0 +1,77 @@
+"""Builds profiles/README.md from the captured files (bench JSON, ncu launch list, ncu --set full raw page).
+
+    python tools/profile_summary.py r02
+reads  profiles/<tag>_bench.json, <tag>_launches.csv, <tag>_ncu_full_raw.csv (any may be missing)."""
+import csv, io, json, pathlib, sys
+from collections import defaultdict
+
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+P = pathlib.Path(__file__).resolve().parent.parent / "profiles"
+out = [f"# Profiles `{tag}` (B200, sm_100a)", "",
+       "All captures are of `python bench.py --steps K --warmup W --no-cpu-baseline` (BASELINE configs[1]: 4096 x 1 s clips, mel + CNN).", ""]
+
+
+def csv_rows(path):
+    text = path.read_text(errors="replace")
+    start = text.index('"ID"')
+    return list(csv.DictReader(io.StringIO(text[start:])))
+
+
+lp = P / f"{tag}_launches.csv"
+if lp.exists():
+    rows = csv_rows(lp)
+    agg = defaultdict(lambda: [0, 0.0])
+    for r in rows:
+        if r.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        v = float(r["Metric Value"].replace(",", ""))
+        unit = r.get("Metric Unit", "ns")
+        ms = v * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(unit, 1e-6)
+        name = r["Kernel Name"].split("(")[0]
+        agg[name][0] += 1; agg[name][1] += ms
+    tot = sum(v[1] for v in agg.values()) or 1.0
+    out += ["## ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`; cold-cache, serialised)", "",
+            "| kernel | launches | total ms | share |", "|---|---|---|---|"]
+    for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        out.append(f"| {k[:90]} | {n} | {ms:.3f} | {ms / tot:.3f} |")
+    out.append("")
+
+bp = P / f"{tag}_bench.json"
+if bp.exists():
+    d = json.loads(bp.read_text())
+    out += [f"## Live CUDA-event profile inside bench.py (same command, `kernels` array of profiles/{tag}_bench.json)", "",
+            "| kernel | launches/step | ms/step | share | achieved | of measured peak |", "|---|---|---|---|---|---|"]
+    for k in d["kernels"]:
+        out.append(f"| {k['kernel']} | {k['launches_per_step']:g} | {k['ms_per_step']:.3f} | {k['share']:.3f} | {k['achieved']:.1f} {k['unit']} | {k['frac']:.3f} |")
+    e = d["e2e"]
+    out += ["", f"Step {d['ms_per_step']:.2f} ms -> {d['value']:.0f} audio-s/s resident, {e['value']:.0f} audio-s/s end to end "
+            f"(host float32 buffers, {e['ms_per_step']:.2f} ms per step)" +
+            (f", {d['e2e_pcm16']['value']:.0f} with PCM_16 host buffers" if "e2e_pcm16" in d else "") + f"; clocks {d['clocks']}."]
+    if "fp32" in d.get("roofline", {}):
+        f = d["roofline"]["fp32"]
+        out.append(f"STFT kernel against the FP32-FMA roof measured on the same device: {f['achieved']:.1f} of {f['peak']:.1f} TFLOP/s = {f['frac']:.2f}.")
+    out.append("")
+
+fp = P / f"{tag}_ncu_full_raw.csv"
+if fp.exists():
+    rows = csv_rows(fp)
+    cols = [("grid", "launch__grid_size"), ("duration", "gpu__time_duration.sum"), ("dram read", "dram__bytes_read.sum"),
+            ("dram write", "dram__bytes_write.sum"), ("tensor pipe active %", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+            ("issue active %", "sm__issue_active.avg.pct_of_peak_sustained_elapsed"),
+            ("fma pipe %", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+            ("lsu pipe %", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"), ("regs", "launch__registers_per_thread"),
+            ("smem wavefronts", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"), ("warp instructions", "smsp__inst_executed.sum")]
+    units = rows[0] if rows and not rows[0].get("ID", "").isdigit() else {}
+    out += [f"## ncu --set full (one launch each; `profiles/{tag}_ncu_full_raw.csv` holds every metric)", "",
+            "| kernel | " + " | ".join(c for c, _ in cols) + " |", "|---|" + "---|" * len(cols)]
+    for r in rows:
+        if not r.get("ID", "").isdigit():
+            continue
+        vals = []
+        for _, key in cols:
+            hit = [k for k in r if k.endswith(key)]
+            vals.append((r[hit[0]] + " " + units.get(hit[0], "")).strip() if hit else "")
+        out.append(f"| {r['Kernel Name'].split('(')[0][:60]} | " + " | ".join(vals) + " |")
+    out.append("")
+(P / "README.md").write_text("\n".join(out) + "\n")
+print("\n".join(out)[:3000])
