@@ -3,15 +3,15 @@
 //
 //   D[pixel (M = 128)][c_out (N)] += A[pixel][k] * B[c_out][k],   k = (tap, c_in)
 //
-// * Activations live in HBM as "chunk planes": [clip][c_in/4][padded pixel][4 floats], split into a TF32
-//   `hi` array and an exact fp32 remainder `lo` (x = hi + lo).  With that layout and the no-swizzle K-major
-//   operand format, the rows an MMA reads for tap (ky,kx) are the SAME shared-memory planes addressed
+// * Activations live in HBM as "chunk planes": [clip][c_in/8][padded pixel][8 x 16 bit], three arrays (hf, hb, lb).
+//   With that layout and the no-swizzle K-major operand format, the rows an MMA reads for tap (ky,kx) are the SAME shared-memory planes addressed
 //   (ky*Wp + kx) * 16 bytes further: im2col costs nothing and every load is a contiguous 1-D bulk (TMA) copy.
-// * Split product: x = hi + lo with hi the TF32 truncation.  hi*hi runs as kind::tf32 MMAs; the two correction
-//   terms lo*hi + hi*lo are 2^-11 of the result, so they run as BF16 MMAs (kind::f16, K = 16 per instruction, half
-//   the instructions and half the operand bytes of a TF32 pass) on BF16 copies of hi and lo.  All three accumulate in
-//   the same FP32 TMEM tile; measured max error 1.2e-5 on |x| ~ 8 (tests/gpu_probe/tc_probe_hybrid.cu), against
-//   5e-3 for a single TF32 pass and 5e-6 for three TF32 passes.  The reference runs the CNN in fp32.
+// * Split product: x = hf + lo with hf = FP16(x).  hf*hf runs as FP16 MMAs, the two correction terms lo*hf + hf*lo -
+//   2^-12 of the result - as BF16 MMAs on BF16 copies (hb = BF16(hf), lb = BF16(lo)); all are kind::f16 with K = 16 and
+//   accumulate in the same FP32 TMEM tile.  Three 16-bit MMAs per 16 channels instead of the six TF32 MMAs of 3xTF32,
+//   6 bytes per stored activation instead of 8, measured max error 4.9e-6 on |x| ~ 7 (tests/gpu_probe/
+//   tc_probe_hybrid.cu: the same as three TF32 passes; one TF32 pass: 5e-3).  The reference runs the CNN in fp32.
+//   (A and B of one MMA must share a format - mixing F16 and BF16 is an illegal instruction - hence the hb copies.)
 // * One CTA per SM, warp-specialised: warp 0 = weight producer, warp 1 = MMA issuer (one thread), warps 2-5 =
 //   epilogue, warp 6 = activation producer.  The 32 input channels of a K block are staged as two HALVES of
 //   16 channels with their own full/empty barriers and the MMAs run half-major (half 0: 9 taps, half 1: 9 taps),
@@ -36,10 +36,10 @@ constexpr int kTcThreads = 224;
 constexpr int kTcStageStride = 33;                // floats per staged pixel (32 channels + 1 pad)
 
 struct ConvTcParams {
-    const float* in_hi;                           // [clip][CIN/4][Hp*Wp][4 fp32]   TF32 parts
-    const unsigned short* in_hb;                  // [clip][CIN/8][Hp*Wp][8 bf16]   BF16(hi)
-    const unsigned short* in_lb;                  // [clip][CIN/8][Hp*Wp][8 bf16]   BF16(x - hi)
-    const float* w;                               // [CIN/32][half][9 taps] stages of {hi: [4][COUT][4 fp32], hb: [2][COUT][8 bf16], lb: same}
+    const unsigned short* in_hf;                  // [clip][CIN/8][Hp*Wp][8 fp16]   FP16(x)
+    const unsigned short* in_hb;                  // [clip][CIN/8][Hp*Wp][8 bf16]   BF16(hf)
+    const unsigned short* in_lb;                  // [clip][CIN/8][Hp*Wp][8 bf16]   BF16(x - hf)
+    const unsigned short* w;                      // [CIN/32][half][9 taps] stages of {hf | hb | lb}, each [2 chunks][COUT][8 x 16 bit]
     const float* bias;                            // [COUT] (BatchNorm folded)
     int n_clips, H, W;                            // conv input size without the border; Hp = H+2, Wp = W+2
     int R;                                        // image rows per group (even, R*seg <= 384)
@@ -47,8 +47,8 @@ struct ConvTcParams {
     int cw;                                       // output columns per column block (even unless there is one block)
     int col_blocks;
     int groups_per_clip;                          // row blocks * col_blocks
-    int out_planes;                               // 1: write next layer's planes (hi / hb / lb); 0: dense NHWC into out_hi
-    float* out_hi; unsigned short* out_hb; unsigned short* out_lb;
+    int out_planes;                               // 1: write next layer's planes (hf / hb / lb); 0: dense fp32 NHWC into out_dense
+    float* out_dense; unsigned short* out_hf; unsigned short* out_hb; unsigned short* out_lb;
     float slope;
     long long* debug;                             // optional [grid][8] cycle counters (profiling builds), else nullptr
 };
@@ -57,8 +57,8 @@ __host__ __device__ inline int conv_tc_plane_pixels(int seg) { return kTcGroupPi
 
 template <int COUT>
 __host__ __device__ inline size_t conv_tc_smem_bytes(int seg, int nstage) {
-    return (size_t)2 * 8 * conv_tc_plane_pixels(seg) * 16          // A: 8 TF32 chunk planes + 4 + 4 BF16 chunk planes
-         + (size_t)nstage * 2 * 4 * COUT * 16                      // weight ring (one stage = one tap of one K half)
+    return (size_t)12 * conv_tc_plane_pixels(seg) * 16             // A: 4 + 4 + 4 chunk planes (hf, hb, lb) of a 32-channel K block
+         + (size_t)nstage * 6 * COUT * 16                          // weight ring (one stage = one tap of one K half)
          + (size_t)kTcGroupPix * kTcStageStride * 4                // epilogue staging
          + 256;                                                    // barriers, tmem slot, alignment
 }
@@ -67,7 +67,7 @@ template <int CIN, int COUT, int NSTAGE>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) {
     using namespace tc;
     constexpr int NKB = CIN / 32;
-    constexpr uint32_t W_STAGE = 2 * 4 * COUT * 16;        // 4 TF32 chunks + 2 + 2 BF16 chunks, each COUT x 16 B
+    constexpr uint32_t W_STAGE = 6 * COUT * 16;            // hf | hb | lb, each 2 chunks x COUT x 16 B
     constexpr int ACC = (2 * kTcTiles * COUT <= 512) ? 2 : 1;      // accumulator sets in TMEM (conv2: 2 x 192 columns)
     constexpr uint32_t TMEM_COLS = ACC * kTcTiles * COUT <= 256 ? 256 : 512;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -76,8 +76,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
     const int Pg = conv_tc_plane_pixels(seg);
     const bool contiguous = p.col_blocks == 1 && seg == Wp;
     const uint32_t plane = (uint32_t)Pg * 16;
-    unsigned char* a_buf = smem;                                   // planes 0-7: hi chunks, 8-11: hb chunks, 12-15: lb chunks
-    unsigned char* w_buf = a_buf + (size_t)2 * 8 * plane;
+    unsigned char* a_buf = smem;                                   // planes 0-3: hf chunks, 4-7: hb chunks, 8-11: lb chunks
+    unsigned char* w_buf = a_buf + (size_t)12 * plane;
     float* staging = reinterpret_cast<float*>(w_buf + (size_t)NSTAGE * W_STAGE);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(staging) + (size_t)kTcGroupPix * kTcStageStride * 4);
     uint64_t* a_full = bars + 0; uint64_t* a_empty = bars + 2; uint64_t* acc_full = bars + 4; uint64_t* acc_empty = bars + 6;
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
                         const uint32_t st = use % NSTAGE;
                         mbar_wait(w_empty + st, ((use / NSTAGE) & 1) ^ 1);
                         mbar_expect_tx(w_full + st, W_STAGE);
-                        bulk_g2s(w_buf + (size_t)st * W_STAGE, p.w + (size_t)(kh * 9 + tap) * (W_STAGE / 4), W_STAGE, w_full + st);
+                        bulk_g2s(w_buf + (size_t)st * W_STAGE, p.w + (size_t)(kh * 9 + tap) * (W_STAGE / 2), W_STAGE, w_full + st);
                     }
         }
     } else if (warp == 6) {
@@ -127,28 +127,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
                 for (int half = 0; half < 2; ++half) {
                     if (lane == 0) {
                         mbar_wait(a_empty + half, (it & 1) ^ 1);
-                        mbar_expect_tx(a_full + half, contiguous ? 8 * plane : 8 * (uint32_t)rows * row_bytes);
+                        mbar_expect_tx(a_full + half, contiguous ? 6 * plane : 6 * (uint32_t)rows * row_bytes);
                     }
                     __syncwarp();
-                    // the 8 planes of this K half: 4 TF32 chunks (4 channels each), 2 + 2 BF16 chunks (8 channels each)
+                    // the 6 planes of this K half: chunks 2*half, 2*half+1 of hf, hb and lb
                     auto plane_src = [&](int q, int& slot) -> const unsigned char* {
-                        if (q < 4) {
-                            slot = half * 4 + q;
-                            return reinterpret_cast<const unsigned char*>(p.in_hi) + ((long long)clip * (CIN / 4) + kb * 8 + slot) * plane_pix * 16;
-                        }
-                        const int c16 = half * 2 + (q & 1);
-                        slot = (q < 6 ? 8 : 12) + c16;
-                        const unsigned short* src = q < 6 ? p.in_hb : p.in_lb;
+                        const int arr = q >> 1, c16 = half * 2 + (q & 1);
+                        slot = arr * 4 + c16;
+                        const unsigned short* src = arr == 0 ? p.in_hf : (arr == 1 ? p.in_hb : p.in_lb);
                         return reinterpret_cast<const unsigned char*>(src) + ((long long)clip * (CIN / 8) + kb * 4 + c16) * plane_pix * 16;
                     };
                     if (contiguous) {
-                        if (lane < 8) {
+                        if (lane < 6) {
                             int slot;
                             const unsigned char* src = plane_src(lane, slot);
                             bulk_g2s(a_buf + (size_t)slot * plane, src + q_start * 16, plane, a_full + half);
                         }
                     } else {                               // R+2 row segments per plane, each seg pixels from column xs-1;
-                        for (int i = lane; i < 8 * rows; i += 32) {        // slot 0 of the plane stays the unused slack pixel
+                        for (int i = lane; i < 6 * rows; i += 32) {        // slot 0 of the plane stays the unused slack pixel
                             const int q = i / rows, a = i - q * rows;
                             int slot;
                             const unsigned char* src = plane_src(q, slot);
@@ -162,15 +158,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
     } else if (warp == 1) {
         // ===================================================== MMA issuer (single thread)
         if (lane == 0) {
-            const uint32_t idesc = idesc_tf32(128, COUT), idesc16 = idesc_bf16(128, COUT);
+            const uint32_t idesc_h = idesc_f16(128, COUT), idesc_b = idesc_bf16(128, COUT);
             // Descriptors differ only in their start address: keep the low words as integers and add offsets.
             // low word = (addr >> 4) | (LBO >> 4) << 16 ; high word = (SBO >> 4) | version 1 at bit 46.
             constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
             const uint32_t a_lbo = (plane >> 4) << 16, b_lbo = ((uint32_t)(COUT * 16) >> 4) << 16;
-            const uint32_t a_hi = (smem_u32(a_buf) >> 4) | a_lbo;
-            const uint32_t a_hb = a_hi + ((8 * plane) >> 4), a_lb = a_hi + ((12 * plane) >> 4);
-            const uint32_t a_step = (2 * plane) >> 4;                     // two 16-byte K chunks per MMA
-            constexpr uint32_t b_step = (2 * COUT * 16) >> 4;
+            const uint32_t a_hf = (smem_u32(a_buf) >> 4) | a_lbo;
+            const uint32_t a_hb = a_hf + ((4 * plane) >> 4), a_lb = a_hf + ((8 * plane) >> 4);
+            const uint32_t a_step = (2 * plane) >> 4;                     // two 16-byte K chunks (16 channels) per MMA
             auto desc = [](uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; };
             uint32_t it = 0, use = 0, wi = 0;
             long long t_acc = 0, t_a = 0, t_w = 0, t0 = 0, t_begin = clock64();
@@ -194,24 +189,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
                             t_w += clock64() - t0;
                             fence_after_thread_sync();
                             const uint32_t row_off = (uint32_t)((tap / 3) * seg + (tap % 3));         // in 16-byte units
-                            const uint32_t w_hi = ((smem_u32(w_buf) + st * W_STAGE) >> 4) | b_lbo;
-                            const uint32_t w_hb = w_hi + ((4 * COUT * 16) >> 4), w_lb = w_hi + ((6 * COUT * 16) >> 4);
-                            // main term: TF32, two MMAs of K = 8 cover the 16 channels of this half
-#pragma unroll
-                            for (int sl = 0; sl < 2; ++sl) {
-                                const uint64_t db = desc(w_hi + sl * b_step);
-                                const uint32_t ah = a_hi + row_off + (uint32_t)(2 * half + sl) * a_step;
-#pragma unroll
-                                for (int g = 0; g < kTcTiles; ++g)
-                                    mma_tf32(d_base + (uint32_t)(g * COUT), desc(ah + g * 128), db, idesc, sl == 0 ? accumulate : 1u);
-                            }
-                            // corrections lo*hi + hi*lo: BF16, one MMA of K = 16 each
-                            const uint32_t ab_off = row_off + (uint32_t)half * a_step;
+                            const uint32_t w_hf = ((smem_u32(w_buf) + st * W_STAGE) >> 4) | b_lbo;
+                            const uint32_t w_hb = w_hf + ((2 * COUT * 16) >> 4), w_lb = w_hf + ((4 * COUT * 16) >> 4);
+                            const uint32_t a_off = row_off + (uint32_t)half * a_step;
 #pragma unroll
                             for (int g = 0; g < kTcTiles; ++g) {
                                 const uint32_t d = d_base + (uint32_t)(g * COUT);
-                                mma_bf16(d, desc(a_lb + ab_off + g * 128), desc(w_hb), idesc16, 1u);
-                                mma_bf16(d, desc(a_hb + ab_off + g * 128), desc(w_lb), idesc16, 1u);
+                                mma_16bit(d, desc(a_hf + a_off + g * 128), desc(w_hf), idesc_h, accumulate);   // hf * hf   (FP16)
+                                mma_16bit(d, desc(a_lb + a_off + g * 128), desc(w_hb), idesc_b, 1u);           // lo * hf   (BF16)
+                                mma_16bit(d, desc(a_hb + a_off + g * 128), desc(w_lb), idesc_b, 1u);           // hf * lo   (BF16)
                             }
                             accumulate = 1;
                             mma_commit(w_empty + st);       // weights of this stage are free once those MMAs retire
@@ -281,18 +267,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
                     const int Y = rb * (p.R / 2) + r;
                     if (p.out_planes) {
                         const long long pix = (long long)(Y + 1) * Wp_out + px + 1;
-                        const long long c4 = (long long)clip * (COUT / 4) + cb * 8 + ch8 * 2;      // first of two 4-channel chunks
                         const long long c8 = (long long)clip * (COUT / 8) + cb * 4 + ch8;
-                        *reinterpret_cast<float4*>(p.out_hi + (c4 * Pout + pix) * 4) =
-                            make_float4(tf32_hi(o[0]), tf32_hi(o[1]), tf32_hi(o[2]), tf32_hi(o[3]));
-                        *reinterpret_cast<float4*>(p.out_hi + ((c4 + 1) * Pout + pix) * 4) =
-                            make_float4(tf32_hi(o[4]), tf32_hi(o[5]), tf32_hi(o[6]), tf32_hi(o[7]));
-                        uint4 hb, lb;
-                        split_bf16x8(o, hb, lb);
+                        uint4 hf, hb, lb;
+                        split16x8(o, hf, hb, lb);
+                        *reinterpret_cast<uint4*>(p.out_hf + (c8 * Pout + pix) * 8) = hf;
                         *reinterpret_cast<uint4*>(p.out_hb + (c8 * Pout + pix) * 8) = hb;
                         *reinterpret_cast<uint4*>(p.out_lb + (c8 * Pout + pix) * 8) = lb;
                     } else {
-                        float* dst = p.out_hi + (((long long)clip * Hpool + Y) * Wpool + px) * COUT + cb * 32 + ch8 * 8;
+                        float* dst = p.out_dense + (((long long)clip * Hpool + Y) * Wpool + px) * COUT + cb * 32 + ch8 * 8;
                         *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
                         *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
                     }
@@ -315,9 +297,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
 struct Conv1PlanesParams {
     const float* in; int N, H, W;
     const float* w; const float* bias;    // [9][32], [32]
-    float* out_hi;                        // [clip][8][(H/2+2)*(W/2+2)][4 fp32]  TF32 parts
-    unsigned short* out_hb;               // [clip][4][(H/2+2)*(W/2+2)][8 bf16]  BF16(hi)
-    unsigned short* out_lb;               // [clip][4][...][8 bf16]              BF16(x - hi)
+    unsigned short* out_hf;               // [clip][4][(H/2+2)*(W/2+2)][8 fp16]  FP16(x)
+    unsigned short* out_hb;               // [clip][4][...][8 bf16]              BF16(hf)
+    unsigned short* out_lb;               // [clip][4][...][8 bf16]              BF16(x - hf)
     float slope;
 };
 
@@ -365,13 +347,10 @@ __global__ void __launch_bounds__(256) conv1_pool_planes_kernel(Conv1PlanesParam
             const float z = best + bs[c];
             o[e] = z > 0.0f ? z : z * p.slope;
         }
-        const long long c4 = (long long)clip * 8 + ch8 * 2, c8 = (long long)clip * 4 + ch8;
-        *reinterpret_cast<float4*>(p.out_hi + (c4 * Pout + pix) * 4) =
-            make_float4(tc::tf32_hi(o[0]), tc::tf32_hi(o[1]), tc::tf32_hi(o[2]), tc::tf32_hi(o[3]));
-        *reinterpret_cast<float4*>(p.out_hi + ((c4 + 1) * Pout + pix) * 4) =
-            make_float4(tc::tf32_hi(o[4]), tc::tf32_hi(o[5]), tc::tf32_hi(o[6]), tc::tf32_hi(o[7]));
-        uint4 hb, lb;
-        tc::split_bf16x8(o, hb, lb);
+        const long long c8 = (long long)clip * 4 + ch8;
+        uint4 hf, hb, lb;
+        tc::split16x8(o, hf, hb, lb);
+        *reinterpret_cast<uint4*>(p.out_hf + (c8 * Pout + pix) * 8) = hf;
         *reinterpret_cast<uint4*>(p.out_hb + (c8 * Pout + pix) * 8) = hb;
         *reinterpret_cast<uint4*>(p.out_lb + (c8 * Pout + pix) * 8) = lb;
     }

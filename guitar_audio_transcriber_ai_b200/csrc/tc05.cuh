@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace gat {
 namespace tc {
@@ -91,7 +92,12 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// FP16 x FP16 (format 0).  The two operands of one MMA must share a format: mixing F16 and BF16 is an illegal
+// instruction on sm_100a (tests/gpu_probe/tc_probe_hybrid.cu).
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_16bit(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
@@ -140,16 +146,29 @@ __host__ __device__ inline unsigned short bf16_bits(float x) {
     u += 0x7fffu + ((u >> 16) & 1u);
     return (unsigned short)(u >> 16);
 }
-// Eight channels -> the 16-byte BF16 chunk of the hi parts and of the remainders.
-__device__ __forceinline__ void split_bf16x8(const float (&o)[8], uint4& hb, uint4& lb) {
-    uint32_t h[4], l[4];
+// Split of an fp32 value for the conv tensor path: hf = FP16(x) (round to nearest; clamped so it never overflows),
+// hb = BF16(hf), lb = BF16(x - hf).  x*w ~= hf*wf + lb*wb_hi + hb*wl: one FP16 MMA + two BF16 MMAs.
+constexpr float kF16Max = 65504.0f;
+__host__ inline void split16_host(float x, unsigned short& hf, unsigned short& hb, unsigned short& lb) {
+    const float c = x > kF16Max ? kF16Max : (x < -kF16Max ? -kF16Max : x);
+    const __half h = __float2half_rn(c);
+    const float hv = __half2float(h);
+    hf = __half_as_ushort(h); hb = bf16_bits(hv); lb = bf16_bits(x - hv);
+}
+// Eight channels -> the three 16-byte chunks.
+__device__ __forceinline__ void split16x8(const float (&o)[8], uint4& hf, uint4& hb, uint4& lb) {
+    uint32_t f[4], h[4], l[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {       // cvt.rn.bf16x2.f32: two conversions per instruction, same rounding as bf16_bits
-        const float h0 = tf32_hi(o[2 * e]), h1 = tf32_hi(o[2 * e + 1]);
-        const __nv_bfloat162 hp = __floats2bfloat162_rn(h0, h1), lp = __floats2bfloat162_rn(o[2 * e] - h0, o[2 * e + 1] - h1);
+    for (int e = 0; e < 4; ++e) {       // packed conversions: two values per instruction
+        const float x0 = fminf(fmaxf(o[2 * e], -kF16Max), kF16Max), x1 = fminf(fmaxf(o[2 * e + 1], -kF16Max), kF16Max);
+        const __half2 fp = __floats2half2_rn(x0, x1);
+        const float2 fv = __half22float2(fp);
+        const __nv_bfloat162 hp = __floats2bfloat162_rn(fv.x, fv.y), lp = __floats2bfloat162_rn(o[2 * e] - fv.x, o[2 * e + 1] - fv.y);
+        f[e] = *reinterpret_cast<const uint32_t*>(&fp);
         h[e] = *reinterpret_cast<const uint32_t*>(&hp);
         l[e] = *reinterpret_cast<const uint32_t*>(&lp);
     }
+    hf = make_uint4(f[0], f[1], f[2], f[3]);
     hb = make_uint4(h[0], h[1], h[2], h[3]);
     lb = make_uint4(l[0], l[1], l[2], l[3]);
 }
