@@ -169,18 +169,31 @@ __global__ void __launch_bounds__(kThreads, 1) stft_mel_kernel(StftMelParams<T> 
         if (kAsync) { cp_async_wait_all(); __syncthreads(); }     // this chunk's raw samples have landed
 
         // ---- stage the chunk: centre padding, volume normalisation, (onset chain) the two gates
-        for (int i = threadIdx.x; i < need; i += blockDim.x) {
-            long long s = s0 + i;                                  // index into the un-padded clip
-            bool inside = s >= 0 && s < p.n;
-            if (!inside && p.pad_mode == kPadReflect) { s = reflect_index(s, p.n); inside = true; }
-            float v = 0.0f;
-            if (inside) v = (kAsync && s >= lo && s < hi) ? raw[s - lo] : src[s];
-            if (p.clip_scale) v = __fdiv_rn(v, c);
-            if (p.sample_gate > 0.0f && inside) {
-                if (!(fabsf(v) >= p.sample_gate)) v = 0.0f;
-                if (p.frame_gate && !p.frame_gate[s / p.gate_hop]) v = 0.0f;
+        constexpr bool kGates = sizeof(T) == 8;          // only the float64 onset chain gates its samples
+        if (!kGates && s0 >= 0 && s0 + need <= p.n) {
+            // no padding inside this chunk (all but the first and last chunks of a clip): plain indices, no branches
+            const float* in = kAsync ? raw : src + s0;     // raw[0] is sample lo = s0 here
+            if (p.clip_scale) {
+#pragma unroll 4
+                for (int i = threadIdx.x; i < need; i += blockDim.x) span[i] = (T)__fdiv_rn(in[i], c);
+            } else {
+#pragma unroll 4
+                for (int i = threadIdx.x; i < need; i += blockDim.x) span[i] = (T)in[i];
             }
-            span[i] = (T)v;
+        } else {
+            for (int i = threadIdx.x; i < need; i += blockDim.x) {
+                long long s = s0 + i;                              // index into the un-padded clip
+                bool inside = s >= 0 && s < p.n;
+                if (!inside && p.pad_mode == kPadReflect) { s = reflect_index(s, p.n); inside = true; }
+                float v = 0.0f;
+                if (inside) v = (kAsync && s >= lo && s < hi) ? raw[s - lo] : src[s];
+                if (p.clip_scale) v = __fdiv_rn(v, c);
+                if (kGates && p.sample_gate > 0.0f && inside) {
+                    if (!(fabsf(v) >= p.sample_gate)) v = 0.0f;
+                    if (p.frame_gate && !p.frame_gate[s / p.gate_hop]) v = 0.0f;
+                }
+                span[i] = (T)v;
+            }
         }
         __syncthreads();
         if (kAsync && work + gridDim.x < n_work) issue_prefetch(work + gridDim.x);   // overlaps the FFT phase below
@@ -239,9 +252,11 @@ __global__ void __launch_bounds__(kThreads, 1) stft_mel_kernel(StftMelParams<T> 
         }
         __syncthreads();
         if (kOut == kOutImage) {
-            for (int idx = threadIdx.x; idx < n_mels * nf; idx += blockDim.x) {
-                const int m = idx / nf, f = idx - m * nf;
-                p.out[((long long)clip * n_mels + m) * p.n_frames + t0 + f] = tile[m * (FC + 1) + f];
+            // rows of the tile to HBM: a warp (or half a warp when the chunk has <= 16 frames) per mel row
+            const int lanes = nf <= 16 ? 16 : 32, rows_per_warp = 32 / lanes;
+            for (int m = warp * rows_per_warp + lane / lanes; m < n_mels; m += nwarps * rows_per_warp) {
+                T* dst = p.out + ((long long)clip * n_mels + m) * p.n_frames + t0;
+                for (int f = lane & (lanes - 1); f < nf; f += lanes) dst[f] = tile[m * (FC + 1) + f];
             }
             __syncthreads();
         }
