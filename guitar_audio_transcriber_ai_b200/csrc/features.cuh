@@ -184,7 +184,12 @@ __global__ void __launch_bounds__(kThreads, 1) stft_mel_kernel(StftMelParams<T> 
             for (int i = threadIdx.x; i < need; i += blockDim.x) {
                 long long s = s0 + i;                              // index into the un-padded clip
                 bool inside = s >= 0 && s < p.n;
-                if (!inside && p.pad_mode == kPadReflect) { s = reflect_index(s, p.n); inside = true; }
+                if (!inside && p.pad_mode == kPadReflect) {
+                    // one mirror is enough when the clip is longer than the padding (the launchers require it)
+                    const long long r = s < 0 ? -s : 2 * (p.n - 1) - s;
+                    s = (r >= 0 && r < p.n) ? r : reflect_index(s, p.n);
+                    inside = true;
+                }
                 float v = 0.0f;
                 if (inside) v = (kAsync && s >= lo && s < hi) ? raw[s - lo] : src[s];
                 if (p.clip_scale) v = __fdiv_rn(v, c);
