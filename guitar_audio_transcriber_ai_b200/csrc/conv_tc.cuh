@@ -304,7 +304,7 @@ struct Conv1PlanesParams {
 };
 
 __global__ void __launch_bounds__(256) conv1_pool_planes_kernel(Conv1PlanesParams p) {
-    __shared__ float ws[9 * 32];
+    __shared__ __align__(16) float ws[9 * 32];
     __shared__ float bs[32];
     for (int i = threadIdx.x; i < 9 * 32; i += blockDim.x) ws[i] = p.w[i];
     for (int i = threadIdx.x; i < 32; i += blockDim.x) bs[i] = p.bias[i];
@@ -328,23 +328,33 @@ __global__ void __launch_bounds__(256) conv1_pool_planes_kernel(Conv1PlanesParam
     const long long pix = (long long)(py + 1) * (Wq + 2) + px + 1;
 #pragma unroll
     for (int ch8 = 0; ch8 < 4; ++ch8) {
+        // eight channels x four pre-pool positions; the weights of a tap come as two 128-bit broadcast loads
+        float acc[8][4];
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) acc[e][q4] = 0.0f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float4 w0 = *reinterpret_cast<const float4*>(ws + (ky * 3 + kx) * 32 + ch8 * 8);
+                const float4 w1 = *reinterpret_cast<const float4*>(ws + (ky * 3 + kx) * 32 + ch8 * 8 + 4);
+                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        const float pv = patch[a + ky][b + kx];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[e][a * 2 + b] = fmaf(pv, wv[e], acc[e][a * 2 + b]);
+                    }
+            }
         float o[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const int c = ch8 * 8 + e;
-            float best = -3.0e38f;
-#pragma unroll
-            for (int a = 0; a < 2; ++a)
-#pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    float acc = 0.0f;
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) acc = fmaf(patch[a + ky][b + kx], ws[(ky * 3 + kx) * 32 + c], acc);
-                    best = fmaxf(best, acc);
-                }
-            const float z = best + bs[c];
+            const float best = fmaxf(fmaxf(acc[e][0], acc[e][1]), fmaxf(acc[e][2], acc[e][3]));
+            const float z = best + bs[ch8 * 8 + e];
             o[e] = z > 0.0f ? z : z * p.slope;
         }
         const long long c8 = (long long)clip * 4 + ch8;
