@@ -35,31 +35,40 @@ class NotePredictor:
         if self.cnn is not None:
             engine.load_cnn(self.cnn.state_dict())
 
+    @staticmethod
+    def _module_from(ckpt: dict, cls, tag: str):
+        """Rebuild a trainer module from a checkpoint dict: ``model_init_args`` -> constructor, ``model`` -> weights."""
+        module = cls(**ckpt["model_init_args"])
+        if "model" not in ckpt:
+            raise KeyError(f"[load_models] {tag} checkpoint missing 'model' field")
+        module.load_state_dict(ckpt["model"])
+        return module.eval()
+
     def load_models(self, mlp_ckpt_data: dict = None, cnn_ckpt_data: dict = None):
-        """note_predictor.py:29-80."""
+        """note_predictor.py:29-80: either checkpoint may be omitted; the label map comes from the MLP checkpoint."""
         if mlp_ckpt_data is not None:
-            self.mlp = MLP(**mlp_ckpt_data["model_init_args"])
-            if "model" not in mlp_ckpt_data:
-                raise KeyError("[load_models] MLP checkpoint missing 'model' field")
-            self.mlp.load_state_dict(mlp_ckpt_data["model"])
-            self.mlp.eval()
-            if self.reverse_map is None and mlp_ckpt_data.get("reverse_map") is not None:
-                self.reverse_map = mlp_ckpt_data["reverse_map"]
+            self.mlp = self._module_from(mlp_ckpt_data, MLP, "MLP")
+            labels = mlp_ckpt_data.get("reverse_map")
+            if self.reverse_map is None and labels is not None:
+                self.reverse_map = labels
         if cnn_ckpt_data is not None:
-            self.cnn = CNN(**cnn_ckpt_data["model_init_args"])
-            if "model" not in cnn_ckpt_data:
-                raise KeyError("[load_models] CNN checkpoint missing 'model' field")
-            self.cnn.load_state_dict(cnn_ckpt_data["model"])
-            self.cnn.eval()
+            self.cnn = self._module_from(cnn_ckpt_data, CNN, "CNN")
         if self.engine is None:
-            cfgs = [d.get("config") if d else None for d in (mlp_ckpt_data, cnn_ckpt_data)]
-            sr = next((c["target_sr"] for c in cfgs if c), 22050)
-            mel = cfgs[1]["features"]["params"] if cfgs[1] else None
-            mf = cfgs[0]["features"]["params"] if cfgs[0] else None
-            mel = {k: mel[k] for k in ("N_MELS", "N_FFT", "HOP_LENGTH")} if mel else None
-            mf = {"N_MFCC": mf["N_MFCC"]} if mf else None
-            self.engine = shared_engine(sr, self.device, mel, mf)
+            self.engine = self._engine_for(mlp_ckpt_data, cnn_ckpt_data)
         self.bind_engine(self.engine)
+
+    def _engine_for(self, mlp_ckpt_data, cnn_ckpt_data):
+        """A context at the checkpoints' sample rate and feature sizes when no Transcriber supplied one."""
+        mlp_cfg = (mlp_ckpt_data or {}).get("config")
+        cnn_cfg = (cnn_ckpt_data or {}).get("config")
+        sr = (mlp_cfg or cnn_cfg or {"target_sr": 22050})["target_sr"]
+        mel = mf = None
+        if cnn_cfg:
+            params = cnn_cfg["features"]["params"]
+            mel = {k: params[k] for k in ("N_MELS", "N_FFT", "HOP_LENGTH")}
+        if mlp_cfg:
+            mf = {"N_MFCC": mlp_cfg["features"]["params"]["N_MFCC"]}
+        return shared_engine(sr, self.device, mel, mf)
 
     def predict(self, mfcc_features=None, melspec_features=None):
         """note_predictor.py:84-135.  Like the reference, BOTH feature sets are needed (it reads an unassigned
@@ -93,16 +102,18 @@ class NotePredictor:
         }
 
     def predict_debug(self, test_weights, mfcc_features=None, melspec_features=None):
-        """note_predictor.py:138-157: sweep the CNN weight, restore it afterwards."""
-        predictions = []
-        cnn_weight, mlp_weight = self.cnn_weight, self.mlp_weight
-        for weight in test_weights:
-            self.cnn_weight = weight
-            self.mlp_weight = 1 - weight
-            prediction = self.predict(mfcc_features=mfcc_features, melspec_features=melspec_features)
-            predictions.append((weight, prediction))
-            print("weight: ", weight)
-            print(prediction["labels"], prediction["confidences"])
-            print()
-        self.cnn_weight, self.mlp_weight = cnn_weight, mlp_weight
-        return predictions
+        """note_predictor.py:138-157: one prediction per candidate CNN weight (MLP weight = 1 - w), printed as the
+        reference prints them; the configured weights are restored afterwards."""
+        saved = (self.cnn_weight, self.mlp_weight)
+        sweep = []
+        try:
+            for w in test_weights:
+                self.cnn_weight, self.mlp_weight = w, 1 - w
+                res = self.predict(mfcc_features=mfcc_features, melspec_features=melspec_features)
+                sweep.append((w, res))
+                print("weight: ", w)
+                print(res["labels"], res["confidences"])
+                print()
+        finally:
+            self.cnn_weight, self.mlp_weight = saved
+        return sweep

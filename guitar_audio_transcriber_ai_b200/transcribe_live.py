@@ -86,60 +86,60 @@ class LiveTranscriber:
 
     @staticmethod
     def slice_from(y: np.ndarray, i, j) -> np.ndarray:
-        if len(y) < i or len(y) < j:
-            return np.zeros((0,), dtype=np.float32)
-        return np.array(y[i:j], dtype=np.float32)
+        """transcribe_live.py:98-102: ``y[i:j]`` as float32, empty when an index lies past the end."""
+        n = len(y)
+        return np.zeros((0,), dtype=np.float32) if (n < i or n < j) else np.array(y[i:j], dtype=np.float32)
 
     @staticmethod
     def pad_or_trim_audio(y: np.ndarray, target_dur: float, sr: int) -> np.ndarray:
-        target_len = int(target_dur * sr)
-        out_y = np.zeros(target_len, y.dtype)
-        if len(y) > target_len:
-            out_y = y[:target_len]
-        elif len(y) < target_len:
-            out_y = np.pad(y, (0, target_len - len(y)))
-        return out_y
+        """transcribe_live.py:104-113: exactly ``int(target_dur * sr)`` samples, right zero padding."""
+        want = int(target_dur * sr)
+        if len(y) >= want:
+            return y[:want]
+        out = np.zeros(want, y.dtype)
+        out[:len(y)] = y
+        return out
 
     # ---- the two halves of live() (transcribe_live.py:113-222)
     def feed(self, indata: np.ndarray):
         """Body of the audio callback (:117-123): first channel of a [frames, channels] block (or a 1-D block)."""
-        a = np.asarray(indata)
-        self.buffer.push((a[:, 0] if a.ndim == 2 else a).astype(np.float32))
+        block = np.asarray(indata)
+        self.buffer.push((block[:, 0] if block.ndim == 2 else block).astype(np.float32))
+
+    def _queue_note(self, piece: np.ndarray) -> bool:
+        """A slice becomes a note when it is longer than 0.3 s (:158-159); queue.Full propagates as in the prototype."""
+        if len(piece) <= 0.3 * self.sample_rate:
+            return False
+        self.note_q.put_nowait(self.pad_or_trim_audio(piece, CLIP_DURATION, self.sample_rate))
+        return True
 
     def step(self) -> list[dict]:
-        """One pass of the main loop (:166-214) without the sleep: returns the results of the notes it transcribed
-        (at most one per pass, as in the prototype; a full queue raises queue.Full there too)."""
-        min_slice_len = 0.3 * self.sample_rate
+        """One pass of the main loop (:166-214) without the sleep: when the ring buffer is full, cut notes between
+        consecutive onsets, drop the consumed audio, then transcribe at most one queued note."""
         if self.buffer.is_full():
-            buf = self.buffer.get_buffer()
-            onsets = [int(o) for o in self.detect_onsets(buf)]
-            h_idx = 0
-            if len(onsets) == 1:
-                s = self.slice_from(buf, onsets[0], -1)
-                if len(s) > min_slice_len:
-                    self.note_q.put_nowait(self.pad_or_trim_audio(s, CLIP_DURATION, self.sample_rate))
-                    h_idx = onsets[0]
-                    del onsets[:]
-            while len(onsets) >= 2:
-                s = self.slice_from(buf, onsets[0], onsets[1])
-                if len(s) > min_slice_len:
-                    self.note_q.put_nowait(self.pad_or_trim_audio(s, CLIP_DURATION, self.sample_rate))
-                    h_idx = onsets[1]
-                    del onsets[:2]
+            snapshot = self.buffer.get_buffer()
+            marks = [int(o) for o in self.detect_onsets(snapshot)]
+            consumed = 0
+            if len(marks) == 1:                        # a single onset: everything after it but the last sample (:176)
+                if self._queue_note(self.slice_from(snapshot, marks[0], -1)):
+                    consumed, marks = marks[0], []
+            k = 0
+            while len(marks) - k >= 2:                 # pairs of onsets; a short slice only advances by one onset (:183-192)
+                if self._queue_note(self.slice_from(snapshot, marks[k], marks[k + 1])):
+                    consumed = marks[k + 1]
+                    k += 2
                 else:
-                    h_idx = onsets[0]
-                    del onsets[:1]
-            self.buffer.clear_from(h_idx + 1, self.drop_newest)
-        out = []
-        try:
+                    consumed = marks[k]
+                    k += 1
+            self.buffer.clear_from(consumed + 1, self.drop_newest)
+        results = []
+        if not self.note_q.empty():
             note = self.note_q.get_nowait()
             if note is not None and len(note) > 0:
-                r = self.inference(np.array(note, dtype=np.float32, copy=False), self.sample_rate)
-                if r is not None:
-                    out.append(r)
-        except queue.Empty:
-            pass
-        return out
+                res = self.inference(np.array(note, dtype=np.float32, copy=False), self.sample_rate)
+                if res is not None:
+                    results.append(res)
+        return results
 
     def inference(self, audio: np.ndarray, sr_in=TARGET_SR):
         """transcribe_live.py:226-267: one note -> transcribe_note -> printed (label, confidence)."""
