@@ -34,6 +34,7 @@ constexpr int kTcTiles = 3;                       // 128-pixel tiles per group
 constexpr int kTcGroupPix = 128 * kTcTiles;
 constexpr int kTcThreads = 224;
 constexpr int kTcStageStride = 33;                // floats per staged pixel (32 channels + 1 pad)
+constexpr int kTcPooledPix = kTcGroupPix / 4;     // pooled pixels of one group (epilogue mode 2 keeps them in shared memory)
 
 struct ConvTcParams {
     const unsigned short* in_hf;                  // [clip][CIN/8][Hp*Wp][8 fp16]   FP16(x)
@@ -47,8 +48,11 @@ struct ConvTcParams {
     int cw;                                       // output columns per column block (even unless there is one block)
     int col_blocks;
     int groups_per_clip;                          // row blocks * col_blocks
-    int out_planes;                               // 1: write next layer's planes (hf / hb / lb); 0: dense fp32 NHWC into out_dense
+    int out_planes;                               // 1: next layer's planes (hf / hb / lb); 0: dense fp32 NHWC into out_dense;
+                                                  // 2: AdaptiveAvgPool2d((4,4)) of the pooled map -> FC1 operand planes (one group per clip)
     float* out_dense; unsigned short* out_hf; unsigned short* out_hb; unsigned short* out_lb;
+    float* feat_hi; float* feat_lo;               // mode 2: [COUT*4 chunks][feat_rows][4] TF32 hi / fp32 remainder (fc_tc.cuh)
+    long long feat_rows; long long clip0;         // mode 2: padded row count of those planes, index of this launch's first clip
     float slope;
     long long* debug;                             // optional [grid][8] cycle counters (profiling builds), else nullptr
 };
@@ -60,6 +64,7 @@ __host__ __device__ inline size_t conv_tc_smem_bytes(int seg, int nstage) {
     return (size_t)12 * conv_tc_plane_pixels(seg) * 16             // A: 4 + 4 + 4 chunk planes (hf, hb, lb) of a 32-channel K block
          + (size_t)nstage * 6 * COUT * 16                          // weight ring (one stage = one tap of one K half)
          + (size_t)kTcGroupPix * kTcStageStride * 4                // epilogue staging
+         + (COUT == 128 ? (size_t)kTcPooledPix * kTcStageStride * 4 : 0)   // pooled map of the last conv layer (mode 2)
          + 256;                                                    // barriers, tmem slot, alignment
 }
 
@@ -79,7 +84,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
     unsigned char* a_buf = smem;                                   // planes 0-3: hf chunks, 4-7: hb chunks, 8-11: lb chunks
     unsigned char* w_buf = a_buf + (size_t)12 * plane;
     float* staging = reinterpret_cast<float*>(w_buf + (size_t)NSTAGE * W_STAGE);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(staging) + (size_t)kTcGroupPix * kTcStageStride * 4);
+    float* pooled = staging + (size_t)kTcGroupPix * kTcStageStride;   // only present (and used) when COUT == 128
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(staging) + (size_t)kTcGroupPix * kTcStageStride * 4
+                                                 + (COUT == 128 ? (size_t)kTcPooledPix * kTcStageStride * 4 : 0));
     uint64_t* a_full = bars + 0; uint64_t* a_empty = bars + 2; uint64_t* acc_full = bars + 4; uint64_t* acc_empty = bars + 6;
     uint64_t* w_full = bars + 8; uint64_t* w_empty = bars + 8 + NSTAGE;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * NSTAGE);
@@ -265,7 +272,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
                         o[e] = z > 0.0f ? z : z * p.slope;
                     }
                     const int Y = rb * (p.R / 2) + r;
-                    if (p.out_planes) {
+                    if (p.out_planes == 1) {
                         const long long pix = (long long)(Y + 1) * Wp_out + px + 1;
                         const long long c8 = (long long)clip * (COUT / 8) + cb * 4 + ch8;
                         uint4 hf, hb, lb;
@@ -273,11 +280,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
                         *reinterpret_cast<uint4*>(p.out_hf + (c8 * Pout + pix) * 8) = hf;
                         *reinterpret_cast<uint4*>(p.out_hb + (c8 * Pout + pix) * 8) = hb;
                         *reinterpret_cast<uint4*>(p.out_lb + (c8 * Pout + pix) * 8) = lb;
+                    } else if (p.out_planes == 2) {
+                        float* dst = pooled + (size_t)(Y * Wpool + px) * kTcStageStride + ch8 * 8;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) dst[e] = o[e];
                     } else {
                         float* dst = p.out_dense + (((long long)clip * Hpool + Y) * Wpool + px) * COUT + cb * 32 + ch8 * 8;
                         *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
                         *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
                     }
+                }
+                if (p.out_planes == 2) {
+                    // AdaptiveAvgPool2d((4,4)) (cnn_trainer.py:105) of the 32 channels just pooled: thread = (window row i, channel);
+                    // same window bounds and summation order as avgpool_planes_kernel, output straight into FC1's operand planes
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    const int i = et >> 5, ch = et & 31;
+                    const int y0 = (i * Hpool) / 4, y1 = ((i + 1) * Hpool + 3) / 4;
+                    float a4[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int x0 = (j * Wpool) / 4, x1 = ((j + 1) * Wpool + 3) / 4;
+                        float sum = 0.0f;
+                        for (int y = y0; y < y1; ++y)
+                            for (int x = x0; x < x1; ++x) sum += pooled[(size_t)(y * Wpool + x) * kTcStageStride + ch];
+                        a4[j] = sum / (float)((y1 - y0) * (x1 - x0));
+                    }
+                    const long long off = (((long long)((cb * 32 + ch) * 4 + i)) * p.feat_rows + p.clip0 + clip) * 4;
+                    const float4 hi = make_float4(tf32_hi(a4[0]), tf32_hi(a4[1]), tf32_hi(a4[2]), tf32_hi(a4[3]));
+                    *reinterpret_cast<float4*>(p.feat_hi + off) = hi;
+                    *reinterpret_cast<float4*>(p.feat_lo + off) = make_float4(a4[0] - hi.x, a4[1] - hi.y, a4[2] - hi.z, a4[3] - hi.w);
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }

@@ -729,6 +729,13 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
     auto arr = [](DevBuf& b, size_t a, int k) { return reinterpret_cast<unsigned short*>(b.as<unsigned char>() + kActGuard + (size_t)k * a); };
     unsigned short *act1_hf = arr(c->act1, a1, 0), *act1_hb = arr(c->act1, a1, 1), *act1_lb = arr(c->act1, a1, 2);
     unsigned short *act2_hf = arr(c->act2, a2, 0), *act2_hb = arr(c->act2, a2, 1), *act2_lb = arr(c->act2, a2, 2);
+    // FC1 operand planes (written by conv3's epilogue when a clip is one group, else by avgpool_planes_kernel)
+    const long long rows_pad = (N + 127) / 128 * 128;
+    const size_t feat_bytes = (size_t)512 * rows_pad * 16;
+    if (c->feat_planes.ensure(2 * feat_bytes) || c->hid.ensure((size_t)N * 256 * 4)) return 1;
+    float* feat_hi = c->feat_planes.as<float>();
+    float* feat_lo = reinterpret_cast<float*>(c->feat_planes.as<unsigned char>() + feat_bytes);
+    const bool fuse_avgpool = t3.groups_per_clip == 1 && H3 * W3 <= kTcPooledPix;
     auto k2 = conv_tc_kernel<32, 64, 6>;
     auto k3 = conv_tc_kernel<64, 128, 4>;
     GAT_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
@@ -738,25 +745,24 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
         Conv1PlanesParams p1{mel + c0 * H0 * W0, nc, H0, W0, c->conv_w[0].as<float>(), c->conv_b[0].as<float>(), act1_hf, act1_hb, act1_lb, 0.01f};
         LAUNCH(c, conv1_pool_planes_kernel, (unsigned)(nc * ceil_div(H1 * W1, 256)), 256, 0, stream, p1);
         ConvTcParams p2{act1_hf, act1_hb, act1_lb, c->conv_w_tc[1].as<unsigned short>(), c->conv_b[1].as<float>(), nc, H1, W1, t2.R,
-                        t2.seg, t2.cw, t2.col_blocks, t2.groups_per_clip, 1, nullptr, act2_hf, act2_hb, act2_lb, 0.01f, c->tc_debug ? c->tc_debug_buf.as<long long>() : nullptr};
+                        t2.seg, t2.cw, t2.col_blocks, t2.groups_per_clip, 1, nullptr, act2_hf, act2_hb, act2_lb, nullptr, nullptr, 0, 0, 0.01f,
+                        c->tc_debug ? c->tc_debug_buf.as<long long>() : nullptr};
         const int work2 = nc * p2.groups_per_clip;
         KNAME("conv2_tc_32_64");
         LAUNCH(c, k2, (unsigned)(work2 < c->num_sms ? work2 : c->num_sms), kTcThreads, smem2, stream, p2);
         ConvTcParams p3{act2_hf, act2_hb, act2_lb, c->conv_w_tc[2].as<unsigned short>(), c->conv_b[2].as<float>(), nc, H2, W2, t3.R,
-                        t3.seg, t3.cw, t3.col_blocks, t3.groups_per_clip, 0, c->act3.as<float>() + (size_t)c0 * H3 * W3 * 128, nullptr, nullptr, nullptr, 0.01f,
+                        t3.seg, t3.cw, t3.col_blocks, t3.groups_per_clip, fuse_avgpool ? 2 : 0,
+                        c->act3.as<float>() + (size_t)c0 * H3 * W3 * 128, nullptr, nullptr, nullptr, feat_hi, feat_lo, rows_pad, c0, 0.01f,
                         c->tc_debug ? c->tc_debug_buf.as<long long>() + 148 * 8 : nullptr};
         const int work3 = nc * p3.groups_per_clip;
         KNAME("conv3_tc_64_128");
         LAUNCH(c, k3, (unsigned)(work3 < c->num_sms ? work3 : c->num_sms), kTcThreads, smem3, stream, p3);
     }
-    // head: adaptive average pool -> FC1 (tcgen05) -> FC2 + softmax
-    const long long rows_pad = (N + 127) / 128 * 128;
-    const size_t feat_bytes = (size_t)512 * rows_pad * 16;
-    if (c->feat_planes.ensure(2 * feat_bytes) || c->hid.ensure((size_t)N * 256 * 4)) return 1;
-    float* feat_hi = c->feat_planes.as<float>();
-    float* feat_lo = reinterpret_cast<float*>(c->feat_planes.as<unsigned char>() + feat_bytes);
-    AvgPoolPlanesParams pa{c->act3.as<float>(), (int)N, H3, W3, 128, feat_hi, feat_lo, rows_pad};
-    LAUNCH(c, avgpool_planes_kernel, (unsigned)((N * 4 * 128 + 255) / 256), 256, 0, stream, pa);
+    // head: (adaptive average pool ->) FC1 (tcgen05) -> FC2 + softmax
+    if (!fuse_avgpool) {
+        AvgPoolPlanesParams pa{c->act3.as<float>(), (int)N, H3, W3, 128, feat_hi, feat_lo, rows_pad};
+        LAUNCH(c, avgpool_planes_kernel, (unsigned)((N * 4 * 128 + 255) / 256), 256, 0, stream, pa);
+    }
     auto kf = fc_tc_kernel<256>;
     const size_t fc_smem = fc_tc_smem_bytes<256>();
     GAT_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fc_smem));
