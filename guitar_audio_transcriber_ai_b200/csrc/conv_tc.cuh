@@ -3,15 +3,15 @@
 //
 //   D[pixel (M = 128)][c_out (N)] += A[pixel][k] * B[c_out][k],   k = (tap, c_in)
 //
-// * Activations live in HBM as "chunk planes": [clip][c_in/8][padded pixel][8 x 16 bit], three arrays (hf, hb, lb).
+// * Activations live in HBM as "chunk planes": [clip][c_in/8][padded pixel][8 x 16 bit], two arrays (hf, lb).
 //   With that layout and the no-swizzle K-major operand format, the rows an MMA reads for tap (ky,kx) are the SAME shared-memory planes addressed
 //   (ky*Wp + kx) * 16 bytes further: im2col costs nothing and every load is a contiguous 1-D bulk (TMA) copy.
-// * Split product: x = hf + lo with hf = FP16(x).  hf*hf runs as FP16 MMAs, the two correction terms lo*hf + hf*lo -
-//   2^-12 of the result - as BF16 MMAs on BF16 copies (hb = BF16(hf), lb = BF16(lo)); all are kind::f16 with K = 16 and
-//   accumulate in the same FP32 TMEM tile.  Three 16-bit MMAs per 16 channels instead of the six TF32 MMAs of 3xTF32,
-//   6 bytes per stored activation instead of 8, measured max error 4.9e-6 on |x| ~ 7 (tests/gpu_probe/
-//   tc_probe_hybrid.cu: the same as three TF32 passes; one TF32 pass: 5e-3).  The reference runs the CNN in fp32.
-//   (A and B of one MMA must share a format - mixing F16 and BF16 is an illegal instruction - hence the hb copies.)
+// * Split product: x = hf + lo with hf = FP16(x), for activations (lo kept as BF16: lb) and for weights (pre-scaled by
+//   a power of two per layer so that lo sits in FP16's normal range: wf, wl in FP16, plus wb = BF16(wf)).
+//   x*w ~= hf*wf (FP16 MMA) + lb*wb (BF16 MMA) + hf*wl (FP16 MMA): three kind::f16 MMAs of K = 16 per 16 channels into
+//   one FP32 TMEM tile where 3xTF32 needs six, 4 bytes per stored activation instead of 8, and the error of three TF32
+//   passes (tests/gpu_probe/tc_probe_hybrid.cu: 4.9e-6 on |x| ~ 7; one TF32 pass: 5e-3).  The reference runs the CNN in
+//   fp32.  (A and B of one MMA must share a format - mixing F16 and BF16 is an illegal instruction - hence wb.)
 // * One CTA per SM, warp-specialised: warp 0 = weight producer, warp 1 = MMA issuer (one thread), warps 2-5 =
 //   epilogue, warp 6 = activation producer.  The 32 input channels of a K block are staged as two HALVES of
 //   16 channels with their own full/empty barriers and the MMAs run half-major (half 0: 9 taps, half 1: 9 taps),
@@ -38,9 +38,9 @@ constexpr int kTcPooledPix = kTcGroupPix / 4;     // pooled pixels of one group 
 
 struct ConvTcParams {
     const unsigned short* in_hf;                  // [clip][CIN/8][Hp*Wp][8 fp16]   FP16(x)
-    const unsigned short* in_hb;                  // [clip][CIN/8][Hp*Wp][8 bf16]   BF16(hf)
     const unsigned short* in_lb;                  // [clip][CIN/8][Hp*Wp][8 bf16]   BF16(x - hf)
-    const unsigned short* w;                      // [CIN/32][half][9 taps] stages of {hf | hb | lb}, each [2 chunks][COUT][8 x 16 bit]
+    const unsigned short* w;                      // [CIN/32][half][9 taps] stages of {wf | wb | wl}, each [2 chunks][COUT][8 x 16 bit]
+    float w_unscale;                              // 2^-S: the weights were multiplied by 2^S before the split
     const float* bias;                            // [COUT] (BatchNorm folded)
     int n_clips, H, W;                            // conv input size without the border; Hp = H+2, Wp = W+2
     int R;                                        // image rows per group (even, R*seg <= 384)
@@ -48,9 +48,9 @@ struct ConvTcParams {
     int cw;                                       // output columns per column block (even unless there is one block)
     int col_blocks;
     int groups_per_clip;                          // row blocks * col_blocks
-    int out_planes;                               // 1: next layer's planes (hf / hb / lb); 0: dense fp32 NHWC into out_dense;
+    int out_planes;                               // 1: next layer's planes (hf / lb); 0: dense fp32 NHWC into out_dense;
                                                   // 2: AdaptiveAvgPool2d((4,4)) of the pooled map -> FC1 operand planes (one group per clip)
-    float* out_dense; unsigned short* out_hf; unsigned short* out_hb; unsigned short* out_lb;
+    float* out_dense; unsigned short* out_hf; unsigned short* out_lb;
     float* feat_hi; float* feat_lo;               // mode 2: [COUT*4 chunks][feat_rows][4] TF32 hi / fp32 remainder (fc_tc.cuh)
     long long feat_rows; long long clip0;         // mode 2: padded row count of those planes, index of this launch's first clip
     float slope;
@@ -61,7 +61,7 @@ __host__ __device__ inline int conv_tc_plane_pixels(int seg) { return kTcGroupPi
 
 template <int COUT>
 __host__ __device__ inline size_t conv_tc_smem_bytes(int seg, int nstage) {
-    return (size_t)12 * conv_tc_plane_pixels(seg) * 16             // A: 4 + 4 + 4 chunk planes (hf, hb, lb) of a 32-channel K block
+    return (size_t)8 * conv_tc_plane_pixels(seg) * 16              // A: 4 + 4 chunk planes (hf, lb) of a 32-channel K block
          + (size_t)nstage * 6 * COUT * 16                          // weight ring (one stage = one tap of one K half)
          + (size_t)kTcGroupPix * kTcStageStride * 4                // epilogue staging
          + (COUT == 128 ? (size_t)kTcPooledPix * kTcStageStride * 4 : 0)   // pooled map of the last conv layer (mode 2)
@@ -72,7 +72,7 @@ template <int CIN, int COUT, int NSTAGE>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) {
     using namespace tc;
     constexpr int NKB = CIN / 32;
-    constexpr uint32_t W_STAGE = 6 * COUT * 16;            // hf | hb | lb, each 2 chunks x COUT x 16 B
+    constexpr uint32_t W_STAGE = 6 * COUT * 16;            // wf | wb | wl, each 2 chunks x COUT x 16 B
     constexpr int ACC = (2 * kTcTiles * COUT <= 512) ? 2 : 1;      // accumulator sets in TMEM (conv2: 2 x 192 columns)
     constexpr uint32_t TMEM_COLS = ACC * kTcTiles * COUT <= 256 ? 256 : 512;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -81,8 +81,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
     const int Pg = conv_tc_plane_pixels(seg);
     const bool contiguous = p.col_blocks == 1 && seg == Wp;
     const uint32_t plane = (uint32_t)Pg * 16;
-    unsigned char* a_buf = smem;                                   // planes 0-3: hf chunks, 4-7: hb chunks, 8-11: lb chunks
-    unsigned char* w_buf = a_buf + (size_t)12 * plane;
+    unsigned char* a_buf = smem;                                   // planes 0-3: hf chunks, 4-7: lb chunks
+    unsigned char* w_buf = a_buf + (size_t)8 * plane;
     float* staging = reinterpret_cast<float*>(w_buf + (size_t)NSTAGE * W_STAGE);
     float* pooled = staging + (size_t)kTcGroupPix * kTcStageStride;   // only present (and used) when COUT == 128
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(staging) + (size_t)kTcGroupPix * kTcStageStride * 4
@@ -134,24 +134,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
                 for (int half = 0; half < 2; ++half) {
                     if (lane == 0) {
                         mbar_wait(a_empty + half, (it & 1) ^ 1);
-                        mbar_expect_tx(a_full + half, contiguous ? 6 * plane : 6 * (uint32_t)rows * row_bytes);
+                        mbar_expect_tx(a_full + half, contiguous ? 4 * plane : 4 * (uint32_t)rows * row_bytes);
                     }
                     __syncwarp();
-                    // the 6 planes of this K half: chunks 2*half, 2*half+1 of hf, hb and lb
+                    // the 4 planes of this K half: chunks 2*half, 2*half+1 of hf and lb
                     auto plane_src = [&](int q, int& slot) -> const unsigned char* {
                         const int arr = q >> 1, c16 = half * 2 + (q & 1);
                         slot = arr * 4 + c16;
-                        const unsigned short* src = arr == 0 ? p.in_hf : (arr == 1 ? p.in_hb : p.in_lb);
+                        const unsigned short* src = arr == 0 ? p.in_hf : p.in_lb;
                         return reinterpret_cast<const unsigned char*>(src) + ((long long)clip * (CIN / 8) + kb * 4 + c16) * plane_pix * 16;
                     };
                     if (contiguous) {
-                        if (lane < 6) {
+                        if (lane < 4) {
                             int slot;
                             const unsigned char* src = plane_src(lane, slot);
                             bulk_g2s(a_buf + (size_t)slot * plane, src + q_start * 16, plane, a_full + half);
                         }
                     } else {                               // R+2 row segments per plane, each seg pixels from column xs-1;
-                        for (int i = lane; i < 6 * rows; i += 32) {        // slot 0 of the plane stays the unused slack pixel
+                        for (int i = lane; i < 4 * rows; i += 32) {        // slot 0 of the plane stays the unused slack pixel
                             const int q = i / rows, a = i - q * rows;
                             int slot;
                             const unsigned char* src = plane_src(q, slot);
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
             constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
             const uint32_t a_lbo = (plane >> 4) << 16, b_lbo = ((uint32_t)(COUT * 16) >> 4) << 16;
             const uint32_t a_hf = (smem_u32(a_buf) >> 4) | a_lbo;
-            const uint32_t a_hb = a_hf + ((4 * plane) >> 4), a_lb = a_hf + ((8 * plane) >> 4);
+            const uint32_t a_lb = a_hf + ((4 * plane) >> 4);
             const uint32_t a_step = (2 * plane) >> 4;                     // two 16-byte K chunks (16 channels) per MMA
             auto desc = [](uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; };
             uint32_t it = 0, use = 0, wi = 0;
@@ -197,14 +197,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
                             fence_after_thread_sync();
                             const uint32_t row_off = (uint32_t)((tap / 3) * seg + (tap % 3));         // in 16-byte units
                             const uint32_t w_hf = ((smem_u32(w_buf) + st * W_STAGE) >> 4) | b_lbo;
-                            const uint32_t w_hb = w_hf + ((2 * COUT * 16) >> 4), w_lb = w_hf + ((4 * COUT * 16) >> 4);
+                            const uint32_t w_hb = w_hf + ((2 * COUT * 16) >> 4), w_lf = w_hf + ((4 * COUT * 16) >> 4);
                             const uint32_t a_off = row_off + (uint32_t)half * a_step;
 #pragma unroll
                             for (int g = 0; g < kTcTiles; ++g) {
                                 const uint32_t d = d_base + (uint32_t)(g * COUT);
-                                mma_16bit(d, desc(a_hf + a_off + g * 128), desc(w_hf), idesc_h, accumulate);   // hf * hf   (FP16)
-                                mma_16bit(d, desc(a_lb + a_off + g * 128), desc(w_hb), idesc_b, 1u);           // lo * hf   (BF16)
-                                mma_16bit(d, desc(a_hb + a_off + g * 128), desc(w_lb), idesc_b, 1u);           // hf * lo   (BF16)
+                                mma_16bit(d, desc(a_hf + a_off + g * 128), desc(w_hf), idesc_h, accumulate);   // hf * wf   (FP16)
+                                mma_16bit(d, desc(a_lb + a_off + g * 128), desc(w_hb), idesc_b, 1u);           // lb * wb   (BF16)
+                                mma_16bit(d, desc(a_hf + a_off + g * 128), desc(w_lf), idesc_h, 1u);           // hf * wl   (FP16)
                             }
                             accumulate = 1;
                             mma_commit(w_empty + st);       // weights of this stage are free once those MMAs retire
@@ -268,17 +268,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         const float m = fmaxf(fmaxf(s00[e], s00[kTcStageStride + e]), fmaxf(s10[e], s10[kTcStageStride + e]));
-                        const float z = m + __ldg(p.bias + cb * 32 + ch8 * 8 + e);
+                        const float z = m * p.w_unscale + __ldg(p.bias + cb * 32 + ch8 * 8 + e);    // exact power-of-two rescale
                         o[e] = z > 0.0f ? z : z * p.slope;
                     }
                     const int Y = rb * (p.R / 2) + r;
                     if (p.out_planes == 1) {
                         const long long pix = (long long)(Y + 1) * Wp_out + px + 1;
                         const long long c8 = (long long)clip * (COUT / 8) + cb * 4 + ch8;
-                        uint4 hf, hb, lb;
-                        split16x8(o, hf, hb, lb);
+                        uint4 hf, lb;
+                        split16x8(o, hf, lb);
                         *reinterpret_cast<uint4*>(p.out_hf + (c8 * Pout + pix) * 8) = hf;
-                        *reinterpret_cast<uint4*>(p.out_hb + (c8 * Pout + pix) * 8) = hb;
                         *reinterpret_cast<uint4*>(p.out_lb + (c8 * Pout + pix) * 8) = lb;
                     } else if (p.out_planes == 2) {
                         float* dst = pooled + (size_t)(Y * Wpool + px) * kTcStageStride + ch8 * 8;
@@ -329,7 +328,6 @@ struct Conv1PlanesParams {
     const float* in; int N, H, W;
     const float* w; const float* bias;    // [9][32], [32]
     unsigned short* out_hf;               // [clip][4][(H/2+2)*(W/2+2)][8 fp16]  FP16(x)
-    unsigned short* out_hb;               // [clip][4][...][8 bf16]              BF16(hf)
     unsigned short* out_lb;               // [clip][4][...][8 bf16]              BF16(x - hf)
     float slope;
 };
@@ -389,10 +387,9 @@ __global__ void __launch_bounds__(256) conv1_pool_planes_kernel(Conv1PlanesParam
             o[e] = z > 0.0f ? z : z * p.slope;
         }
         const long long c8 = (long long)clip * 4 + ch8;
-        uint4 hf, hb, lb;
-        tc::split16x8(o, hf, hb, lb);
+        uint4 hf, lb;
+        tc::split16x8(o, hf, lb);
         *reinterpret_cast<uint4*>(p.out_hf + (c8 * Pout + pix) * 8) = hf;
-        *reinterpret_cast<uint4*>(p.out_hb + (c8 * Pout + pix) * 8) = hb;
         *reinterpret_cast<uint4*>(p.out_lb + (c8 * Pout + pix) * 8) = lb;
     }
 }

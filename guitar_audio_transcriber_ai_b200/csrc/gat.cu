@@ -159,6 +159,7 @@ struct gat_ctx {
     // models
     DevBuf mlp_params; int mlp_dims[kMlpMaxLayers + 1] = {0}; int mlp_n_linear = 0; int mlp_n_params = 0;
     DevBuf conv_w[3], conv_b[3], fc1_w, fc1_b, fc2_w, fc2_b;
+    float conv_w_unscale[3] = {1.0f, 1.0f, 1.0f};   // 2^-S of the pre-scaled tensor-core weights
     DevBuf conv_w_tc[3];   // conv2/conv3 weights in the tensor-core operand layout (hi/lo TF32 split)
     DevBuf fc1_w_tc, feat_planes, hid, tc_debug_buf;
     bool tc_debug = false;
@@ -413,19 +414,27 @@ extern "C" int gat_load_cnn(gat_ctx* c, int32_t n_conv, const int32_t* ch, const
     }
 #ifndef GAT_CPU_EMU
     for (int i = 1; i < 3; ++i) {
-        // one contiguous blob per pipeline stage (K block, half, tap), 6*c_out*16 bytes: hf | hb | lb, each
-        // [2 chunks][c_out][8 x 16 bit] = FP16(w), BF16(FP16(w)), BF16(w - FP16(w))
+        // The weights of a layer are multiplied by 2^S (exact; undone in the epilogue) so that the largest is about 2^14:
+        // the FP16 remainders wl of all but vanishing weights then sit in FP16's normal range.
+        // One contiguous blob per pipeline stage (K block, half, tap), 6*c_out*16 bytes: wf | wb | wl, each
+        // [2 chunks][c_out][8 x 16 bit] = FP16(w'), BF16(FP16(w')), FP16(w' - FP16(w')) with w' = w * 2^S.
         const int cin = ch[i], cout = ch[i + 1];
+        float wmax = 0.0f;
+        for (size_t k = 0; k < (size_t)9 * cin * cout; ++k) wmax = fmaxf(wmax, fabsf(conv_w[i][k]));
+        int S = 0;
+        if (wmax > 0.0f) { int e; frexpf(wmax, &e); S = 14 - e; }          // wmax * 2^S in [2^13, 2^14)
+        S = S > 24 ? 24 : (S < -24 ? -24 : S);
+        c->conv_w_unscale[i] = ldexpf(1.0f, -S);
         const size_t stage = (size_t)6 * cout * 8;                     // 16-bit elements
         std::vector<unsigned short> t((size_t)(cin / 16) * 9 * stage, 0);
         for (int tap = 0; tap < 9; ++tap)
             for (int ci = 0; ci < cin; ++ci)
                 for (int oc = 0; oc < cout; ++oc) {
-                    const float w = conv_w[i][((size_t)tap * cin + ci) * cout + oc];
+                    const float w = ldexpf(conv_w[i][((size_t)tap * cin + ci) * cout + oc], S);
                     const int kh = ci / 16, c = ci % 16;                   // kh = K block * 2 + half
                     unsigned short* st = t.data() + (size_t)(kh * 9 + tap) * stage;
                     const size_t idx = ((size_t)(c / 8) * cout + oc) * 8 + (c % 8);
-                    tc::split16_host(w, st[idx], st[(size_t)2 * cout * 8 + idx], st[(size_t)4 * cout * 8 + idx]);
+                    tc::split16_weight_host(w, st[idx], st[(size_t)2 * cout * 8 + idx], st[(size_t)4 * cout * 8 + idx]);
                 }
         if (upload(c->conv_w_tc[i], t.data(), t.size())) return 1;
     }
@@ -715,20 +724,20 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
     const long long per_pass = (long long)c->num_sms * c->conv_pass_mult;
     const long long chunk = N < per_pass ? N : per_pass;
     const size_t P1 = (size_t)(H1 + 2) * (W1 + 2), P2 = (size_t)(H2 + 2) * (W2 + 2);
-    const size_t a1 = (size_t)chunk * 4 * P1 * 16, a2 = (size_t)chunk * 8 * P2 * 16;   // bytes of ONE of the three arrays (hf, hb, lb)
+    const size_t a1 = (size_t)chunk * 4 * P1 * 16, a2 = (size_t)chunk * 8 * P2 * 16;   // bytes of ONE of the two arrays (hf, lb)
     const size_t a3 = (size_t)N * H3 * W3 * 128 * 4;
-    const bool fresh = c->act1.cap < 3 * a1 + 2 * kActGuard || c->act2.cap < 3 * a2 + 2 * kActGuard ||
+    const bool fresh = c->act1.cap < 2 * a1 + 2 * kActGuard || c->act2.cap < 2 * a2 + 2 * kActGuard ||
                        c->act_shape[0] != chunk || c->act_shape[1] != H0 || c->act_shape[2] != W0;
-    if (c->act1.ensure(3 * a1 + 2 * kActGuard) || c->act2.ensure(3 * a2 + 2 * kActGuard) || c->act3.ensure(a3)) return 1;
+    if (c->act1.ensure(2 * a1 + 2 * kActGuard) || c->act2.ensure(2 * a2 + 2 * kActGuard) || c->act3.ensure(a3)) return 1;
     if (fresh) {   // zero borders (and guards) once per geometry; the kernels only ever write interiors
-        GAT_CUDA(cudaMemsetAsync(c->act1.p, 0, 3 * a1 + 2 * kActGuard, (cudaStream_t)stream));
-        GAT_CUDA(cudaMemsetAsync(c->act2.p, 0, 3 * a2 + 2 * kActGuard, (cudaStream_t)stream));
+        GAT_CUDA(cudaMemsetAsync(c->act1.p, 0, 2 * a1 + 2 * kActGuard, (cudaStream_t)stream));
+        GAT_CUDA(cudaMemsetAsync(c->act2.p, 0, 2 * a2 + 2 * kActGuard, (cudaStream_t)stream));
         c->act_shape[0] = chunk; c->act_shape[1] = H0; c->act_shape[2] = W0;
     }
-    // each activation buffer: [hf | hb | lb] chunk-plane arrays of a bytes each, between two guard bands
+    // each activation buffer: [hf | lb] chunk-plane arrays of a bytes each, between two guard bands
     auto arr = [](DevBuf& b, size_t a, int k) { return reinterpret_cast<unsigned short*>(b.as<unsigned char>() + kActGuard + (size_t)k * a); };
-    unsigned short *act1_hf = arr(c->act1, a1, 0), *act1_hb = arr(c->act1, a1, 1), *act1_lb = arr(c->act1, a1, 2);
-    unsigned short *act2_hf = arr(c->act2, a2, 0), *act2_hb = arr(c->act2, a2, 1), *act2_lb = arr(c->act2, a2, 2);
+    unsigned short *act1_hf = arr(c->act1, a1, 0), *act1_lb = arr(c->act1, a1, 1);
+    unsigned short *act2_hf = arr(c->act2, a2, 0), *act2_lb = arr(c->act2, a2, 1);
     // FC1 operand planes (written by conv3's epilogue when a clip is one group, else by avgpool_planes_kernel)
     const long long rows_pad = (N + 127) / 128 * 128;
     const size_t feat_bytes = (size_t)512 * rows_pad * 16;
@@ -742,17 +751,17 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
     GAT_CUDA(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
     for (long long c0 = 0; c0 < N; c0 += chunk) {
         const int nc = (int)(N - c0 < chunk ? N - c0 : chunk);
-        Conv1PlanesParams p1{mel + c0 * H0 * W0, nc, H0, W0, c->conv_w[0].as<float>(), c->conv_b[0].as<float>(), act1_hf, act1_hb, act1_lb, 0.01f};
+        Conv1PlanesParams p1{mel + c0 * H0 * W0, nc, H0, W0, c->conv_w[0].as<float>(), c->conv_b[0].as<float>(), act1_hf, act1_lb, 0.01f};
         LAUNCH(c, conv1_pool_planes_kernel, (unsigned)(nc * ceil_div(H1 * W1, 256)), 256, 0, stream, p1);
-        ConvTcParams p2{act1_hf, act1_hb, act1_lb, c->conv_w_tc[1].as<unsigned short>(), c->conv_b[1].as<float>(), nc, H1, W1, t2.R,
-                        t2.seg, t2.cw, t2.col_blocks, t2.groups_per_clip, 1, nullptr, act2_hf, act2_hb, act2_lb, nullptr, nullptr, 0, 0, 0.01f,
+        ConvTcParams p2{act1_hf, act1_lb, c->conv_w_tc[1].as<unsigned short>(), c->conv_w_unscale[1], c->conv_b[1].as<float>(), nc, H1, W1, t2.R,
+                        t2.seg, t2.cw, t2.col_blocks, t2.groups_per_clip, 1, nullptr, act2_hf, act2_lb, nullptr, nullptr, 0, 0, 0.01f,
                         c->tc_debug ? c->tc_debug_buf.as<long long>() : nullptr};
         const int work2 = nc * p2.groups_per_clip;
         KNAME("conv2_tc_32_64");
         LAUNCH(c, k2, (unsigned)(work2 < c->num_sms ? work2 : c->num_sms), kTcThreads, smem2, stream, p2);
-        ConvTcParams p3{act2_hf, act2_hb, act2_lb, c->conv_w_tc[2].as<unsigned short>(), c->conv_b[2].as<float>(), nc, H2, W2, t3.R,
+        ConvTcParams p3{act2_hf, act2_lb, c->conv_w_tc[2].as<unsigned short>(), c->conv_w_unscale[2], c->conv_b[2].as<float>(), nc, H2, W2, t3.R,
                         t3.seg, t3.cw, t3.col_blocks, t3.groups_per_clip, fuse_avgpool ? 2 : 0,
-                        c->act3.as<float>() + (size_t)c0 * H3 * W3 * 128, nullptr, nullptr, nullptr, feat_hi, feat_lo, rows_pad, c0, 0.01f,
+                        c->act3.as<float>() + (size_t)c0 * H3 * W3 * 128, nullptr, nullptr, feat_hi, feat_lo, rows_pad, c0, 0.01f,
                         c->tc_debug ? c->tc_debug_buf.as<long long>() + 148 * 8 : nullptr};
         const int work3 = nc * p3.groups_per_clip;
         KNAME("conv3_tc_64_128");

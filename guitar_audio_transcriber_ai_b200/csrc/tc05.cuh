@@ -146,30 +146,30 @@ __host__ __device__ inline unsigned short bf16_bits(float x) {
     u += 0x7fffu + ((u >> 16) & 1u);
     return (unsigned short)(u >> 16);
 }
-// Split of an fp32 value for the conv tensor path: hf = FP16(x) (round to nearest; clamped so it never overflows),
-// hb = BF16(hf), lb = BF16(x - hf).  x*w ~= hf*wf + lb*wb_hi + hb*wl: one FP16 MMA + two BF16 MMAs.
+// Split of an fp32 value for the conv tensor path: hf = FP16(x) (round to nearest; clamped so it never overflows) and
+// the remainder lo = x - hf, stored as BF16 (activations) or FP16 (weights, which are pre-scaled by a power of two so
+// that their remainders sit in FP16's normal range).  x*w ~= hf*wf + lb*wb + hf*wl: FP16, BF16 and FP16 MMAs - the two
+// operands of one MMA must share a format, which is why the weights carry a BF16 copy of their hi part (wb).
 constexpr float kF16Max = 65504.0f;
-__host__ inline void split16_host(float x, unsigned short& hf, unsigned short& hb, unsigned short& lb) {
-    const float c = x > kF16Max ? kF16Max : (x < -kF16Max ? -kF16Max : x);
+__host__ inline void split16_weight_host(float w, unsigned short& hf, unsigned short& hb, unsigned short& lf) {
+    const float c = w > kF16Max ? kF16Max : (w < -kF16Max ? -kF16Max : w);
     const __half h = __float2half_rn(c);
     const float hv = __half2float(h);
-    hf = __half_as_ushort(h); hb = bf16_bits(hv); lb = bf16_bits(x - hv);
+    hf = __half_as_ushort(h); hb = bf16_bits(hv); lf = __half_as_ushort(__float2half_rn(w - hv));
 }
-// Eight channels -> the three 16-byte chunks.
-__device__ __forceinline__ void split16x8(const float (&o)[8], uint4& hf, uint4& hb, uint4& lb) {
-    uint32_t f[4], h[4], l[4];
+// Eight channels -> the two 16-byte chunks of an activation: hf (FP16) and lb (BF16 of the remainder).
+__device__ __forceinline__ void split16x8(const float (&o)[8], uint4& hf, uint4& lb) {
+    uint32_t f[4], l[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {       // packed conversions: two values per instruction
         const float x0 = fminf(fmaxf(o[2 * e], -kF16Max), kF16Max), x1 = fminf(fmaxf(o[2 * e + 1], -kF16Max), kF16Max);
         const __half2 fp = __floats2half2_rn(x0, x1);
         const float2 fv = __half22float2(fp);
-        const __nv_bfloat162 hp = __floats2bfloat162_rn(fv.x, fv.y), lp = __floats2bfloat162_rn(o[2 * e] - fv.x, o[2 * e + 1] - fv.y);
+        const __nv_bfloat162 lp = __floats2bfloat162_rn(o[2 * e] - fv.x, o[2 * e + 1] - fv.y);
         f[e] = *reinterpret_cast<const uint32_t*>(&fp);
-        h[e] = *reinterpret_cast<const uint32_t*>(&hp);
         l[e] = *reinterpret_cast<const uint32_t*>(&lp);
     }
     hf = make_uint4(f[0], f[1], f[2], f[3]);
-    hb = make_uint4(h[0], h[1], h[2], h[3]);
     lb = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
