@@ -156,10 +156,10 @@ def kernel_table(prof: dict, steps: int, n_clips: int, T: int, peaks: dict):
     work = {   # kernel -> (bound, algorithmic bytes or flops per STEP)
         "clip_scale_kernel": ("hbm", n_clips * (4 * n + 4)),
         "stft_mel_f32_image": ("hbm", n_clips * (4 * n + 4 * 64 * T)),
-        "conv1_pool_planes_kernel": ("hbm", n_clips * (4 * 64 * T + 6 * H1 * W1 * 32)),       # fp32 image in, hf+hb+lb (3 x 16 bit) planes out
+        "conv1_pool_planes_kernel": ("hbm", n_clips * (4 * 64 * T + 4 * H1 * W1 * 32)),       # fp32 image in, hf + lb (2 x 16 bit) planes out
         "conv2_tc_32_64": ("tensor", n_clips * 2.0 * H1 * W1 * 64 * 32 * 9),
         "conv3_tc_64_128": ("tensor", n_clips * 2.0 * H2 * W2 * 128 * 64 * 9),
-        "avgpool_planes_kernel": ("hbm", n_clips * (4 * 8 * (T // 8) * 128 + 2 * 4 * 2048)),
+        "avgpool_planes_kernel": ("hbm", n_clips * (4 * 8 * (T // 8) * 128 + 2 * 4 * 2048)),   # only launched for clips longer than one conv3 group
         "fc1_tc_2048_256": ("tensor", n_clips * 2.0 * 2048 * 256),
         "fc2_softmax_kernel": ("hbm", n_clips * (4 * 256 + 8 * 47)),
         "argmax_kernel": ("hbm", n_clips * (4 * 47 + 12)),
