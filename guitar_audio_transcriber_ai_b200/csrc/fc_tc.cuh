@@ -44,15 +44,16 @@ __global__ void __launch_bounds__(256) avgpool_planes_kernel(AvgPoolPlanesParams
     *reinterpret_cast<float4*>(p.out_lo + off) = make_float4(o[0] - hi.x, o[1] - hi.y, o[2] - hi.z, o[3] - hi.w);
 }
 
-// ---- FC1 + bias + LeakyReLU on tcgen05.  One CTA per 128 rows (clips); K streamed in blocks of 32.
+// ---- FC1 on tcgen05.  CTA (x, y) = 128 rows (clips) x one of `k_splits` slices of K, streamed in blocks of 32; the
+// slices' partial sums are added, biased and activated by fc2_softmax_kernel (split-K keeps every SM busy when there
+// are few clips: a single note used to wait 72 us for one CTA walking all of K).
 struct FcTcParams {
     const float* a_hi; const float* a_lo;   // [K/4][rows_pad][4]
     long long rows_pad;                     // multiple of 128
     const float* w;                         // [K/32][hi|lo][8 chunks][NOUT][4]
-    const float* bias;                      // [NOUT]
     int n_rows, K;
-    float slope;
-    float* out;                             // [n_rows][NOUT]
+    int k_splits;                           // gridDim.y; K/32 must be divisible by it
+    float* out;                             // [k_splits][n_rows][NOUT] partial sums (no bias, no activation)
 };
 
 constexpr int kFcStages = 2;
@@ -84,7 +85,8 @@ __global__ void __launch_bounds__(192, 1) fc_tc_kernel(FcTcParams p) {
     __syncthreads();
     fence_after_thread_sync();
     const uint32_t tmem = *tmem_slot;
-    const int nkb = p.K / 32;
+    const int nkb = p.K / 32 / p.k_splits;                  // K blocks of this slice
+    const int kb0 = blockIdx.y * nkb;
     const long long row0 = (long long)blockIdx.x * 128;
 
     if (warp == 0) {
@@ -97,9 +99,9 @@ __global__ void __launch_bounds__(192, 1) fc_tc_kernel(FcTcParams p) {
                 for (int part = 0; part < 2; ++part) {
                     const float* src = part ? p.a_lo : p.a_hi;
                     for (int c = 0; c < 8; ++c)
-                        bulk_g2s(dst + (size_t)(part * 8 + c) * 2048, src + (((long long)kb * 8 + c) * p.rows_pad + row0) * 4, 2048, full + st);
+                        bulk_g2s(dst + (size_t)(part * 8 + c) * 2048, src + (((long long)(kb0 + kb) * 8 + c) * p.rows_pad + row0) * 4, 2048, full + st);
                 }
-                bulk_g2s(dst + A_STAGE, p.w + (size_t)kb * (W_STAGE / 4), W_STAGE, full + st);
+                bulk_g2s(dst + A_STAGE, p.w + (size_t)(kb0 + kb) * (W_STAGE / 4), W_STAGE, full + st);
             }
         }
     } else if (warp == 1) {
@@ -134,17 +136,9 @@ __global__ void __launch_bounds__(192, 1) fc_tc_kernel(FcTcParams p) {
             float v[32];
             tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cb * 32), v);
             if (row < p.n_rows) {
-                float* o = p.out + row * NOUT + cb * 32;
+                float* o = p.out + ((long long)blockIdx.y * p.n_rows + row) * NOUT + cb * 32;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 r;
-                    float z;
-                    z = v[j + 0] + __ldg(p.bias + cb * 32 + j + 0); r.x = z > 0.0f ? z : z * p.slope;
-                    z = v[j + 1] + __ldg(p.bias + cb * 32 + j + 1); r.y = z > 0.0f ? z : z * p.slope;
-                    z = v[j + 2] + __ldg(p.bias + cb * 32 + j + 2); r.z = z > 0.0f ? z : z * p.slope;
-                    z = v[j + 3] + __ldg(p.bias + cb * 32 + j + 3); r.w = z > 0.0f ? z : z * p.slope;
-                    *reinterpret_cast<float4*>(o + j) = r;
-                }
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
         }
     }
@@ -153,9 +147,11 @@ __global__ void __launch_bounds__(192, 1) fc_tc_kernel(FcTcParams p) {
     if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-// ---- FC2 + softmax: one warp per clip.
+// ---- FC1 finish (sum of the K slices + bias + LeakyReLU) -> FC2 + softmax: one warp per clip.
 struct Fc2Params {
-    const float* hid; int N, hidden;     // [N][hidden]
+    const float* hid; int N, hidden;     // [k_splits][N][hidden] partial sums of FC1
+    int k_splits;
+    const float* b1; float slope;        // FC1 bias [hidden], LeakyReLU slope
     const float* w2; const float* b2;    // [hidden][classes], [classes]
     int classes;                         // <= 64
     float* logits; float* probs;         // [N][classes]
@@ -164,18 +160,27 @@ struct Fc2Params {
 __global__ void __launch_bounds__(256) fc2_softmax_kernel(Fc2Params p) {
     GAT_DYN_SMEM(smem_raw);
     float* w = reinterpret_cast<float*>(smem_raw);                 // [hidden][classes]
+    float* hbuf = w + p.hidden * p.classes;                        // [warps][hidden] activated hidden vectors
     for (int i = threadIdx.x; i < p.hidden * p.classes; i += blockDim.x) w[i] = p.w2[i];
     __syncthreads();
     const int lane = lane_id(), nwarps = blockDim.x >> 5;
+    float* h = hbuf + warp_id() * p.hidden;
     for (int clip = blockIdx.x * nwarps + warp_id(); clip < p.N; clip += gridDim.x * nwarps) {
-        const float* h = p.hid + (long long)clip * p.hidden;
+        for (int k = lane; k < p.hidden; k += 32) {
+            float acc = 0.0f;
+            for (int s = 0; s < p.k_splits; ++s) acc += __ldg(p.hid + ((long long)s * p.N + clip) * p.hidden + k);
+            const float z = acc + __ldg(p.b1 + k);
+            h[k] = z > 0.0f ? z : z * p.slope;
+        }
+        __syncwarp();
         float a0 = 0.0f, a1 = 0.0f;
         const bool has0 = lane < p.classes, has1 = lane + 32 < p.classes;
         for (int k = 0; k < p.hidden; ++k) {
-            const float x = __ldg(h + k);
+            const float x = h[k];
             if (has0) a0 = fmaf(x, w[k * p.classes + lane], a0);
             if (has1) a1 = fmaf(x, w[k * p.classes + lane + 32], a1);
         }
+        __syncwarp();
         const float v0 = has0 ? a0 + p.b2[lane] : -3.0e38f;
         const float v1 = has1 ? a1 + p.b2[lane + 32] : -3.0e38f;
         const float mx = warp_max(fmaxf(v0, v1));

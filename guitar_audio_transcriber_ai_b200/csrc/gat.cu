@@ -588,7 +588,12 @@ int run_yin(gat_ctx* c, const float* audio, int64_t N, int64_t n, bool normalize
     p.max_period = mp < kYinFrame - kYinWin - 1 ? mp : kYinFrame - kYinWin - 1;
     if (p.min_period < 1 || p.max_period <= p.min_period + 1) return fail("yin: period range [%d, %d] unusable", p.min_period, p.max_period);
     p.trough_threshold = c->cfg.yin_trough_threshold; p.f0 = f0;
-    p.seg_frames = T < 11 ? T : 11;          // one extra block of work per segment: 12/11 blocks per frame instead of 2
+    // A warp walks `seg_frames` frames of a clip with seg_frames + 1 blocks of work (12/11 blocks per frame at 11).  With
+    // few clips (a single note) shorter segments trade redundant blocks for parallelism: latency, not throughput.
+    const long long warps = (long long)c->num_sms * 12;
+    int seg = 11;
+    while (seg > 1 && (long long)N * ((T + seg - 1) / seg) < warps) seg = (seg + 1) / 2;
+    p.seg_frames = T < seg ? T : seg;
     const int lags = p.max_period + 1;
     int rc;
     if (lags <= 7 * 32) rc = launch_yin<7>(c, p, stream);
@@ -775,11 +780,18 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
     auto kf = fc_tc_kernel<256>;
     const size_t fc_smem = fc_tc_smem_bytes<256>();
     GAT_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fc_smem));
-    FcTcParams pf{feat_hi, feat_lo, rows_pad, c->fc1_w_tc.as<float>(), c->fc1_b.as<float>(), (int)N, 2048, 0.01f, c->hid.as<float>()};
+    // K is always cut into the same 8 slices, whatever the batch: the summation order of a clip's hidden vector - and so
+    // its probabilities, bit for bit - must not depend on how many other clips are in the call (tests check that).
+    // 32 row blocks x 8 slices at 4096 clips; 8 CTAs instead of one walking all of K for a single note.
+    const int row_blocks = (int)(rows_pad / 128);
+    const int k_splits = 8;
+    if (c->hid.ensure((size_t)k_splits * N * 256 * 4)) return 1;
+    FcTcParams pf{feat_hi, feat_lo, rows_pad, c->fc1_w_tc.as<float>(), (int)N, 2048, k_splits, c->hid.as<float>()};
     KNAME("fc1_tc_2048_256");
-    LAUNCH(c, kf, (unsigned)(rows_pad / 128), 192, fc_smem, stream, pf);
-    Fc2Params p2f{c->hid.as<float>(), (int)N, 256, c->fc2_w.as<float>(), c->fc2_b.as<float>(), c->classes, cnn_logits, cnn_probs};
-    const size_t fc2_smem = (size_t)256 * c->classes * 4 + 64;
+    LAUNCH(c, kf, dim3((unsigned)row_blocks, (unsigned)k_splits), 192, fc_smem, stream, pf);
+    Fc2Params p2f{c->hid.as<float>(), (int)N, 256, k_splits, c->fc1_b.as<float>(), 0.01f, c->fc2_w.as<float>(), c->fc2_b.as<float>(),
+                  c->classes, cnn_logits, cnn_probs};
+    const size_t fc2_smem = (size_t)256 * c->classes * 4 + (size_t)8 * 256 * 4 + 64;
     GAT_CUDA(cudaFuncSetAttribute(fc2_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fc2_smem));
     const long long ctas2 = (N + 7) / 8;
     LAUNCH(c, fc2_softmax_kernel, (unsigned)(ctas2 < 2 * c->num_sms ? ctas2 : 2 * c->num_sms), 256, fc2_smem, stream, p2f);
