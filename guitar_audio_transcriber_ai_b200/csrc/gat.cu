@@ -1051,9 +1051,10 @@ int transcribe_host(gat_ctx* c, const void* audio_host_v, int sample_bytes, int6
         c->e2e_streams = true;
     }
     const int classes = c->classes;
-    // 4 x num_sms clips per chunk (592 clips = 52 MB at 1 s), measured on B200 at 4096 x 1 s clips: 1x 11.6 ms, 2x 8.6, 3x 8.1,
-    // 4x 7.6, 6x 7.9 - smaller chunks pay ~0.25 ms of fixed kernel cost each and stop hiding behind the copies, larger
-    // ones lengthen the un-overlapped tail.  At 4x the step is copy-bound: 361 MB at the 53 GB/s this host link sustains.
+    // 4 x num_sms clips per chunk (592 clips = 52 MB at 1 s).  Measured on B200 at 4096 x 1 s clips, float32 / PCM_16 host
+    // clips: 2x 7.14 / 6.37 ms, 3x 7.25 / 5.98, 4x 7.25 / 5.58, 5x 7.34 / 5.60.  With float32 clips the step is copy-bound
+    // (361 MB at the ~51 GB/s this host link sustains) and the chunk size hardly matters; with PCM_16 clips the kernels
+    // are the bound and larger chunks amortise their fixed cost.
     const int64_t want = 4 * (int64_t)c->num_sms;
     const int64_t chunk = N < want ? N : want;
     if (sample_bytes == 2 && (c->e2e_pcm[0].ensure((size_t)chunk * n * 2) || c->e2e_pcm[1].ensure((size_t)chunk * n * 2))) return 1;
