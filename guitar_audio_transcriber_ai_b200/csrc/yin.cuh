@@ -80,14 +80,24 @@ __global__ void __launch_bounds__(384, 1) yin_kernel(YinParams p) {
             if (fill_left == 0) {
                 __syncwarp();
                 const long long nb = (long long)kYinBlock * (blk - 1);
+                // global loads eight at a time per lane: the refill is latency-bound, not bandwidth-bound
+                auto fill = [&](int first) {
+                    for (int i0 = first + lane; i0 < kYinBuf; i0 += 32 * 8) {
+                        float v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) { const int i = i0 + 32 * u; v[u] = i < kYinBuf ? padded(nb + i) : 0.0f; }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) { const int i = i0 + 32 * u; if (i < kYinBuf) buf[i] = v[u]; }
+                    }
+                };
                 if (blk == f0) {
-                    for (int i = lane; i < kYinBuf; i += 32) buf[i] = padded(nb + i);
+                    fill(0);
                 } else {                                            // slide: keep the tail, load the rest
                     // the shift is a multiple of 32, so every address is read and later overwritten by the SAME
                     // lane: program order makes the in-place forward copy safe without a staging array
                     const int keep = (int)(buf_base + kYinBuf - nb), off = kYinBuf - keep;
                     for (int i = lane; i < keep; i += 32) buf[i] = buf[i + off];
-                    for (int i = keep + lane; i < kYinBuf; i += 32) buf[i] = padded(nb + i);
+                    fill(keep);
                 }
                 buf_base = nb;
                 fill_left = kBlocksPerFill;
@@ -101,17 +111,27 @@ __global__ void __launch_bounds__(384, 1) yin_kernel(YinParams p) {
 #pragma unroll
             for (int q = 0; q < kLPT; ++q) { ring[q] = xs[b + 1 + q]; acc[q] = 0.0f; }
             float e_blk = 0.0f;
-            for (int j0 = 1; j0 <= kYinBlock; j0 += kLPT) {
+            constexpr int kFull = kYinBlock / kLPT;                 // iterations that need no bounds check
+            for (int it = 0; it < kFull; ++it) {
+                const int j0 = 1 + it * kLPT;
 #pragma unroll
                 for (int s = 0; s < kLPT; ++s) {
                     const int j = j0 + s;
-                    const bool in = j <= kYinBlock;
-                    const float xj = in ? xs[j] : 0.0f;
+                    const float xj = xs[j];
 #pragma unroll
                     for (int i = 0; i < kLPT; ++i) acc[i] = fmaf(xj, ring[(s + i) % kLPT], acc[i]);
-                    if (in) e_blk = fmaf(ring[s], ring[s], e_blk);
+                    e_blk = fmaf(ring[s], ring[s], e_blk);
                     ring[s] = xs[b + j + kLPT];
                 }
+            }
+#pragma unroll
+            for (int s = 0; s < kYinBlock - kFull * kLPT; ++s) {    // the last, partial iteration
+                const int j = 1 + kFull * kLPT + s;
+                const float xj = xs[j];
+#pragma unroll
+                for (int i = 0; i < kLPT; ++i) acc[i] = fmaf(xj, ring[(s + i) % kLPT], acc[i]);
+                e_blk = fmaf(ring[s], ring[s], e_blk);
+                ring[s] = xs[b + j + kLPT];
             }
             if (blk > f0) {
                 // ---- frame t = blk - 1: acf = previous block + this block
