@@ -186,6 +186,26 @@ def test_c_abi_argument_errors(tr22):
     out = torch.zeros(1, 64, 3, device="cuda")
     assert lib.gat_melspec_db(ctx, C.c_void_p(a.data_ptr()), 1, 600, 1, C.c_void_p(out.data_ptr()), None) != 0
     assert b"too short" in lib.gat_last_error()
+    # file front end / onset entry points
+    x = torch.zeros(2, 1000, device="cuda")
+    y = torch.zeros(2, 500, device="cuda")
+    taps = torch.zeros(33, dtype=torch.float64, device="cuda")
+    P = lambda t: C.c_void_p(t.data_ptr())
+    assert lib.gat_resample(ctx, P(x), 2, 1000, 1, 2, P(taps), 16, P(y), 499, None) != 0 and b"n_out" in lib.gat_last_error()
+    assert lib.gat_resample(ctx, P(x), 2, 1000, 0, 2, P(taps), 16, P(y), 500, None) != 0
+    assert lib.gat_resample(ctx, P(x), 2, 1000, 1, 2, P(taps), 16, P(y), 500, None) == 0
+    assert lib.gat_decode_mono(ctx, P(x), 7, 1000, 2, P(y), None) != 0 and b"sample_format" in lib.gat_last_error()
+    assert lib.gat_decode_mono(ctx, None, 0, 1000, 2, P(y), None) != 0
+    assert lib.gat_pcm16_roundtrip(ctx, None, 10, None) != 0 and lib.gat_pcm16_roundtrip(ctx, None, 0, None) == 0
+    sp = tr22.engine.slicer_params(22050, 0.5)
+    on = torch.zeros(64, dtype=torch.int64, device="cuda")
+    n = torch.zeros(1, dtype=torch.int32, device="cuda")
+    sp.onset_hop = 511
+    assert lib.gat_detect_onsets(ctx, P(x), 2000, C.byref(sp), 64, P(on), P(n), None) != 0 and b"hop" in lib.gat_last_error()
+    sp.onset_hop = 512
+    assert lib.gat_detect_onsets(ctx, P(x), 2000, C.byref(sp), 0, P(on), P(n), None) != 0
+    assert lib.gat_transcribe_clips_host_pcm16(ctx, None, 4, 11025, 0, None, None, None) != 0
+    torch.cuda.synchronize()
 
 
 def test_transcribe_audio_matches_reference_pipeline(tr22, golden_phrases):
