@@ -449,3 +449,32 @@ def test_host_entry_point_pcm16(tr22):
     b = tr22.engine.transcribe_clips_host(torch.from_numpy(q.astype(np.float32) / np.float32(32768.0)).pin_memory())
     assert np.array_equal(ia, b["indices"]) and np.array_equal(pa, b["probs"])
     assert a["h2d_bytes"] * 2 == b["h2d_bytes"]
+
+
+def test_context_lifecycle_releases_memory():
+    """gat_ctx_create / gat_ctx_destroy: every workspace a context grew is returned to the device."""
+    from guitar_audio_transcriber_ai_b200 import synth
+    from guitar_audio_transcriber_ai_b200.checkpoint import load_checkpoint
+    from guitar_audio_transcriber_ai_b200.engine import Engine
+    cnn = load_checkpoint(CKPT / "cnn_synth_sr22050.ckpt")["model"]
+    mlp = load_checkpoint(CKPT / "mlp_synth_sr22050.ckpt")["model"]
+    clips = torch.from_numpy(synth.clip_batch(64, 0.5, 22050, 0)[0]).cuda()
+    y = torch.from_numpy(synth.phrase(0)[0]).cuda()
+
+    def cycle():
+        eng = Engine(22050, device="cuda:0")
+        eng.load_cnn(cnn); eng.load_mlp(mlp)
+        eng.transcribe_clips(clips)
+        eng.segment(y, 0.5)
+        eng.resample(clips[:4], 22050, 11025)
+        torch.cuda.synchronize()
+        eng.close()
+
+    cycle()
+    torch.cuda.synchronize(); torch.cuda.empty_cache()
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(10):
+        cycle()
+    torch.cuda.synchronize(); torch.cuda.empty_cache()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 8 << 20, f"{(free0 - free1) / 2**20:.1f} MiB not returned after 10 create/destroy cycles"
