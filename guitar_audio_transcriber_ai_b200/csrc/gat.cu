@@ -160,7 +160,7 @@ struct gat_ctx {
     DevBuf mlp_params; int mlp_dims[kMlpMaxLayers + 1] = {0}; int mlp_n_linear = 0; int mlp_n_params = 0;
     DevBuf conv_w[3], conv_b[3], fc1_w, fc1_b, fc2_w, fc2_b;
     float conv_w_unscale[3] = {1.0f, 1.0f, 1.0f};   // 2^-S of the pre-scaled tensor-core weights
-    DevBuf conv_w_tc[3];   // conv2/conv3 weights in the tensor-core operand layout (hi/lo TF32 split)
+    DevBuf conv_w_tc[3];   // conv2/conv3 weights in the tensor-core operand layout (wf | wb | wl stages, see conv_tc.cuh)
     DevBuf fc1_w_tc, feat_planes, hid, tc_debug_buf;
     bool tc_debug = false;
     int conv_pass_mult = 16;  // clips per conv pass = conv_pass_mult * num_sms; measured on B200: long passes win (5.84 ms at 1, 5.21 at 14,
@@ -683,8 +683,8 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
 }
 #else
 // conv1 on CUDA cores (C_in = 1), conv2/conv3 as tcgen05 implicit GEMMs (csrc/conv_tc.cuh), head once per batch.
-// Clips go through the convs num_sms at a time: conv3 then has exactly one group per SM and conv2 four,
-// and act1+act2 (hi/lo planes, ~0.6 MB per clip at T = 87) stay inside the 126 MB L2 between layers.
+// Clips go through the convs in passes of conv_pass_mult * num_sms (default 16 x 148 = 2368): act1 + act2 are hf / lb
+// chunk planes, 4 bytes per element (~0.3 MB per clip at T = 87); measured, long passes beat keeping them inside L2.
 constexpr size_t kActGuard = 65536;   // bytes before/after the plane buffers: halo reads of edge groups stay in bounds
 
 // Tiling of one conv layer: column blocks of `cw` output columns (one block spanning the width when the staged
