@@ -73,5 +73,14 @@ if fp.exists():
             vals.append((r[hit[0]] + " " + units.get(hit[0], "")).strip() if hit else "")
         out.append(f"| {r['Kernel Name'].split('(')[0][:60]} | " + " | ".join(vals) + " |")
     out.append("")
+yp = P / f"{tag}_yin_ncu_full_raw.csv"
+if yp.exists():
+    r = [x for x in csv_rows(yp) if x.get("ID", "").isdigit()][0]
+    g = lambda key: r[[k for k in r if k.endswith(key)][0]]
+    out += [f"## YIN kernel (`tools/yin_only.py`, 4096 x 1 s clips; `profiles/{tag}_yin_ncu_full_raw.csv`)", "",
+            f"`yin_kernel<15>`: {float(g('gpu__time_duration.sum')):.2f} ms per launch (3.73 ms before the batched refill and the bounds-check-free "
+            f"inner loop); issue slots {float(g('sm__issue_active.avg.pct_of_peak_sustained_elapsed')):.0f} %, FMA pipe "
+            f"{float(g('sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active')):.0f} %, FP64 pipe "
+            f"{float(g('sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active')):.1f} %, {g('launch__registers_per_thread')} registers.", ""]
 (P / "README.md").write_text("\n".join(out) + "\n")
 print("\n".join(out)[:3000])
