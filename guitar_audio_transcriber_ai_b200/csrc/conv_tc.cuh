@@ -12,8 +12,8 @@
 //   one FP32 TMEM tile where 3xTF32 needs six, 4 bytes per stored activation instead of 8, and the error of three TF32
 //   passes (tests/gpu_probe/tc_probe_hybrid.cu: 4.9e-6 on |x| ~ 7; one TF32 pass: 5e-3).  The reference runs the CNN in
 //   fp32.  (A and B of one MMA must share a format - mixing F16 and BF16 is an illegal instruction - hence wb.)
-// * One CTA per SM, warp-specialised: warp 0 = weight producer, warp 1 = MMA issuer (one thread), warps 2-5 =
-//   epilogue, warp 6 = activation producer.  The 32 input channels of a K block are staged as two HALVES of
+// * One CTA per SM, warp-specialised: warp 0 = weight producer, warp 1 = MMA issuer (one thread), then one (conv2) or
+//   two (conv3) groups of four epilogue warps, last warp = activation producer.  The 32 input channels of a K block are staged as two HALVES of
 //   16 channels with their own full/empty barriers and the MMAs run half-major (half 0: 9 taps, half 1: 9 taps),
 //   so the next group's half 0 streams in from HBM while this group's half 1 is being multiplied: the
 //   activation buffer is single (it fills shared memory) yet its load latency is hidden.  A work item is a GROUP of three consecutive 128-pixel tiles covering R whole image rows, so
@@ -32,7 +32,10 @@ namespace gat {
 
 constexpr int kTcTiles = 3;                       // 128-pixel tiles per group
 constexpr int kTcGroupPix = 128 * kTcTiles;
-constexpr int kTcThreads = 224;
+// threads of a CTA: weight producer + MMA issuer + EPI groups of four epilogue warps + activation producer
+__host__ __device__ constexpr int conv_tc_threads(int epi) { return 32 * (3 + 4 * epi); }
+// the last conv layer has a single accumulator set (TMEM), so its epilogue is exposed: two epilogue groups drain it
+__host__ __device__ constexpr int conv_tc_epi_groups(int cout) { return cout == 128 ? 2 : 1; }
 constexpr int kTcStageStride = 33;                // floats per staged pixel (32 channels + 1 pad)
 constexpr int kTcPooledPix = kTcGroupPix / 4;     // pooled pixels of one group (epilogue mode 2 keeps them in shared memory)
 
@@ -61,16 +64,19 @@ __host__ __device__ inline int conv_tc_plane_pixels(int seg) { return kTcGroupPi
 
 template <int COUT>
 __host__ __device__ inline size_t conv_tc_smem_bytes(int seg, int nstage) {
+    constexpr int EPI = conv_tc_epi_groups(COUT);
     return (size_t)8 * conv_tc_plane_pixels(seg) * 16              // A: 4 + 4 chunk planes (hf, lb) of a 32-channel K block
          + (size_t)nstage * 6 * COUT * 16                          // weight ring (one stage = one tap of one K half)
-         + (size_t)kTcGroupPix * kTcStageStride * 4                // epilogue staging
-         + (COUT == 128 ? (size_t)kTcPooledPix * kTcStageStride * 4 : 0)   // pooled map of the last conv layer (mode 2)
+         + (size_t)EPI * kTcGroupPix * kTcStageStride * 4          // epilogue staging, one tile per epilogue group
+         + (COUT == 128 ? (size_t)EPI * kTcPooledPix * kTcStageStride * 4 : 0)   // pooled maps of the last conv layer (mode 2)
          + 256;                                                    // barriers, tmem slot, alignment
 }
 
 template <int CIN, int COUT, int NSTAGE>
-__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) {
+__global__ void __launch_bounds__(conv_tc_threads(conv_tc_epi_groups(COUT)), 1) conv_tc_kernel(ConvTcParams p) {
     using namespace tc;
+    constexpr int EPI = conv_tc_epi_groups(COUT);          // epilogue groups (4 warps each), channel blocks interleaved between them
+    constexpr int kAWarp = 2 + 4 * EPI;                    // the activation producer is the last warp
     constexpr int NKB = CIN / 32;
     constexpr uint32_t W_STAGE = 6 * COUT * 16;            // wf | wb | wl, each 2 chunks x COUT x 16 B
     constexpr int ACC = (2 * kTcTiles * COUT <= 512) ? 2 : 1;      // accumulator sets in TMEM (conv2: 2 x 192 columns)
@@ -84,9 +90,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
     unsigned char* a_buf = smem;                                   // planes 0-3: hf chunks, 4-7: lb chunks
     unsigned char* w_buf = a_buf + (size_t)8 * plane;
     float* staging = reinterpret_cast<float*>(w_buf + (size_t)NSTAGE * W_STAGE);
-    float* pooled = staging + (size_t)kTcGroupPix * kTcStageStride;   // only present (and used) when COUT == 128
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(staging) + (size_t)kTcGroupPix * kTcStageStride * 4
-                                                 + (COUT == 128 ? (size_t)kTcPooledPix * kTcStageStride * 4 : 0));
+    float* pooled = staging + (size_t)EPI * kTcGroupPix * kTcStageStride;   // only present (and used) when COUT == 128
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(staging) + (size_t)EPI * kTcGroupPix * kTcStageStride * 4
+                                                 + (COUT == 128 ? (size_t)EPI * kTcPooledPix * kTcStageStride * 4 : 0));
     uint64_t* a_full = bars + 0; uint64_t* a_empty = bars + 2; uint64_t* acc_full = bars + 4; uint64_t* acc_empty = bars + 6;
     uint64_t* w_full = bars + 8; uint64_t* w_empty = bars + 8 + NSTAGE;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * NSTAGE);
@@ -94,7 +100,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4 * EPI); }
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1); }
         fence_barrier_init();
     }
@@ -120,7 +126,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
                         bulk_g2s(w_buf + (size_t)st * W_STAGE, p.w + (size_t)(kh * 9 + tap) * (W_STAGE / 2), W_STAGE, w_full + st);
                     }
         }
-    } else if (warp == 6) {
+    } else if (warp == kAWarp) {
         // ===================================================== activation producer (32 lanes issue the copies)
         uint32_t it = 0;
         const uint32_t row_bytes = (uint32_t)seg * 16;
@@ -222,7 +228,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
     } else {
         // ===================================================== epilogue (4 warps = 128 threads)
         const int quarter = warp & 3;                       // the TMEM lanes this warp may read: 32*quarter ..
-        const int et = (warp - 2) * 32 + lane;
+        const int eg = (warp - 2) >> 2;                     // epilogue group: handles channel blocks eg, eg + EPI, ...
+        const int et = ((warp - 2) & 3) * 32 + lane;        // thread index inside the group
+        float* const stage_g = staging + (size_t)eg * kTcGroupPix * kTcStageStride;
+        float* const pooled_g = pooled + (size_t)eg * kTcPooledPix * kTcStageStride;
+        constexpr int kLastCb = COUT / 32 - 1;
         const int Hpool = p.H / 2, Wpool = p.W / 2;
         const int Wp_out = Wpool + 2;
         const long long Pout = (long long)(Hpool + 2) * Wp_out;
@@ -241,28 +251,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
             mbar_wait(acc_full + as, (wi / ACC) & 1);
             e_wait += clock64() - e0;
             fence_after_thread_sync();
-            for (int cb = 0; cb < COUT / 32; ++cb) {
+            for (int cb = eg; cb < COUT / 32; cb += EPI) {
 #pragma unroll
                 for (int g = 0; g < kTcTiles; ++g) {
                     float v[32];
                     tmem_ld32(t_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * COUT + cb * 32), v);
-                    float* dst = staging + (size_t)(g * 128 + quarter * 32 + lane) * kTcStageStride;
+                    float* dst = stage_g + (size_t)(g * 128 + quarter * 32 + lane) * kTcStageStride;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) dst[j] = v[j];
                 }
-                if (cb == COUT / 32 - 1) {                  // TMEM fully drained: the next group's MMAs may start
+                if (cb + EPI > kLastCb) {                   // this group's last block is out of TMEM: (with the others) the next MMAs may start
                     fence_before_thread_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty + as);
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
                 const int n_items = prow * pcol * 4;            // one item = one pooled pixel x 8 channels
                 for (int item = et; item < n_items; item += 128) {
                     const int pxl = item % pcol;
                     const int rest = item / pcol;
                     const int r = rest % prow, ch8 = rest / prow;
                     const int px = colb * (p.cw / 2) + pxl;
-                    const float* s00 = staging + (size_t)(2 * r * seg + 1 + 2 * pxl) * kTcStageStride + ch8 * 8;
+                    const float* s00 = stage_g + (size_t)(2 * r * seg + 1 + 2 * pxl) * kTcStageStride + ch8 * 8;
                     const float* s10 = s00 + (size_t)seg * kTcStageStride;
                     float o[8];
 #pragma unroll
@@ -280,7 +290,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
                         *reinterpret_cast<uint4*>(p.out_hf + (c8 * Pout + pix) * 8) = hf;
                         *reinterpret_cast<uint4*>(p.out_lb + (c8 * Pout + pix) * 8) = lb;
                     } else if (p.out_planes == 2) {
-                        float* dst = pooled + (size_t)(Y * Wpool + px) * kTcStageStride + ch8 * 8;
+                        float* dst = pooled_g + (size_t)(Y * Wpool + px) * kTcStageStride + ch8 * 8;
 #pragma unroll
                         for (int e = 0; e < 8; ++e) dst[e] = o[e];
                     } else {
@@ -292,7 +302,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
                 if (p.out_planes == 2) {
                     // AdaptiveAvgPool2d((4,4)) (cnn_trainer.py:105) of the 32 channels just pooled: thread = (window row i, channel);
                     // same window bounds and summation order as avgpool_planes_kernel, output straight into FC1's operand planes
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
                     const int i = et >> 5, ch = et & 31;
                     const int y0 = (i * Hpool) / 4, y1 = ((i + 1) * Hpool + 3) / 4;
                     float a4[4];
@@ -301,7 +311,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
                         const int x0 = (j * Wpool) / 4, x1 = ((j + 1) * Wpool + 3) / 4;
                         float sum = 0.0f;
                         for (int y = y0; y < y1; ++y)
-                            for (int x = x0; x < x1; ++x) sum += pooled[(size_t)(y * Wpool + x) * kTcStageStride + ch];
+                            for (int x = x0; x < x1; ++x) sum += pooled_g[(size_t)(y * Wpool + x) * kTcStageStride + ch];
                         a4[j] = sum / (float)((y1 - y0) * (x1 - x0));
                     }
                     const long long off = (((long long)((cb * 32 + ch) * 4 + i)) * p.feat_rows + p.clip0 + clip) * 4;
@@ -309,10 +319,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(ConvTcParams p) 
                     *reinterpret_cast<float4*>(p.feat_hi + off) = hi;
                     *reinterpret_cast<float4*>(p.feat_lo + off) = make_float4(a4[0] - hi.x, a4[1] - hi.y, a4[2] - hi.z, a4[3] - hi.w);
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
             }
         }
-        if (p.debug && et == 0) {
+        if (p.debug && et == 0 && eg == 0) {
             long long* d = p.debug + (long long)blockIdx.x * 8;
             d[4] = clock64() - e_total; d[5] = e_wait;
         }

@@ -722,7 +722,7 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
     const int H0 = c->cfg.mel_n_mels, W0 = T;
     const int H1 = H0 / 2, W1 = W0 / 2, H2 = H1 / 2, W2 = W1 / 2, H3 = H2 / 2, W3 = W2 / 2;
     if (H3 < 1 || W3 < 1) return fail("infer: mel image %dx%d too small for three 2x2 pools", H0, W0);
-    const ConvTiling t2 = conv_tc_tiling<64>(H1, W1, 6), t3 = conv_tc_tiling<128>(H2, W2, 4);
+    const ConvTiling t2 = conv_tc_tiling<64>(H1, W1, 6), t3 = conv_tc_tiling<128>(H2, W2, 3);
     if (t2.R < 2 || t3.R < 2 || t2.smem > 227 * 1024 || t3.smem > 227 * 1024)
         return fail("infer: no tensor-core conv tiling for a mel image of %d x %d", H0, W0);
     const size_t smem2 = t2.smem, smem3 = t3.smem;
@@ -751,7 +751,7 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
     float* feat_lo = reinterpret_cast<float*>(c->feat_planes.as<unsigned char>() + feat_bytes);
     const bool fuse_avgpool = t3.groups_per_clip == 1 && H3 * W3 <= kTcPooledPix;
     auto k2 = conv_tc_kernel<32, 64, 6>;
-    auto k3 = conv_tc_kernel<64, 128, 4>;
+    auto k3 = conv_tc_kernel<64, 128, 3>;
     GAT_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     GAT_CUDA(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
     for (long long c0 = 0; c0 < N; c0 += chunk) {
@@ -763,14 +763,14 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
                         c->tc_debug ? c->tc_debug_buf.as<long long>() : nullptr};
         const int work2 = nc * p2.groups_per_clip;
         KNAME("conv2_tc_32_64");
-        LAUNCH(c, k2, (unsigned)(work2 < c->num_sms ? work2 : c->num_sms), kTcThreads, smem2, stream, p2);
+        LAUNCH(c, k2, (unsigned)(work2 < c->num_sms ? work2 : c->num_sms), conv_tc_threads(conv_tc_epi_groups(64)), smem2, stream, p2);
         ConvTcParams p3{act2_hf, act2_lb, c->conv_w_tc[2].as<unsigned short>(), c->conv_w_unscale[2], c->conv_b[2].as<float>(), nc, H2, W2, t3.R,
                         t3.seg, t3.cw, t3.col_blocks, t3.groups_per_clip, fuse_avgpool ? 2 : 0,
                         c->act3.as<float>() + (size_t)c0 * H3 * W3 * 128, nullptr, nullptr, feat_hi, feat_lo, rows_pad, c0, 0.01f,
                         c->tc_debug ? c->tc_debug_buf.as<long long>() + 148 * 8 : nullptr};
         const int work3 = nc * p3.groups_per_clip;
         KNAME("conv3_tc_64_128");
-        LAUNCH(c, k3, (unsigned)(work3 < c->num_sms ? work3 : c->num_sms), kTcThreads, smem3, stream, p3);
+        LAUNCH(c, k3, (unsigned)(work3 < c->num_sms ? work3 : c->num_sms), conv_tc_threads(conv_tc_epi_groups(128)), smem3, stream, p3);
     }
     // head: (adaptive average pool ->) FC1 (tcgen05) -> FC2 + softmax
     if (!fuse_avgpool) {
