@@ -169,8 +169,9 @@ __global__ void __launch_bounds__(conv_tc_threads(conv_tc_epi_groups(COUT)), 1) 
             }
         }
     } else if (warp == 1) {
-        // ===================================================== MMA issuer (single thread)
-        if (lane == 0) {
+        // ===================================================== MMA issuer (the warp runs the loop, one elected lane issues)
+        {
+            const bool leader = elect_one();
             const uint32_t idesc_h = idesc_f16(128, COUT), idesc_b = idesc_bf16(128, COUT);
             // Descriptors differ only in their start address: keep the low words as integers and add offsets.
             // low word = (addr >> 4) | (LBO >> 4) << 16 ; high word = (SBO >> 4) | version 1 at bit 46.
@@ -208,19 +209,22 @@ __global__ void __launch_bounds__(conv_tc_threads(conv_tc_epi_groups(COUT)), 1) 
 #pragma unroll
                             for (int g = 0; g < kTcTiles; ++g) {
                                 const uint32_t d = d_base + (uint32_t)(g * COUT);
-                                mma_16bit(d, desc(a_hf + a_off + g * 128), desc(w_hf), idesc_h, accumulate);   // hf * wf   (FP16)
-                                mma_16bit(d, desc(a_lb + a_off + g * 128), desc(w_hb), idesc_b, 1u);           // lb * wb   (BF16)
-                                mma_16bit(d, desc(a_hf + a_off + g * 128), desc(w_lf), idesc_h, 1u);           // hf * wl   (FP16)
+                                if (leader) {
+                                    mma_16bit(d, desc(a_hf + a_off + g * 128), desc(w_hf), idesc_h, accumulate);   // hf * wf   (FP16)
+                                    mma_16bit(d, desc(a_lb + a_off + g * 128), desc(w_hb), idesc_b, 1u);           // lb * wb   (BF16)
+                                    mma_16bit(d, desc(a_hf + a_off + g * 128), desc(w_lf), idesc_h, 1u);           // hf * wl   (FP16)
+                                }
                             }
                             accumulate = 1;
-                            mma_commit(w_empty + st);       // weights of this stage are free once those MMAs retire
+                            if (leader) mma_commit(w_empty + st);       // weights of this stage are free once those MMAs retire
+                            __syncwarp();
                         }
-                        mma_commit(a_empty + half);         // ... and so is this half of the activation buffer
+                        if (leader) mma_commit(a_empty + half);         // ... and so is this half of the activation buffer
                     }
                 }
-                mma_commit(acc_full + as);                  // accumulators of the group are complete
+                if (leader) mma_commit(acc_full + as);                  // accumulators of the group are complete
             }
-            if (p.debug) {
+            if (p.debug && leader) {
                 long long* d = p.debug + (long long)blockIdx.x * 8;
                 d[0] = clock64() - t_begin; d[1] = t_acc; d[2] = t_a; d[3] = t_w;
             }

@@ -50,6 +50,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// One lane of a converged warp (elect.sync).  Code that issues tcgen05 instructions is written warp-uniformly - all
+// lanes run the control flow and compute the operands - and only the issue itself is guarded by this predicate: with
+// the whole block under `if (lane == 0)` ptxas cannot prove the operands uniform and wraps EVERY MMA in an
+// ELECT / branch loop (seen in the SASS: ~10 extra instructions per UTCHMMA, which bound the N = 64 layer).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- tensor memory
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem, uint32_t ncols) {   // one full warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(ncols) : "memory");
