@@ -105,28 +105,31 @@ __global__ void __launch_bounds__(192, 1) fc_tc_kernel(FcTcParams p) {
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = idesc_tf32(128, NOUT);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const uint32_t st = kb % kFcStages;
-                mbar_wait(full + st, (kb / kFcStages) & 1);
-                fence_after_thread_sync();
-                const uint32_t a_hi = smem_u32(smem) + st * STAGE, a_lo = a_hi + 8 * 2048;
-                const uint32_t w_hi = a_hi + A_STAGE, w_lo = w_hi + 8 * NOUT * 16;
+        // the warp runs the loop, one elected lane issues (see tc::elect_one)
+        const bool leader = elect_one();
+        const uint32_t idesc = idesc_tf32(128, NOUT);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const uint32_t st = kb % kFcStages;
+            mbar_wait(full + st, (kb / kFcStages) & 1);
+            fence_after_thread_sync();
+            const uint32_t a_hi = smem_u32(smem) + st * STAGE, a_lo = a_hi + 8 * 2048;
+            const uint32_t w_hi = a_hi + A_STAGE, w_lo = w_hi + 8 * NOUT * 16;
 #pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    const uint64_t dah = smem_desc_kmajor_noswizzle(a_hi + 2 * s * 2048, 2048, 128);
-                    const uint64_t dal = smem_desc_kmajor_noswizzle(a_lo + 2 * s * 2048, 2048, 128);
-                    const uint64_t dbh = smem_desc_kmajor_noswizzle(w_hi + 2 * s * NOUT * 16, NOUT * 16, 128);
-                    const uint64_t dbl = smem_desc_kmajor_noswizzle(w_lo + 2 * s * NOUT * 16, NOUT * 16, 128);
+            for (int s = 0; s < 4; ++s) {
+                const uint64_t dah = smem_desc_kmajor_noswizzle(a_hi + 2 * s * 2048, 2048, 128);
+                const uint64_t dal = smem_desc_kmajor_noswizzle(a_lo + 2 * s * 2048, 2048, 128);
+                const uint64_t dbh = smem_desc_kmajor_noswizzle(w_hi + 2 * s * NOUT * 16, NOUT * 16, 128);
+                const uint64_t dbl = smem_desc_kmajor_noswizzle(w_lo + 2 * s * NOUT * 16, NOUT * 16, 128);
+                if (leader) {
                     mma_tf32(tmem, dah, dbh, idesc, (kb | s) != 0 ? 1u : 0u);
                     mma_tf32(tmem, dal, dbh, idesc, 1u);
                     mma_tf32(tmem, dah, dbl, idesc, 1u);
                 }
-                mma_commit(empty + st);
             }
-            mma_commit(acc_full);
+            if (leader) mma_commit(empty + st);
+            __syncwarp();
         }
+        if (leader) mma_commit(acc_full);
     } else {
         const int quarter = warp & 3;
         const long long row = row0 + quarter * 32 + lane;
