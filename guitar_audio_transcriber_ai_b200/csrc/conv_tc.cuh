@@ -347,7 +347,7 @@ struct Conv1PlanesParams {
     float slope;
 };
 
-__global__ void __launch_bounds__(256) conv1_pool_planes_kernel(Conv1PlanesParams p) {
+__global__ void __launch_bounds__(256, 4) conv1_pool_planes_kernel(Conv1PlanesParams p) {
     __shared__ __align__(16) float ws[9 * 32];
     __shared__ float bs[32];
     for (int i = threadIdx.x; i < 9 * 32; i += blockDim.x) ws[i] = p.w[i];
