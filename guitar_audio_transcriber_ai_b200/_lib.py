@@ -21,6 +21,11 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 GAT_FLAG_YIN_ON_NORMALIZED = 1
 GAT_FLAG_APPLY_SCALER = 2
 GAT_FLAG_SKIP_MLP = 4
+GAT_FLAG_NO_PITCH = 8
+GAT_FLAG_NO_NORMALIZE_MFCC = 16
+GAT_FLAG_NO_NORMALIZE_MEL = 32
+GAT_MEL_NORMALIZE = 1
+GAT_MEL_POWER = 2
 
 
 class GatConfig(C.Structure):
@@ -61,6 +66,8 @@ _PROTOTYPES = {
     "gat_infer": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int64, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gat_segment": (C.c_int, [_P, _P, C.c_int64, C.POINTER(GatSlicerParams), C.c_int32, _P, _P, _P, _P, _P, _P, _P,
                               _P, _P, _P]),
+    "gat_segment_batch": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.POINTER(GatSlicerParams), C.c_int32, _P, _P, _P, C.c_int64,
+                                    _P, _P, _P]),
     "gat_transcribe_clips": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gat_transcribe_clips_host": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int32, _P, _P, _P]),
     "gat_transcribe_clips_host_pcm16": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int32, _P, _P, _P]),

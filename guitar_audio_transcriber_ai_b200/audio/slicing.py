@@ -42,11 +42,11 @@ class AudioSlicer:
     @staticmethod
     def save_clip(clip, sr, out_dir, idx, onset_s, audio_name="clip"):
         """slicing.py:139-144: ``NNNN_<name>__<onset>s.wav``, PCM_16 as soundfile writes .wav files
-        (rint(x * 32767), libsndfile's normalised float -> short conversion)."""
+        (libsndfile's clipping float -> short conversion, ``wavio.float_to_pcm16``)."""
         out_dir = Path(out_dir)
         out_dir.mkdir(parents=True, exist_ok=True)
         x = clip.detach().cpu().numpy() if torch.is_tensor(clip) else np.asarray(clip, dtype=np.float32)
-        q = np.clip(np.rint(x.astype(np.float32) * np.float32(32767.0)), -32768, 32767).astype(np.int16)
+        q = wavio.float_to_pcm16(x)
         wavio.write_wav_pcm16(out_dir / f"{idx:04d}_{audio_name}__{onset_s:.3f}s.wav", q, sr)
 
     def sliceNsave(self, audio_path, out_dir, target_sr=TARGET_SR, hop_len=SLICER_CONFIG.HOP_LEN, length_sec=CLIP_DURATION,

@@ -68,6 +68,19 @@ def read_wav_frames(path) -> tuple[np.ndarray, int]:
     return np.ascontiguousarray(out), int(rate)
 
 
+def float_to_pcm16(x) -> np.ndarray:
+    """What ``soundfile.write`` stores for float32 samples in a PCM_16 file.  python-soundfile enables
+    SFC_SET_CLIPPING on every file, so libsndfile runs its clipping converter (src/pcm.c f2les_clip_array):
+    ``scaled = x * 2^31`` in float32; ``>= 2^31 - 1`` -> 0x7FFF; ``<= -2^31`` -> -0x8000; else
+    ``lrintf(scaled) >> 16`` (a floor to the 16-bit grid, not a round).  Same arithmetic as
+    ``pcm16_quantize`` in csrc/frontend.cuh."""
+    s = np.asarray(x, dtype=np.float32) * np.float32(2147483648.0)
+    with np.errstate(invalid="ignore"):
+        q = np.rint(np.clip(s, -2147483648.0, 2147483520.0)).astype(np.int64) >> 16
+    q = np.where(s >= np.float32(2147483648.0), 32767, np.where(s <= np.float32(-2147483648.0), -32768, q))
+    return q.astype(np.int16)
+
+
 def write_wav_pcm16(path, samples_i16: np.ndarray, sample_rate: int) -> None:
     """Mono or interleaved int16 samples -> canonical 44-byte-header WAV (what sf.write produces for .wav)."""
     a = np.ascontiguousarray(samples_i16, dtype="<i2")

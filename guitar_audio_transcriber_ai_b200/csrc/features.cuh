@@ -47,7 +47,8 @@ struct StftMelParams {
     long long n;               // samples per clip
     int N;                     // clips
     const float* clip_scale;   // [N] divisor c = rms + 1e-9, or nullptr (no volume normalisation)
-    const unsigned char* frame_gate;  // onset chain: per 512-sample block keep flag, or nullptr
+    const unsigned char* frame_gate;  // onset chain: per 512-sample block keep flag [N][gate_stride], or nullptr
+    long long gate_stride;     // frame_gate entries per clip
     float sample_gate;         // onset chain: samples with |y| < sample_gate are zeroed; 0 disables both gates
     int gate_hop;              // samples per frame_gate entry (512)
     int use_async;             // 1: prefetch the next chunk's samples with cp.async into a raw landing zone
@@ -62,6 +63,7 @@ struct StftMelParams {
     int frames_per_cta;
     int chunks_per_clip;
     T amin;                    // 1e-10
+    int power_out;             // 1: write the mel POWER (MelSpecConfig.TO_DB = False, features.py:313-316), no log
     // kOutImage: out[(clip*n_mels + m)*T + t] = 10 log10(max(amin, mel))
     // kOutSpec : out[(clip*T + t)*n_mels + m] = same, plus per-clip running max in spec_max (ordered ints)
     T* out;
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(kThreads, 1) stft_mel_kernel(StftMelParams<T> 
                 if (p.clip_scale) v = __fdiv_rn(v, c);
                 if (kGates && p.sample_gate > 0.0f && inside) {
                     if (!(fabsf(v) >= p.sample_gate)) v = 0.0f;
-                    if (p.frame_gate && !p.frame_gate[s / p.gate_hop]) v = 0.0f;
+                    if (p.frame_gate && !p.frame_gate[(long long)clip * p.gate_stride + s / p.gate_hop]) v = 0.0f;
                 }
                 span[i] = (T)v;
             }
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, 1) stft_mel_kernel(StftMelParams<T> 
                         acc += pv.w * (T)wv.w;
                     }
                     if (m >= 0) {
-                        const T db = db10(acc > p.amin ? acc : p.amin);
+                        const T db = p.power_out ? acc : db10(acc > p.amin ? acc : p.amin);
                         if (kOut == kOutImage) {
                             tile[m * (FC + 1) + f] = db;
                         } else {

@@ -13,16 +13,22 @@
 
 namespace gat {
 
-// libsndfile, float -> PCM_16 -> float (normalised I/O): write scales by 0x7FFF and rounds to nearest even
-// (lrintf), read scales by 1/0x8000.  Samples outside [-1, 1] are clipped (libsndfile would wrap unless
-// SFC_SET_CLIPPING is on; a wrapped sample is never what a caller wants).
+// soundfile.write(float32 -> PCM_16 .wav) followed by a float32 read.  python-soundfile switches SFC_SET_CLIPPING
+// on for every file it opens, so libsndfile converts with its CLIPPING routine (src/pcm.c f2les_clip_array,
+// normalised input): scaled = x * 2^31 in float, >= 2^31 - 1 -> 0x7FFF, <= -2^31 -> 0x8000, otherwise
+// lrintf(scaled) >> 16 - i.e. floor(x * 32768) up to the rounding at 2^-16 of a step, NOT rint(x * 32767).
+// The read scales by 1 / 0x8000.
+__device__ __forceinline__ int pcm16_quantize(float x) {
+    const float s = x * 2147483648.0f;
+    if (s >= 2147483648.0f) return 32767;        // the largest float below 2^31 is 2^31 - 128: same test as >= 2^31 - 1
+    if (s <= -2147483648.0f) return -32768;
+    return __float2int_rn(s) >> 16;
+}
+
 __global__ void pcm16_roundtrip_kernel(float* __restrict__ x, long long count) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
-        float q = rintf(x[i] * 32767.0f);
-        q = fminf(fmaxf(q, -32768.0f), 32767.0f);
-        x[i] = q * (1.0f / 32768.0f);
-    }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+        x[i] = (float)pcm16_quantize(x[i]) * (1.0f / 32768.0f);
 }
 
 // Interleaved PCM_16 frames -> mono float32: x / 32768 per channel (libsndfile read), then the float32 channel

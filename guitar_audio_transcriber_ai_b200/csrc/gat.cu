@@ -138,7 +138,7 @@ int build_sparse_fb(SparseFbDev& out, const float* dense, int n_mels, int n_freq
 struct ProfRec { const char* name; cudaEvent_t e0, e1; };
 
 // kernels launched through a function pointer are reported under a readable name
-static const char* g_kernel_alias = nullptr;
+static thread_local const char* g_kernel_alias = nullptr;   // per thread: contexts on different threads must not rename each other's launches
 static inline const char* kernel_name(const char* expr) {
     const char* n = g_kernel_alias ? g_kernel_alias : expr;
     g_kernel_alias = nullptr;
@@ -172,7 +172,7 @@ struct gat_ctx {
     DevBuf clip_scale, spec, spec_max, f0, act1, act2, act3, hz_tmp, logits_cnn, logits_mlp;
     long long act_shape[3] = {0, 0, 0};   // (chunk, H, W) the zero borders of act1/act2 were prepared for
     DevBuf seg_small, seg_rms, seg_rms_med, seg_gate, seg_env, seg_envn, seg_cand, seg_peaks, seg_frames, seg_table,
-           seg_keep, seg_dest;
+           seg_keep, seg_dest, seg_base, seg_counts;
     // end-to-end staging
     DevBuf e2e_audio[2], e2e_pcm[2], e2e_mel, e2e_mfcc, e2e_probs, e2e_mlp_probs, e2e_cnn_probs, e2e_index, e2e_conf;
     cudaStream_t e2e_stream[2] = {nullptr, nullptr};
@@ -372,7 +372,7 @@ extern "C" void gat_ctx_destroy(gat_ctx* c) {
                      &c->fc1_w, &c->fc1_b, &c->fc2_w, &c->fc2_b, &c->scaler_mean, &c->scaler_scale,
                      &c->clip_scale, &c->spec, &c->spec_max, &c->f0, &c->act1, &c->act2, &c->act3, &c->hz_tmp, &c->logits_cnn, &c->logits_mlp,
                      &c->seg_small, &c->seg_rms, &c->seg_rms_med, &c->seg_gate, &c->seg_env, &c->seg_envn, &c->seg_cand,
-                     &c->seg_peaks, &c->seg_frames, &c->seg_table, &c->seg_keep, &c->seg_dest,
+                     &c->seg_peaks, &c->seg_frames, &c->seg_table, &c->seg_keep, &c->seg_dest, &c->seg_base, &c->seg_counts,
                      &c->e2e_audio[0], &c->e2e_audio[1], &c->e2e_pcm[0], &c->e2e_pcm[1], &c->e2e_mel, &c->e2e_mfcc, &c->e2e_probs, &c->e2e_mlp_probs,
                      &c->e2e_cnn_probs, &c->e2e_index, &c->e2e_conf};
     for (DevBuf* b : all) b->release();
@@ -520,7 +520,8 @@ int launch_stft_mel(gat_ctx* c, StftMelParams<T> p, void* stream) {
     return 0;
 }
 
-int run_melspec(gat_ctx* c, const float* audio, int64_t N, int64_t n, bool normalize, bool scale_ready, float* out, void* stream) {
+int run_melspec(gat_ctx* c, const float* audio, int64_t N, int64_t n, bool normalize, bool scale_ready, float* out, void* stream,
+                bool power_out = false) {
     const int n_fft = c->cfg.mel_n_fft;
     if (n <= n_fft / 2) return fail("melspec: clips of %lld samples are too short for reflect padding of %d", (long long)n, n_fft / 2);
     if (normalize && !scale_ready && launch_clip_scale(c, audio, N, n, stream)) return 1;
@@ -530,7 +531,7 @@ int run_melspec(gat_ctx* c, const float* audio, int64_t N, int64_t n, bool norma
     p.hop = c->cfg.mel_hop; p.n_frames = (int)(1 + n / c->cfg.mel_hop); p.pad_mode = kPadReflect;
     p.window = c->win_mel.as<float>(); p.window_half = c->win_mel_half.as<float>();
     p.tw = c->tw_mel.as<Cpx<float>>(); p.w2 = c->w2_mel.as<Cpx<float>>();
-    p.fb = c->fb_mel.view(); p.amin = 1e-10f; p.out = out; p.spec_max = nullptr;
+    p.fb = c->fb_mel.view(); p.amin = 1e-10f; p.out = out; p.spec_max = nullptr; p.power_out = power_out ? 1 : 0;
     switch (n_fft) {     // MelSpecConfig.N_FFT is configurable (features.py:296-302; BASELINE config 5 sweeps it)
         case 512:  return launch_stft_mel<float, kOutImage, 512, 8>(c, p, stream);
         case 1024: return launch_stft_mel<float, kOutImage, 512, 16>(c, p, stream);
@@ -610,7 +611,7 @@ int run_yin(gat_ctx* c, const float* audio, int64_t N, int64_t n, bool normalize
 extern "C" int gat_melspec_db(gat_ctx* c, const float* audio, int64_t N, int64_t n, int32_t normalize, float* out, void* stream) {
     if (!c || !audio || !out) return fail("gat_melspec_db: null argument");
     if (N <= 0) return 0;
-    return run_melspec(c, audio, N, n, normalize != 0, false, out, stream);
+    return run_melspec(c, audio, N, n, (normalize & GAT_MEL_NORMALIZE) != 0, false, out, stream, (normalize & GAT_MEL_POWER) != 0);
 }
 
 extern "C" int gat_mfcc_features(gat_ctx* c, const float* audio, int64_t N, int64_t n, int32_t normalize, int32_t add_pitch,
@@ -644,43 +645,7 @@ extern "C" int gat_yin(gat_ctx* c, const float* audio, int64_t N, int64_t n, int
 namespace {
 
 #ifdef GAT_CPU_EMU
-// Host-emulation stand-in (tests/emu only): the tcgen05 kernels cannot be emulated, so the emulation build
-// keeps a plain CUDA-core formulation of the same layers to exercise everything around them.
-constexpr int kCnnChunk = 256;
-
-int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, float* cnn_logits, void* stream) {
-    if (!c->cnn_loaded) return fail("infer: no CNN loaded (gat_load_cnn)");
-    const int H0 = c->cfg.mel_n_mels, W0 = T;
-    const int H1 = H0 / 2, W1 = W0 / 2, H2 = H1 / 2, W2 = W1 / 2, H3 = H2 / 2, W3 = W2 / 2;
-    if (H3 < 1 || W3 < 1) return fail("infer: mel image %dx%d too small for three 2x2 pools", H0, W0);
-    const long long chunk = N < kCnnChunk ? N : kCnnChunk;
-    const size_t a1 = (size_t)chunk * (H1 + 2) * (W1 + 2) * 32, a2 = (size_t)chunk * (H2 + 2) * (W2 + 2) * 64,
-                 a3 = (size_t)N * H3 * W3 * 128;
-    const bool fresh = c->act1.cap < a1 * 4 || c->act2.cap < a2 * 4 || c->act_shape[0] != chunk || c->act_shape[1] != H0 || c->act_shape[2] != W0;
-    if (c->act1.ensure(a1 * 4) || c->act2.ensure(a2 * 4) || c->act3.ensure(a3 * 4)) return 1;
-    if (fresh) {
-        GAT_CUDA(cudaMemsetAsync(c->act1.p, 0, a1 * 4, (cudaStream_t)stream));
-        GAT_CUDA(cudaMemsetAsync(c->act2.p, 0, a2 * 4, (cudaStream_t)stream));
-        c->act_shape[0] = chunk; c->act_shape[1] = H0; c->act_shape[2] = W0;
-    }
-    const size_t head_smem = ((size_t)128 * 16 * kHeadClips + (size_t)c->hidden * kHeadClips + kHeadClips * 64) * sizeof(float) + 64;
-    for (long long c0 = 0; c0 < N; c0 += chunk) {
-        const int nc = (int)(N - c0 < chunk ? N - c0 : chunk);
-        Conv1Params p1{mel + c0 * H0 * W0, nc, H0, W0, c->conv_w[0].as<float>(), c->conv_b[0].as<float>(), c->act1.as<float>(), 32, 0.01f};
-        LAUNCH(c, conv1_pool_kernel, (unsigned)(nc * ceil_div(H1 * W1, 256)), 256, 0, stream, p1);
-        ConvParams p2{c->act1.as<float>(), nc, H1, W1, c->conv_w[1].as<float>(), c->conv_b[1].as<float>(), c->act2.as<float>(), 1, 0.01f};
-        auto k2 = conv3x3_pool_kernel<32, 64>;
-        LAUNCH(c, k2, (unsigned)(nc * ceil_div(H2 * W2, 32)), 256, 0, stream, p2);
-        ConvParams p3{c->act2.as<float>(), nc, H2, W2, c->conv_w[2].as<float>(), c->conv_b[2].as<float>(),
-                      c->act3.as<float>() + (size_t)c0 * H3 * W3 * 128, 0, 0.01f};
-        auto k3 = conv3x3_pool_kernel<64, 128>;
-        LAUNCH(c, k3, (unsigned)(nc * ceil_div(H3 * W3, 16)), 256, 0, stream, p3);
-    }
-    HeadParams ph{c->act3.as<float>(), (int)N, H3, W3, 128, c->fc1_w.as<float>(), c->fc1_b.as<float>(), c->hidden,
-                  c->fc2_w.as<float>(), c->fc2_b.as<float>(), c->classes, 0.01f, cnn_logits, cnn_probs};
-    LAUNCH(c, cnn_head_kernel, (unsigned)ceil_div((int)N, kHeadClips), 256, head_smem, stream, ph);
-    return 0;
-}
+#include "emu_run_cnn.inc"   // tests/emu: CUDA-core stand-in for the tensor-core CNN (host-emulation build only)
 #else
 // conv1 on CUDA cores (C_in = 1), conv2/conv3 as tcgen05 implicit GEMMs (csrc/conv_tc.cuh), head once per batch.
 // Clips go through the convs in passes of conv_pass_mult * num_sms (default 16 x 148 = 2368): act1 + act2 are hf / lb
@@ -893,36 +858,40 @@ extern "C" int gat_resample(gat_ctx* c, const float* in, int64_t N, int64_t n_in
 // ------------------------------------------------------------------------------------------------- segmentation
 namespace {
 
-// Scalars shared by the segmentation kernels, in seg_small: spec max (8 B) | env min, max (16 B) | n_peaks |
-// any_nonzero | gate value.
+// Per-signal scalars shared by the segmentation kernels, in seg_small: spec max [P] (8 B) | env min, max [P][2] (16 B) |
+// n_peaks [P] | any_nonzero [P] | gate value [P].
 struct SegScalars { long long* spec_max; long long* env_minmax; int* n_peaks; int* any_nonzero; float* gate_val; };
 
-int seg_scalars(gat_ctx* c, cudaStream_t st, SegScalars* s) {
-    if (c->seg_small.ensure(64)) return 1;
+int seg_scalars(gat_ctx* c, int64_t P, cudaStream_t st, SegScalars* s) {
+    if (c->seg_small.ensure((size_t)P * 36 + 64)) return 1;
     unsigned char* small = c->seg_small.as<unsigned char>();
     s->spec_max = reinterpret_cast<long long*>(small);
-    s->env_minmax = reinterpret_cast<long long*>(small + 8);
-    s->n_peaks = reinterpret_cast<int*>(small + 24);
-    s->any_nonzero = reinterpret_cast<int*>(small + 28);
-    s->gate_val = reinterpret_cast<float*>(small + 32);
-    GAT_CUDA(cudaMemsetAsync(small, 0x80, 24, st));
-    GAT_CUDA(cudaMemsetAsync(small + 24, 0, 40, st));
+    s->env_minmax = reinterpret_cast<long long*>(small + (size_t)P * 8);
+    s->n_peaks = reinterpret_cast<int*>(small + (size_t)P * 24);
+    s->any_nonzero = reinterpret_cast<int*>(small + (size_t)P * 28);
+    s->gate_val = reinterpret_cast<float*>(small + (size_t)P * 32);
+    GAT_CUDA(cudaMemsetAsync(small, 0x80, (size_t)P * 24, st));
+    GAT_CUDA(cudaMemsetAsync(small + (size_t)P * 24, 0, (size_t)P * 12, st));
     return 0;
 }
 
-// AudioSlicer.detect_onsets (slicing.py:106-122) on y[L]: float64 STFT -> Slaney mel-128 -> dB -> flux envelope ->
-// normalise, pick peaks -> backtrack -> frames * hop -> greedy minimum separation.  `gated` applies the sample
-// gate and the frame gate (seg_gate) of sliceNsave while the samples are staged.  Also fills the slice table.
-int onset_chain(gat_ctx* c, const float* y, int64_t L, const gat_slicer_params* sp, bool gated, const SegScalars& sc,
+// AudioSlicer.detect_onsets (slicing.py:106-122) on P signals y[P][L]: float64 STFT -> Slaney mel-128 -> dB -> flux
+// envelope -> normalise, pick peaks -> backtrack -> frames * hop -> greedy minimum separation.  `gated` applies the
+// sample gate and the frame gate (seg_gate) of sliceNsave while the samples are staged.  Also fills the slice table.
+// Per-signal outputs: onsets[P][max_onsets], n_onsets[P].
+int onset_chain(gat_ctx* c, const float* y, int64_t P, int64_t L, const gat_slicer_params* sp, bool gated, const SegScalars& sc,
                 int32_t max_onsets, int64_t* onsets, int32_t* n_onsets, double* env_out, int64_t* frames_out,
                 int32_t* n_frames_out, cudaStream_t st) {
-    const int To = (int)(1 + L / sp->onset_hop);      // onset frames
-    if (c->spec.ensure((size_t)To * 128 * sizeof(double)) || c->seg_env.ensure((size_t)To * 8) || c->seg_envn.ensure((size_t)To * 8) ||
-        c->seg_cand.ensure((size_t)(To / 32 + 2) * 4) || c->seg_peaks.ensure((size_t)To * 4) || c->seg_frames.ensure((size_t)To * 8) ||
-        c->seg_table.ensure((size_t)max_onsets * 3 * 8)) return 1;
+    const int To = (int)(1 + L / sp->onset_hop);      // onset frames per signal
+    const int words = To / 32 + 2;
+    const size_t PT = (size_t)P * To;
+    if (c->spec.ensure(PT * 128 * sizeof(double)) || c->seg_env.ensure(PT * 8) || c->seg_envn.ensure(PT * 8) ||
+        c->seg_cand.ensure((size_t)P * words * 4) || c->seg_peaks.ensure(PT * 4) || c->seg_frames.ensure(PT * 8) ||
+        c->seg_table.ensure((size_t)P * max_onsets * 3 * 8)) return 1;
     StftMelParams<double> p{};
-    p.audio = y; p.n = L; p.N = 1; p.clip_scale = nullptr;
+    p.audio = y; p.n = L; p.N = (int)P; p.clip_scale = nullptr;
     p.frame_gate = gated ? c->seg_gate.as<unsigned char>() : nullptr;
+    p.gate_stride = 1 + L / sp->rms_hop;
     p.sample_gate = gated ? sp->sample_gate : 0.0f; p.gate_hop = sp->rms_hop;
     p.hop = sp->onset_hop; p.n_frames = To; p.pad_mode = kPadZero;
     p.window = c->win64.as<double>(); p.tw = c->tw64.as<Cpx<double>>(); p.w2 = c->w2_64.as<Cpx<double>>();
@@ -930,25 +899,63 @@ int onset_chain(gat_ctx* c, const float* y, int64_t L, const gat_slicer_params* 
     if (launch_stft_mel<double, kOutSpec, 192, 32>(c, p, st)) return 1;
 
     // flux envelope -> normalise + candidate peaks -> sequential wait rule
+    const dim3 frames_grid((unsigned)ceil_div(To, 128), (unsigned)P);
     FluxParams fp{c->spec.as<double>(), sc.spec_max, To, 128, 1 + 2048 / (2 * sp->onset_hop), 80.0, c->seg_env.as<double>(), sc.env_minmax};
-    LAUNCH(c, onset_flux_kernel, (unsigned)ceil_div(To, 128), 128, 0, st, fp);
+    LAUNCH(c, onset_flux_kernel, frames_grid, 128, 0, st, fp);
     PeakParams pp{c->seg_env.as<double>(), sc.env_minmax, To, sp->pre_max, sp->post_max, sp->pre_avg, sp->post_avg, sp->wait,
-                  (double)sp->delta, c->seg_envn.as<double>(), c->seg_cand.as<unsigned>(), sc.n_peaks, c->seg_peaks.as<int>(), sc.any_nonzero};
-    LAUNCH(c, peak_candidates_kernel, (unsigned)ceil_div(To, 128), 128, 0, st, pp);
-    LAUNCH(c, peak_select_kernel, 1, 32, 0, st, pp);
-    if (env_out) GAT_CUDA(cudaMemcpyAsync(env_out, c->seg_envn.p, (size_t)To * 8, cudaMemcpyDeviceToDevice, st));
+                  (double)sp->delta, c->seg_envn.as<double>(), c->seg_cand.as<unsigned>(), sc.n_peaks, c->seg_peaks.as<int>(), sc.any_nonzero, words};
+    LAUNCH(c, peak_candidates_kernel, frames_grid, 128, 0, st, pp);
+    LAUNCH(c, peak_select_kernel, (unsigned)P, 32, 0, st, pp);
+    if (env_out) GAT_CUDA(cudaMemcpyAsync(env_out, c->seg_envn.p, PT * 8, cudaMemcpyDeviceToDevice, st));
 
     // backtrack, min separation, slice table
     SliceParams s{c->seg_envn.as<double>(), To, sc.n_peaks, c->seg_peaks.as<int>(), sp->onset_hop, (long long)L,
                   (long long)sp->min_sep_samples, (long long)sp->attack_skip, (long long)sp->clip_len, max_onsets,
                   n_onsets, (long long*)onsets, c->seg_frames.as<long long>(), c->seg_table.as<long long>()};
-    LAUNCH(c, backtrack_kernel, (unsigned)ceil_div(To, 128), 128, 0, st, s);
-    LAUNCH(c, minsep_table_kernel, 1, 1024, 0, st, s);
-    if (frames_out && n_frames_out) {
+    LAUNCH(c, backtrack_kernel, frames_grid, 128, 0, st, s);
+    LAUNCH(c, minsep_table_kernel, (unsigned)P, 1024, 0, st, s);
+    if (frames_out && n_frames_out) {      // diagnostics of the single-signal entry point
         const size_t nb = (size_t)(max_onsets < To ? max_onsets : To) * 8;
         GAT_CUDA(cudaMemcpyAsync(frames_out, c->seg_frames.p, nb, cudaMemcpyDeviceToDevice, st));
         GAT_CUDA(cudaMemcpyAsync(n_frames_out, sc.n_peaks, 4, cudaMemcpyDeviceToDevice, st));
     }
+    return 0;
+}
+
+// AudioSlicer.sliceNsave minus file I/O for P signals of L samples: gates -> onsets -> slice table -> loudness test ->
+// one compacted clip list in (signal, onset) order.  gat_segment is P = 1 with 3-column table rows.
+int segment_impl(gat_ctx* c, const float* y, int64_t P, int64_t L, const gat_slicer_params* sp, int32_t max_onsets,
+                 int64_t* onsets, int32_t* n_onsets, float* clips, int64_t max_clips, int64_t* clip_table, int table_cols,
+                 int32_t* n_clips /* [P + 1] */, float* rms_db_out, double* env_out, int64_t* frames_out, int32_t* n_frames_out,
+                 cudaStream_t st) {
+    const int T = (int)(1 + L / sp->rms_hop);         // rms frames per signal
+    const size_t PT = (size_t)P * T;
+    if (c->seg_rms.ensure(PT * 4) || c->seg_rms_med.ensure(PT * 4) || c->seg_gate.ensure(PT) ||
+        c->seg_keep.ensure((size_t)P * max_onsets) || c->seg_dest.ensure((size_t)P * max_onsets * 4) ||
+        c->seg_base.ensure((size_t)P * 8)) return 1;
+    SegScalars sc{};
+    if (seg_scalars(c, P, st, &sc)) return 1;
+
+    // 1-3: sample gate (fused into the loads) -> frame RMS dB -> median-5 -> p20 + 6 dB frame gate
+    RmsParams rp{y, (long long)L, T, sp->rms_hop, sp->sample_gate, c->seg_rms.as<float>()};
+    LAUNCH(c, rms_db_kernel, dim3((unsigned)ceil_div(T, 128), (unsigned)P), 128, 0, st, rp);
+    LAUNCH(c, median5_kernel, dim3((unsigned)ceil_div(T, 256), (unsigned)P), 256, 0, st, c->seg_rms.as<float>(), c->seg_rms_med.as<float>(), T);
+    GateParams gp{c->seg_rms_med.as<float>(), T, sp->p20_k, sp->p20_gamma, sp->gate_offset_db, c->seg_gate.as<unsigned char>(), sc.gate_val};
+    LAUNCH(c, rms_gate_kernel, (unsigned)P, T >= 4096 ? 1024 : 256, 0, st, gp);
+    if (rms_db_out) GAT_CUDA(cudaMemcpyAsync(rms_db_out, c->seg_rms_med.p, PT * 4, cudaMemcpyDeviceToDevice, st));
+
+    // 4-9: onsets of the doubly gated signals
+    if (onset_chain(c, y, P, L, sp, true, sc, max_onsets, onsets, n_onsets, env_out, frames_out, n_frames_out, st)) return 1;
+
+    // 10-11: loudness test, compaction, gather
+    GatherParams g{y, (long long)L, n_onsets, c->seg_table.as<long long>(), (long long)sp->clip_len, sp->min_slice_rms_db,
+                   c->seg_keep.as<unsigned char>(), c->seg_dest.as<int>(), n_clips, c->seg_base.as<long long>(), clips,
+                   (long long*)clip_table, max_onsets, table_cols, (long long)max_clips, (int)P};
+    const dim3 onsets_grid((unsigned)max_onsets, (unsigned)P);
+    LAUNCH(c, slice_loudness_kernel, onsets_grid, 256, 0, st, g);
+    LAUNCH(c, slice_compact_kernel, (unsigned)P, max_onsets > 256 ? 1024 : 256, 0, st, g);
+    LAUNCH(c, slice_base_kernel, 1, 1024, 0, st, g);
+    LAUNCH(c, slice_gather_kernel, onsets_grid, 256, 0, st, g);
     return 0;
 }
 
@@ -962,8 +969,8 @@ extern "C" int gat_detect_onsets(gat_ctx* c, const float* y, int64_t L, const ga
     if (sp->onset_hop < 2 || (sp->onset_hop & 1) || sp->onset_hop > 2048) return fail("gat_detect_onsets: hop %d unsupported (even, 2..2048)", sp->onset_hop);
     cudaStream_t st = (cudaStream_t)stream;
     SegScalars sc{};
-    if (seg_scalars(c, st, &sc)) return 1;
-    return onset_chain(c, y, L, sp, false, sc, max_onsets, onsets, n_onsets, nullptr, nullptr, nullptr, st);
+    if (seg_scalars(c, 1, st, &sc)) return 1;
+    return onset_chain(c, y, 1, L, sp, false, sc, max_onsets, onsets, n_onsets, nullptr, nullptr, nullptr, st);
 }
 
 extern "C" int gat_segment(gat_ctx* c, const float* y, int64_t L, const gat_slicer_params* sp, int32_t max_onsets,
@@ -974,30 +981,24 @@ extern "C" int gat_segment(gat_ctx* c, const float* y, int64_t L, const gat_slic
     if (max_onsets < 1) return fail("gat_segment: max_onsets must be positive");
     if (sp->rms_hop < 1 || sp->onset_hop != 512) return fail("gat_segment: onset hop %d unsupported (the reference always uses 512)", sp->onset_hop);
     cudaStream_t st = (cudaStream_t)stream;
-    const int T = (int)(1 + L / sp->rms_hop);         // rms frames
-    if (c->seg_rms.ensure((size_t)T * 4) || c->seg_rms_med.ensure((size_t)T * 4) || c->seg_gate.ensure((size_t)T) ||
-        c->seg_keep.ensure((size_t)max_onsets) || c->seg_dest.ensure((size_t)max_onsets * 4)) return 1;
-    SegScalars sc{};
-    if (seg_scalars(c, st, &sc)) return 1;
-
-    // 1-3: sample gate (fused into the loads) -> frame RMS dB -> median-5 -> p20 + 6 dB frame gate
-    RmsParams rp{y, (long long)L, T, sp->rms_hop, sp->sample_gate, c->seg_rms.as<float>()};
-    LAUNCH(c, rms_db_kernel, (unsigned)ceil_div(T, 128), 128, 0, st, rp);
-    LAUNCH(c, median5_kernel, (unsigned)ceil_div(T, 256), 256, 0, st, c->seg_rms.as<float>(), c->seg_rms_med.as<float>(), T);
-    GateParams gp{c->seg_rms_med.as<float>(), T, sp->p20_k, sp->p20_gamma, sp->gate_offset_db, c->seg_gate.as<unsigned char>(), sc.gate_val};
-    LAUNCH(c, rms_gate_kernel, 1, 1024, 0, st, gp);
-    if (rms_db_out) GAT_CUDA(cudaMemcpyAsync(rms_db_out, c->seg_rms_med.p, (size_t)T * 4, cudaMemcpyDeviceToDevice, st));
-
-    // 4-9: onsets of the doubly gated signal
-    if (onset_chain(c, y, L, sp, true, sc, max_onsets, onsets, n_onsets, env_out, frames_out, n_frames_out, st)) return 1;
-
-    // 10-11: loudness test, compaction, gather
-    GatherParams g{y, (long long)L, n_onsets, c->seg_table.as<long long>(), (long long)sp->clip_len, sp->min_slice_rms_db,
-                   c->seg_keep.as<unsigned char>(), c->seg_dest.as<int>(), n_clips, clips, (long long*)clip_table, max_onsets};
-    LAUNCH(c, slice_loudness_kernel, (unsigned)max_onsets, 256, 0, st, g);
-    LAUNCH(c, slice_compact_kernel, 1, 1024, 0, st, g);
-    LAUNCH(c, slice_gather_kernel, (unsigned)max_onsets, 256, 0, st, g);
+    if (c->seg_counts.ensure(8)) return 1;     // [kept clips of the signal, total]: the caller's n_clips is one int
+    if (segment_impl(c, y, 1, L, sp, max_onsets, onsets, n_onsets, clips, max_onsets, clip_table, 3, c->seg_counts.as<int32_t>(),
+                     rms_db_out, env_out, frames_out, n_frames_out, st)) return 1;
+    GAT_CUDA(cudaMemcpyAsync(n_clips, c->seg_counts.p, 4, cudaMemcpyDeviceToDevice, st));
     return 0;
+}
+
+extern "C" int gat_segment_batch(gat_ctx* c, const float* y, int64_t P, int64_t L, const gat_slicer_params* sp, int32_t max_onsets,
+                                 int64_t* onsets, int32_t* n_onsets, float* clips, int64_t max_clips, int64_t* clip_table,
+                                 int32_t* n_clips, void* stream) {
+    if (!c || !y || !sp || !onsets || !n_onsets || !clips || !clip_table || !n_clips) return fail("gat_segment_batch: null argument");
+    if (P < 1) return 0;
+    if (P > 65535) return fail("gat_segment_batch: at most 65535 signals per call (got %lld)", (long long)P);
+    if (L <= 1024) return fail("gat_segment_batch: signals of %lld samples are too short (reflect padding needs > 1024)", (long long)L);
+    if (max_onsets < 1 || max_onsets > 65535 || max_clips < 1) return fail("gat_segment_batch: max_onsets / max_clips out of range");
+    if (sp->rms_hop < 1 || sp->onset_hop != 512) return fail("gat_segment_batch: onset hop %d unsupported (the reference always uses 512)", sp->onset_hop);
+    return segment_impl(c, y, P, L, sp, max_onsets, onsets, n_onsets, clips, max_clips, clip_table, 4, n_clips,
+                        nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------- end to end
@@ -1007,19 +1008,32 @@ extern "C" int gat_transcribe_clips(gat_ctx* c, const float* audio, int64_t N, i
     if (!c || !audio || !probs || !index || !conf) return fail("gat_transcribe_clips: null argument");
     if (N <= 0) return 0;
     const bool skip_mlp = (flags & GAT_FLAG_SKIP_MLP) != 0;
+    const bool add_pitch = (flags & GAT_FLAG_NO_PITCH) == 0;                 // MFCCConfig.ADD_PITCH_FEATURES
+    const bool norm_mfcc = (flags & GAT_FLAG_NO_NORMALIZE_MFCC) == 0;        // MFCCConfig.NORMALIZE_AUDIO_VOLUME
+    const bool norm_mel = (flags & GAT_FLAG_NO_NORMALIZE_MEL) == 0;          // MelSpecConfig.NORMALIZE_AUDIO_VOLUME
     const int T = (int)(1 + n / c->cfg.mel_hop);
     const int classes = c->classes;
-    const int F = c->cfg.mfcc_n_mfcc + 1;
+    const int F = c->cfg.mfcc_n_mfcc + (add_pitch ? 1 : 0);
     if (!c->cnn_loaded) return fail("gat_transcribe_clips: no CNN loaded");
     if (!skip_mlp && (!mlp_probs || !cnn_probs)) return fail("gat_transcribe_clips: mlp_probs/cnn_probs required unless GAT_FLAG_SKIP_MLP");
+    if (!skip_mlp) {
+        // the MLP reads mlp_dims[0] floats per row of the [N][F] feature matrix: a mismatch would make rows bleed into each other
+        if (!c->mlp_n_linear) return fail("gat_transcribe_clips: no MLP loaded (gat_load_mlp)");
+        if (c->mlp_dims[0] != F)
+            return fail("gat_transcribe_clips: the MLP takes %d inputs but the feature rows have %d columns (n_mfcc %d%s)",
+                        c->mlp_dims[0], F, c->cfg.mfcc_n_mfcc, add_pitch ? " + pitch" : "");
+        if ((flags & GAT_FLAG_APPLY_SCALER) && c->scaler_n != F)
+            return fail("gat_transcribe_clips: scaler has %d columns, features have %d", c->scaler_n, F);
+    }
     if (!mel) { if (c->e2e_mel.ensure((size_t)N * c->cfg.mel_n_mels * T * 4)) return 1; mel = c->e2e_mel.as<float>(); }
     if (!skip_mlp && !mfcc) { if (c->e2e_mfcc.ensure((size_t)N * F * 4)) return 1; mfcc = c->e2e_mfcc.as<float>(); }
     if (c->logits_cnn.ensure((size_t)N * classes * 4) || c->logits_mlp.ensure((size_t)N * classes * 4)) return 1;
     float* cnn_logits = c->logits_cnn.as<float>();
     float* mlp_logits = c->logits_mlp.as<float>();
     // one RMS pass serves all three chains (the reference recomputes it per chain: features.py:185,311,460,497)
-    if (launch_clip_scale(c, audio, N, n, stream)) return 1;
-    if (run_melspec(c, audio, N, n, true, true, mel, stream)) return 1;
+    const bool any_norm = norm_mel || (!skip_mlp && norm_mfcc);
+    if (any_norm && launch_clip_scale(c, audio, N, n, stream)) return 1;
+    if (run_melspec(c, audio, N, n, norm_mel, true, mel, stream)) return 1;
     if (skip_mlp) {
         if (run_cnn(c, mel, N, T, probs, cnn_logits, stream)) return 1;
         if (cnn_probs && cnn_probs != probs)
@@ -1027,10 +1041,13 @@ extern "C" int gat_transcribe_clips(gat_ctx* c, const float* audio, int64_t N, i
         LAUNCH(c, argmax_kernel, (unsigned)((N + 7) / 8), 256, 0, stream, probs, (int)N, classes, (long long*)index, conf);
         return 0;
     }
-    if (run_mfcc(c, audio, N, n, true, true, mfcc, F, stream)) return 1;
-    if (run_yin(c, audio, N, n, (flags & GAT_FLAG_YIN_ON_NORMALIZED) != 0, true, yin_hz, nullptr, mfcc, F, c->cfg.mfcc_n_mfcc, stream)) return 1;
+    if (run_mfcc(c, audio, N, n, norm_mfcc, true, mfcc, F, stream)) return 1;
+    if (add_pitch || yin_hz) {
+        // features.py:473 hands YIN the (normalised, when the MFCC chain normalises) clip; :201 the raw one
+        const bool yn = norm_mfcc && (flags & GAT_FLAG_YIN_ON_NORMALIZED) != 0;
+        if (run_yin(c, audio, N, n, yn, true, yin_hz, nullptr, add_pitch ? mfcc : nullptr, F, c->cfg.mfcc_n_mfcc, stream)) return 1;
+    }
     if (flags & GAT_FLAG_APPLY_SCALER) {
-        if (c->scaler_n != F) return fail("gat_transcribe_clips: scaler has %d columns, features have %d", c->scaler_n, F);
         const long long tot = (long long)N * F;
         LAUNCH(c, standard_scale_kernel, (unsigned)((tot + 255) / 256), 256, 0, stream, mfcc, (int)N, F, F,
                c->scaler_mean.as<double>(), c->scaler_scale.as<double>());

@@ -5,6 +5,10 @@
 // comparisons, so the arithmetic here follows its dtypes AND its summation orders where a decision hangs
 // on them (frame RMS: float32 sequential; mel-band mean: float64 sequential).  The mel spectrogram itself
 // comes from stft_mel_kernel<double, kOutSpec> in features.cuh.
+//
+// Every kernel is batched over P independent signals of equal length (gat_segment_batch: the phrases / files a
+// rank owns when an hour of audio is sharded across GPUs, SURVEY 8(e) option (i)); the signal index is
+// blockIdx.y (blockIdx.x for the one-CTA-per-signal kernels) and gat_segment is the P = 1 case of the same code.
 #pragma once
 #include "common.cuh"
 #include "features.cuh"
@@ -21,8 +25,8 @@ namespace gat {
 //      np.log10 on float32 is glibc's log10f (not correctly rounded, libm-version dependent); we round the
 //      float64 log10 instead, which can differ from it by <= 3 float32 ulp (~1e-5 dB).
 struct RmsParams {
-    const float* y; long long L; int T; int hop; float sample_gate;
-    float* rms_db;   // [T]
+    const float* y; long long L; int T; int hop; float sample_gate;   // y[P][L]
+    float* rms_db;   // [P][T]
 };
 
 __global__ void __launch_bounds__(128) rms_db_kernel(RmsParams p) {
@@ -30,6 +34,7 @@ __global__ void __launch_bounds__(128) rms_db_kernel(RmsParams p) {
     const int lane = lane_id(), warp = warp_id();
     const int t = (blockIdx.x * 4 + warp) * 32 + lane;
     const int t_base = (blockIdx.x * 4 + warp) * 32;
+    const float* y = p.y + (long long)blockIdx.y * p.L;
     float r[8];
     float sums[4];      // binary-counter stack of block sums: 16 blocks of 128 -> 4 levels
     float total = 0.0f;
@@ -40,7 +45,7 @@ __global__ void __launch_bounds__(128) rms_db_kernel(RmsParams p) {
             if (tt < p.T) {
                 long long s = (long long)tt * p.hop + j0 + lane - 1024;
                 if (s < 0 || s >= p.L) s = reflect_index(s, p.L);
-                v = p.y[s];
+                v = y[s];
                 if (!(fabsf(v) >= p.sample_gate)) v = 0.0f;
             }
             tile[warp][row][lane] = v;
@@ -69,7 +74,7 @@ __global__ void __launch_bounds__(128) rms_db_kernel(RmsParams p) {
     if (t < p.T) {
         const float rms = sqrtf(total / 2048.0f);
         const float l = (float)log10((double)__fadd_rn(rms, 1e-10f));
-        p.rms_db[t] = __fmul_rn(20.0f, l);
+        p.rms_db[(long long)blockIdx.y * p.T + t] = __fmul_rn(20.0f, l);
     }
 }
 
@@ -77,6 +82,7 @@ __global__ void __launch_bounds__(128) rms_db_kernel(RmsParams p) {
 __global__ void median5_kernel(const float* __restrict__ in, float* __restrict__ out, int T) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
+    in += (long long)blockIdx.y * T; out += (long long)blockIdx.y * T;
     float v[5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
@@ -96,12 +102,12 @@ __global__ void median5_kernel(const float* __restrict__ in, float* __restrict__
 // ---- np.percentile(rms_db, 20) with linear interpolation in float32, gate = p20 + 6 dB, frame mask
 //      (slicing.py:59-90).  Exact order statistics by a 4-pass 8-bit radix select; a single CTA.
 struct GateParams {
-    const float* db; int T;
+    const float* db; int T;      // db[P][T]; one CTA per signal
     int k_lo;            // floor of the virtual index (T-1)*q computed in float32 on the host
     float gamma;         // its fractional part, float32
     float gate_offset;   // 6.0
-    unsigned char* frame_gate;   // [T] 1 = keep
-    float* gate_out;     // [1] gate level in dB (diagnostic)
+    unsigned char* frame_gate;   // [P][T] 1 = keep
+    float* gate_out;     // [P] gate level in dB (diagnostic)
 };
 
 __device__ __forceinline__ unsigned ordered_u32(float f) {
@@ -141,36 +147,39 @@ __device__ float radix_select(const float* __restrict__ db, int T, int k, unsign
 
 __global__ void __launch_bounds__(1024) rms_gate_kernel(GateParams p) {
     __shared__ unsigned hist[256];
-    const float a = radix_select(p.db, p.T, p.k_lo, hist);
-    const float b = radix_select(p.db, p.T, min(p.k_lo + 1, p.T - 1), hist);
+    const float* db = p.db + (long long)blockIdx.x * p.T;
+    unsigned char* frame_gate = p.frame_gate + (long long)blockIdx.x * p.T;
+    const float a = radix_select(db, p.T, p.k_lo, hist);
+    const float b = radix_select(db, p.T, min(p.k_lo + 1, p.T - 1), hist);
     // numpy _lerp in float32: a + (b-a)*t, replaced by b - (b-a)*(1-t) where t >= 0.5
     const float diff = __fsub_rn(b, a);
     float q = __fadd_rn(a, __fmul_rn(diff, p.gamma));
     if (p.gamma >= 0.5f) q = __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.0f, p.gamma)));
     const float gate = __fadd_rn(q, p.gate_offset);
-    if (threadIdx.x == 0) p.gate_out[0] = gate;
-    for (int i = threadIdx.x; i < p.T; i += blockDim.x) p.frame_gate[i] = p.db[i] > gate ? 1 : 0;
+    if (threadIdx.x == 0) p.gate_out[blockIdx.x] = gate;
+    for (int i = threadIdx.x; i < p.T; i += blockDim.x) frame_gate[i] = db[i] > gate ? 1 : 0;
 }
 
 // ---- onset strength (librosa.onset.onset_strength): S' = max(S, max(S) - 80); flux[u] = mean_m
 //      relu(S'[u+1][m] - S'[u][m]); env = [0,0,0, flux...][:T].  Also tracks min / max of env.
 struct FluxParams {
-    const double* spec;        // [T][n_mels] mel dB before the top_db clamp
-    const long long* spec_max; // ordered bits of the global max
+    const double* spec;        // [P][T][n_mels] mel dB before the top_db clamp
+    const long long* spec_max; // [P] ordered bits of each signal's max
     int T, n_mels, lag_pad;    // lag_pad = 1 + 2048/(2*hop) = 3
     double top_db;
-    double* env;               // [T]
-    long long* env_minmax;     // [2] ordered bits: min (stored negated for atomicMax), max
+    double* env;               // [P][T]
+    long long* env_minmax;     // [P][2] ordered bits: min (stored negated for atomicMax), max
 };
 
 __global__ void onset_flux_kernel(FluxParams p) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long sig = blockIdx.y;
     double e = 0.0;
     if (t < p.T) {
         const int u = t - p.lag_pad;
         if (u >= 0 && u + 1 < p.T) {
-            const double floor_db = from_ordered_bits(p.spec_max[0]) - p.top_db;
-            const double* s0 = p.spec + (long long)u * p.n_mels;
+            const double floor_db = from_ordered_bits(p.spec_max[sig]) - p.top_db;
+            const double* s0 = p.spec + (sig * p.T + u) * p.n_mels;
             const double* s1 = s0 + p.n_mels;
             double acc = 0.0;
             for (int m = 0; m < p.n_mels; ++m) {
@@ -181,38 +190,41 @@ __global__ void onset_flux_kernel(FluxParams p) {
             }
             e = acc / (double)p.n_mels;
         }
-        p.env[t] = e;
+        p.env[sig * p.T + t] = e;
     }
     double mx = t < p.T ? e : -1e300, mn = t < p.T ? e : 1e300;
     mx = warp_max(mx); mn = warp_min(mn);
     if (lane_id() == 0) {
-        atomicMax(p.env_minmax + 1, ordered_bits(mx));
-        atomicMax(p.env_minmax + 0, ordered_bits(-mn));
+        atomicMax(p.env_minmax + 2 * sig + 1, ordered_bits(mx));
+        atomicMax(p.env_minmax + 2 * sig + 0, ordered_bits(-mn));
     }
 }
 
 // ---- onset_detect normalisation + candidate peaks (librosa.util.peak_pick's two tests)
-struct PeakParams {
+struct PeakParams {       // all arrays carry a leading signal dimension [P]
     const double* env; const long long* env_minmax; int T;
     int pre_max, post_max, pre_avg, post_avg, wait;
     double delta;              // float32(0.07) promoted
     double* envn;              // [T] normalised envelope
     unsigned* cand;            // [ceil(T/32)] bit t%32 of word t/32 = frame t passes both peak_pick tests
-    int* n_peaks; int* peaks;  // outputs of peak_select_kernel
-    int* any_nonzero;          // [1]
+    int* n_peaks; int* peaks;  // outputs of peak_select_kernel: [P], [P][T]
+    int* any_nonzero;          // [P]
+    int words;                 // mask words per signal = ceil(T/32) + 1
 };
 
 __global__ void peak_candidates_kernel(PeakParams p) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long sig = blockIdx.y;
+    const double* env = p.env + sig * p.T;
     bool ok = false;
     if (t < p.T) {
-        const double mn = -from_ordered_bits(p.env_minmax[0]);
-        const double mx = from_ordered_bits(p.env_minmax[1]);
+        const double mn = -from_ordered_bits(p.env_minmax[2 * sig + 0]);
+        const double mx = from_ordered_bits(p.env_minmax[2 * sig + 1]);
         const double den = __dadd_rn(__dsub_rn(mx, mn), 2.2250738585072014e-308);
-        auto x = [&](int i) { return __ddiv_rn(__dsub_rn(p.env[i], mn), den); };
+        auto x = [&](int i) { return __ddiv_rn(__dsub_rn(env[i], mn), den); };
         const double xt = x(t);
-        p.envn[t] = xt;
-        if (xt != 0.0) atomicExch(p.any_nonzero, 1);
+        p.envn[sig * p.T + t] = xt;
+        if (xt != 0.0) atomicExch(p.any_nonzero + sig, 1);
         const int lo_m = t == 0 ? 0 : max(0, t - p.pre_max), hi_m = min(t + p.post_max, p.T);
         double mxw = -1e300;
         for (int i = lo_m; i < hi_m; ++i) { const double v = x(i); mxw = v > mxw ? v : mxw; }
@@ -226,7 +238,7 @@ __global__ void peak_candidates_kernel(PeakParams p) {
         }
     }
     const unsigned m = __ballot_sync(0xffffffffu, ok);       // blockDim is a multiple of 32: word t/32 belongs to this warp
-    if (lane_id() == 0 && t < p.T) p.cand[t >> 5] = m;
+    if (lane_id() == 0 && t < p.T) p.cand[sig * p.words + (t >> 5)] = m;
 }
 
 // Sequential `wait` rule: after a peak at n the next frame examined is n + wait + 1.  One warp: each lane
@@ -234,11 +246,14 @@ __global__ void peak_candidates_kernel(PeakParams p) {
 // ballot, set bits are walked in order.  Candidates are sparse (one per note), so this is a few microseconds.
 __global__ void __launch_bounds__(32) peak_select_kernel(PeakParams p) {
     const int lane = lane_id();
-    if (*p.any_nonzero == 0) { if (lane == 0) *p.n_peaks = 0; return; }
+    const long long sig = blockIdx.x;
+    const unsigned* cand = p.cand + sig * p.words;
+    int* peaks = p.peaks + sig * p.T;
+    if (p.any_nonzero[sig] == 0) { if (lane == 0) p.n_peaks[sig] = 0; return; }
     const int n_words = (p.T + 31) >> 5;
     int count = 0, next_ok = 0;
     for (int w0 = 0; w0 < n_words; w0 += 32) {
-        const unsigned mine = w0 + lane < n_words ? p.cand[w0 + lane] : 0u;
+        const unsigned mine = w0 + lane < n_words ? cand[w0 + lane] : 0u;
         unsigned live = __ballot_sync(0xffffffffu, mine != 0u);
         while (live) {
             const int src = __ffs((int)live) - 1;
@@ -249,41 +264,43 @@ __global__ void __launch_bounds__(32) peak_select_kernel(PeakParams p) {
                 m &= m - 1;
                 const int n = ((w0 + src) << 5) + b;
                 if (n >= next_ok && n < p.T) {
-                    if (lane == 0) p.peaks[count] = n;
+                    if (lane == 0) peaks[count] = n;
                     ++count;
                     next_ok = n + p.wait + 1;
                 }
             }
         }
     }
-    if (lane == 0) *p.n_peaks = count;
+    if (lane == 0) p.n_peaks[sig] = count;
 }
 
 // ---- onset_backtrack + frames_to_samples + greedy minimum separation + slice table (slicing.py:109-136,
 //      :153-161).  K is small (one entry per note), so a single thread does the sequential parts.
-struct SliceParams {
+struct SliceParams {      // all arrays carry a leading signal dimension [P]
     const double* envn; int T;
-    const int* n_peaks; const int* peaks;
+    const int* n_peaks; const int* peaks;      // [P], [P][T]
     int hop; long long L;
     long long min_sep_samples;   // int(min_sep * sr)
     long long skip;              // int(attack_skip_sec * sr)
     long long length;            // int(length_sec * sr)
     int max_onsets;
-    int* n_onsets; long long* onsets;          // filtered onset sample positions
-    long long* frames_bt;                      // [n_peaks] backtracked frames (diagnostic)
-    long long* table;                          // [max_onsets][3] start, end, valid
+    int* n_onsets; long long* onsets;          // [P], [P][max_onsets] filtered onset sample positions
+    long long* frames_bt;                      // [P][T] backtracked frames (first n_peaks valid; diagnostic)
+    long long* table;                          // [P][max_onsets][3] start, end, valid
 };
 
 __global__ void backtrack_kernel(SliceParams p) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *p.n_peaks) return;
-    int f = p.peaks[i];
+    const long long sig = blockIdx.y;
+    if (i >= p.n_peaks[sig]) return;
+    const double* envn = p.envn + sig * p.T;
+    int f = p.peaks[sig * p.T + i];
     // nearest local minimum at or before the event; index 0 always qualifies (fix_frames pads it)
     while (f > 0) {
-        if (f <= p.T - 2 && p.envn[f] <= p.envn[f - 1] && p.envn[f] < p.envn[f + 1]) break;
+        if (f <= p.T - 2 && envn[f] <= envn[f - 1] && envn[f] < envn[f + 1]) break;
         --f;
     }
-    p.frames_bt[i] = f;
+    p.frames_bt[sig * p.T + i] = f;
 }
 
 // Greedy minimum separation is sequential in the kept onset, but cheap once the inputs sit in shared memory:
@@ -295,61 +312,74 @@ __global__ void __launch_bounds__(1024) minsep_table_kernel(SliceParams p) {
     __shared__ long long tile[kSepTile];
     __shared__ int s_k;
     __shared__ long long s_last;
-    const int n = *p.n_peaks;
+    const long long sig = blockIdx.x;
+    const int n = p.n_peaks[sig];
+    const long long* frames_bt = p.frames_bt + sig * p.T;
+    long long* onsets = p.onsets + sig * p.max_onsets;
+    long long* table = p.table + sig * p.max_onsets * 3;
     if (threadIdx.x == 0) { s_k = 0; s_last = -999999; }
     __syncthreads();
     for (int i0 = 0; i0 < n; i0 += kSepTile) {
         const int nt = min(kSepTile, n - i0);
-        for (int i = threadIdx.x; i < nt; i += blockDim.x) tile[i] = p.frames_bt[i0 + i] * p.hop;
+        for (int i = threadIdx.x; i < nt; i += blockDim.x) tile[i] = frames_bt[i0 + i] * p.hop;
         __syncthreads();
         if (threadIdx.x == 0) {
             int k = s_k; long long last = s_last;
             for (int i = 0; i < nt; ++i) {
                 const long long s = tile[i];
-                if (s - last >= p.min_sep_samples && k < p.max_onsets) { p.onsets[k++] = s; last = s; }
+                if (s - last >= p.min_sep_samples && k < p.max_onsets) { onsets[k++] = s; last = s; }
             }
             s_k = k; s_last = last;
         }
         __syncthreads();
     }
     const int k = s_k;
-    if (threadIdx.x == 0) *p.n_onsets = k;
+    if (threadIdx.x == 0) p.n_onsets[sig] = k;
     __threadfence_block();
     __syncthreads();
     for (int i = threadIdx.x; i < k; i += blockDim.x) {
-        const long long next = i + 1 < k ? p.onsets[i + 1] : p.onsets[k - 1];
-        const long long start = p.onsets[i] + p.skip;
+        const long long next = i + 1 < k ? onsets[i + 1] : onsets[k - 1];
+        const long long start = onsets[i] + p.skip;
         const long long end = (start + p.length < next) ? start + p.length : next;
         const bool empty = start >= p.L || end > p.L;
-        p.table[3 * i + 0] = start;
-        p.table[3 * i + 1] = end;
-        p.table[3 * i + 2] = empty ? 0 : 1;
+        table[3 * i + 0] = start;
+        table[3 * i + 1] = end;
+        table[3 * i + 2] = empty ? 0 : 1;
     }
 }
 
 // ---- is_slice_loud_enough (slicing.py:96-100) on the zero-padded fixed-length clip, compaction, gather.
+//      Kept clips are compacted in (signal, onset) order into ONE list: per-signal counts (slice_compact_kernel),
+//      an exclusive scan over the signals (slice_base_kernel), then the gather writes rows base[signal] + k.
 struct GatherParams {
-    const float* y; long long L;
-    const int* n_onsets; const long long* table;
+    const float* y; long long L;             // y[P][L]
+    const int* n_onsets; const long long* table;   // [P], [P][max_onsets][3]
     long long length;
     float min_rms_db;            // -37
-    unsigned char* keep;         // [max_onsets]
-    int* dest;                   // [max_onsets] compacted position
-    int* n_clips;
-    float* clips;                // [max_onsets][length]
-    long long* clip_table;       // [max_onsets][3]: onset index, start, end
+    unsigned char* keep;         // [P][max_onsets]
+    int* dest;                   // [P][max_onsets] position among the signal's kept clips, -1 = dropped
+    int* n_clips;                // [P] kept clips per signal, then [P] = total over all signals
+    long long* base;             // [P] first row of each signal in the compacted list
+    float* clips;                // [max_clips][length]
+    long long* clip_table;       // [max_clips][table_cols]: (signal,) onset index, start, end
     int max_onsets;
+    int table_cols;              // 3 (gat_segment) or 4 (gat_segment_batch: signal index first)
+    long long max_clips;         // rows the caller provided; rows past it are counted but not written
+    int P;
 };
 
 __global__ void slice_loudness_kernel(GatherParams p) {
     __shared__ double red[8];
     const int i = blockIdx.x;
-    if (i >= *p.n_onsets) return;
-    const long long start = p.table[3 * i], end = p.table[3 * i + 1];
-    const bool valid = p.table[3 * i + 2] != 0;
+    const long long sig = blockIdx.y;
+    if (i >= p.n_onsets[sig]) return;
+    const long long* table = p.table + sig * p.max_onsets * 3;
+    const float* y = p.y + sig * p.L;
+    const long long start = table[3 * i], end = table[3 * i + 1];
+    const bool valid = table[3 * i + 2] != 0;
     double acc = 0.0;
     if (valid)   // python slicing y[start:end] with end < start is empty; the pad makes it all zeros
-        for (long long s = start + threadIdx.x; s < end; s += blockDim.x) { const float v = p.y[s]; acc += (double)__fmul_rn(v, v); }
+        for (long long s = start + threadIdx.x; s < end; s += blockDim.x) { const float v = y[s]; acc += (double)__fmul_rn(v, v); }
     acc = warp_sum(acc);
     if (lane_id() == 0) red[warp_id()] = acc;
     __syncthreads();
@@ -362,21 +392,24 @@ __global__ void slice_loudness_kernel(GatherParams p) {
             const float db = __fmul_rn(20.0f, (float)log10((double)__fadd_rn(rms, 1e-10f)));
             keep = db > p.min_rms_db;
         }
-        p.keep[i] = keep ? 1 : 0;
+        p.keep[sig * p.max_onsets + i] = keep ? 1 : 0;
     }
 }
 
-// Order-preserving compaction of the kept clips: one CTA, chunked block scan of the keep flags.
+// Order-preserving compaction of one signal's kept clips: one CTA per signal, chunked block scan of the keep flags.
 __global__ void __launch_bounds__(1024) slice_compact_kernel(GatherParams p) {
     __shared__ int warp_tot[32];
     __shared__ int s_base;
-    const int n = *p.n_onsets;
+    const long long sig = blockIdx.x;
+    const int n = p.n_onsets[sig];
+    const unsigned char* keep_s = p.keep + sig * p.max_onsets;
+    int* dest = p.dest + sig * p.max_onsets;
     const int lane = lane_id(), warp = warp_id();
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
     for (int i0 = 0; i0 < n; i0 += (int)blockDim.x) {
         const int i = i0 + threadIdx.x;
-        const int keep = i < n ? (int)p.keep[i] : 0;
+        const int keep = i < n ? (int)keep_s[i] : 0;
         int incl = keep;                                    // inclusive scan inside the warp
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -387,31 +420,61 @@ __global__ void __launch_bounds__(1024) slice_compact_kernel(GatherParams p) {
         __syncthreads();
         int before = s_base;
         for (int w = 0; w < warp; ++w) before += warp_tot[w];
-        const int k = before + incl - keep;
-        if (i < n) {
-            p.dest[i] = keep ? k : -1;
-            if (keep) {
-                p.clip_table[3 * k + 0] = i;
-                p.clip_table[3 * k + 1] = p.table[3 * i];
-                p.clip_table[3 * k + 2] = p.table[3 * i + 1];
-            }
-        }
+        if (i < n) dest[i] = keep ? before + incl - keep : -1;
         __syncthreads();
         if (threadIdx.x == blockDim.x - 1) s_base = before + incl;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *p.n_clips = s_base;
+    if (threadIdx.x == 0) p.n_clips[sig] = s_base;
+}
+
+// Exclusive scan of the per-signal clip counts (one CTA; P is the number of signals of one call), total in n_clips[P].
+__global__ void __launch_bounds__(1024) slice_base_kernel(GatherParams p) {
+    __shared__ long long warp_tot[32];
+    __shared__ long long s_base;
+    const int lane = lane_id(), warp = warp_id();
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < p.P; i0 += (int)blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        const long long cnt = i < p.P ? (long long)p.n_clips[i] : 0;
+        long long incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        long long before = s_base;
+        for (int w = 0; w < warp; ++w) before += warp_tot[w];
+        if (i < p.P) p.base[i] = before + incl - cnt;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_base = before + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) p.n_clips[p.P] = (int)(s_base < 0x7fffffffLL ? s_base : 0x7fffffffLL);
 }
 
 __global__ void slice_gather_kernel(GatherParams p) {
     const int i = blockIdx.x;
-    if (i >= *p.n_onsets) return;
-    const int d = p.dest[i];
+    const long long sig = blockIdx.y;
+    if (i >= p.n_onsets[sig]) return;
+    const int d = p.dest[sig * p.max_onsets + i];
     if (d < 0) return;
-    const long long start = p.table[3 * i], end = p.table[3 * i + 1];
-    float* o = p.clips + (long long)d * p.length;
+    const long long row = p.base[sig] + d;
+    if (row >= p.max_clips) return;
+    const long long* table = p.table + sig * p.max_onsets * 3;
+    const float* y = p.y + sig * p.L;
+    const long long start = table[3 * i], end = table[3 * i + 1];
+    if (threadIdx.x == 0) {
+        long long* t = p.clip_table + row * p.table_cols;
+        if (p.table_cols == 4) *t++ = sig;
+        t[0] = i; t[1] = start; t[2] = end;
+    }
+    float* o = p.clips + row * p.length;
     for (long long j = threadIdx.x; j < p.length; j += blockDim.x)
-        o[j] = (start + j < end) ? p.y[start + j] : 0.0f;
+        o[j] = (start + j < end) ? y[start + j] : 0.0f;
 }
 
 }  // namespace gat

@@ -56,6 +56,8 @@ class Engine:
             self.lib.check(self.lib.gat_ctx_create(C.byref(cfg), self.device.index or 0, C.byref(handle)), ValueError)
         self._ctx = handle
         self._resample_cache = {}
+        self._host_out = None
+        self.mlp_in = 0
 
     # ------------------------------------------------------------------ plumbing
     def _on_device(self):
@@ -121,6 +123,7 @@ class Engine:
         self.lib.check(self.lib.gat_load_mlp(self._ctx, _lib.ptr(dims), len(dims) - 1, _lib.ptr(params), params.size), ValueError)
         self.num_classes = int(dims[-1])
         self.mlp_in = int(dims[0])
+        self._host_out = None
 
     def load_cnn(self, state_dict: dict):
         packed = pack_cnn(state_dict)
@@ -138,6 +141,7 @@ class Engine:
                                              _lib.ptr(fcs[0]["w"]), _lib.ptr(fcs[0]["b"]),
                                              _lib.ptr(fcs[1]["w"]), _lib.ptr(fcs[1]["b"])), ValueError)
         self.num_classes = int(classes)
+        self._host_out = None
 
     def set_scaler(self, scaler):
         if scaler is None:
@@ -153,13 +157,14 @@ class Engine:
         self.lib.check(self.lib.gat_set_ensemble_weights(self._ctx, np.float32(mlp_weight), np.float32(cnn_weight)))
 
     # ------------------------------------------------------------------ features
-    def melspec_db(self, audio, normalize: bool = True) -> torch.Tensor:
-        """[N, n] -> [N, 1, n_mels, T] (features.py:296-331)."""
+    def melspec_db(self, audio, normalize: bool = True, to_db: bool = True) -> torch.Tensor:
+        """[N, n] -> [N, 1, n_mels, T] (features.py:296-331); ``to_db=False`` returns the mel power (:313-316)."""
         a = self._clips(audio)
         N, n = a.shape
         out = self._empty((N, 1, self.n_mels, self.mel_frames(n)), torch.float32)
+        mode = (_lib.GAT_MEL_NORMALIZE if normalize else 0) | (0 if to_db else _lib.GAT_MEL_POWER)
         with self._on_device():
-            self.lib.check(self.lib.gat_melspec_db(self._ctx, _lib.ptr(a), N, n, int(normalize), _lib.ptr(out), self._stream()), ValueError)
+            self.lib.check(self.lib.gat_melspec_db(self._ctx, _lib.ptr(a), N, n, mode, _lib.ptr(out), self._stream()), ValueError)
         return out
 
     def mfcc_features(self, audio, normalize=True, add_pitch=True, yin_on_normalized=False, apply_scaler=False):
@@ -210,14 +215,32 @@ class Engine:
                                               _lib.ptr(out["cnn_logits"]), self._stream()), ValueError)
         return out
 
+    @staticmethod
+    def _flags(yin_on_normalized, apply_scaler, skip_mlp, add_pitch=True, normalize_mfcc=True, normalize_mel=True) -> int:
+        return ((_lib.GAT_FLAG_YIN_ON_NORMALIZED if yin_on_normalized else 0) | (_lib.GAT_FLAG_APPLY_SCALER if apply_scaler else 0) |
+                (_lib.GAT_FLAG_SKIP_MLP if skip_mlp else 0) | (0 if add_pitch else _lib.GAT_FLAG_NO_PITCH) |
+                (0 if normalize_mfcc else _lib.GAT_FLAG_NO_NORMALIZE_MFCC) | (0 if normalize_mel else _lib.GAT_FLAG_NO_NORMALIZE_MEL))
+
+    def _check_mlp_width(self, skip_mlp: bool, add_pitch: bool):
+        """The MLP reads ``mlp_in`` floats per feature row; the C side refuses a mismatch too (gat_transcribe_clips)."""
+        if skip_mlp:
+            return
+        F = self.n_mfcc + (1 if add_pitch else 0)
+        if not self.mlp_in:
+            raise ValueError("no MLP loaded (Engine.load_mlp)")
+        if self.mlp_in != F:
+            raise ValueError(f"the loaded MLP takes {self.mlp_in} inputs but this engine builds {F} feature columns "
+                             f"(N_MFCC {self.n_mfcc}{' + pitch' if add_pitch else ''})")
+
     def transcribe_clips(self, audio, yin_on_normalized=True, apply_scaler=False, skip_mlp=False,
-                         return_features=False) -> dict:
-        """Features + ensemble for N equal-length clips in one call (transcribe.py:186-197 batched)."""
+                         return_features=False, add_pitch=True, normalize_mfcc=True, normalize_mel=True) -> dict:
+        """Features + ensemble for N equal-length clips in one call (transcribe.py:186-197 batched).
+        ``add_pitch`` / ``normalize_*`` are the checkpoints' ADD_PITCH_FEATURES / NORMALIZE_AUDIO_VOLUME switches."""
         a = self._clips(audio)
         N, n = a.shape
         K = self.num_classes
-        flags = (_lib.GAT_FLAG_YIN_ON_NORMALIZED if yin_on_normalized else 0) | \
-                (_lib.GAT_FLAG_APPLY_SCALER if apply_scaler else 0) | (_lib.GAT_FLAG_SKIP_MLP if skip_mlp else 0)
+        self._check_mlp_width(skip_mlp, add_pitch)
+        flags = self._flags(yin_on_normalized, apply_scaler, skip_mlp, add_pitch, normalize_mfcc, normalize_mel)
         out = {"probs": self._empty((N, K), torch.float32), "cnn_probs": self._empty((N, K), torch.float32),
                "indices": self._empty((N,), torch.int64), "confidences": self._empty((N,), torch.float32)}
         out["mlp_probs"] = None if skip_mlp else self._empty((N, K), torch.float32)
@@ -225,7 +248,7 @@ class Engine:
         if return_features:
             mel = self._empty((N, 1, self.n_mels, self.mel_frames(n)), torch.float32)
             if not skip_mlp:
-                mfcc = self._empty((N, self.n_mfcc + 1), torch.float32)
+                mfcc = self._empty((N, self.n_mfcc + (1 if add_pitch else 0)), torch.float32)
                 hz = self._empty((N,), torch.float64)
         with self._on_device():
             self.lib.check(self.lib.gat_transcribe_clips(
@@ -236,9 +259,10 @@ class Engine:
         return out
 
     def transcribe_clips_host(self, audio_host, yin_on_normalized=True, apply_scaler=False, skip_mlp=False,
-                              want_probs=True) -> dict:
+                              want_probs=True, add_pitch=True, normalize_mfcc=True, normalize_mel=True) -> dict:
         """Host buffers in (float32 clips, or int16 = PCM_16 clips scaled by 1/32768 on the device), host buffers
-        out: H2D (chunked, overlapped), kernels, D2H inside the call."""
+        out: H2D (chunked, overlapped), kernels, D2H inside the call.  The returned arrays are copies: the pinned
+        landing buffers are reused by the next call."""
         if isinstance(audio_host, torch.Tensor):
             if audio_host.device.type != "cpu" or audio_host.dtype not in (torch.float32, torch.int16) or not audio_host.is_contiguous():
                 raise ValueError("audio_host must be a contiguous float32 or int16 (PCM_16) CPU tensor (pinned for overlap)")
@@ -250,9 +274,9 @@ class Engine:
         src = _lib.ptr(audio_host)
         entry = self.lib.gat_transcribe_clips_host_pcm16 if pcm16 else self.lib.gat_transcribe_clips_host
         K = self.num_classes
-        flags = (_lib.GAT_FLAG_YIN_ON_NORMALIZED if yin_on_normalized else 0) | \
-                (_lib.GAT_FLAG_APPLY_SCALER if apply_scaler else 0) | (_lib.GAT_FLAG_SKIP_MLP if skip_mlp else 0)
-        if not hasattr(self, "_host_out") or self._host_out["indices"].shape[0] != N:
+        self._check_mlp_width(skip_mlp, add_pitch)
+        flags = self._flags(yin_on_normalized, apply_scaler, skip_mlp, add_pitch, normalize_mfcc, normalize_mel)
+        if self._host_out is None or self._host_out["probs"].shape != (N, K):
             pin = self.device.type == "cuda"
             self._host_out = {"indices": torch.empty(N, dtype=torch.int64, pin_memory=pin),
                               "confidences": torch.empty(N, dtype=torch.float32, pin_memory=pin),
@@ -262,8 +286,8 @@ class Engine:
             self.lib.check(entry(
                 self._ctx, src, N, n, flags, _lib.ptr(ho["indices"]), _lib.ptr(ho["confidences"]),
                 _lib.ptr(ho["probs"]) if want_probs else None), ValueError)
-        return {"indices": ho["indices"].numpy(), "confidences": ho["confidences"].numpy(),
-                "probs": ho["probs"].numpy() if want_probs else None,
+        return {"indices": ho["indices"].numpy().copy(), "confidences": ho["confidences"].numpy().copy(),
+                "probs": ho["probs"].numpy().copy() if want_probs else None,
                 "h2d_bytes": N * n * (2 if pcm16 else 4), "d2h_bytes": N * 12 + (N * K * 4 if want_probs else 0)}
 
     # ------------------------------------------------------------------ segmentation
@@ -377,6 +401,37 @@ class Engine:
             nf = int(diag["n_frames"].item())
             res.update(rms_db=diag["rms_db"], env=diag["env"], frames=diag["frames"][:nf])
         return res
+
+    def segment_batch(self, signals, length_sec: float, cfg=None) -> dict:
+        """``segment`` for P independent equal-length signals ``[P, L]`` in one pass of batched kernels
+        (gat_segment_batch): each signal is sliced exactly as AudioSlicer.sliceNsave slices a file of its own.
+        Returns device tensors: onsets [P, max_onsets] (first n_onsets[p] valid), n_onsets [P], clips [K, n] in
+        (signal, onset) order, table [K, 4] = (signal, onset index, start, end), n_clips [P]."""
+        Y = torch.as_tensor(signals).to(device=self.device, dtype=torch.float32).contiguous()
+        if Y.dim() != 2:
+            raise ValueError("segment_batch: signals must be [P, L]")
+        P, L = Y.shape
+        sp = self.slicer_params(L, length_sec, cfg)
+        max_onsets = max(2, L // max(1, sp.min_sep_samples) + 2)
+        out = {"onsets": self._empty((P, max_onsets), torch.int64), "n_onsets": self._empty((P,), torch.int32),
+               "n_clips": self._empty((P + 1,), torch.int32)}
+        if P == 0:
+            return {"onsets": out["onsets"], "n_onsets": out["n_onsets"], "clips": self._empty((0, sp.clip_len), torch.float32),
+                    "table": self._empty((0, 4), torch.int64), "n_clips": out["n_clips"][:0], "params": sp}
+        # K onsets yield at most K - 1 clips (the last onset never does, slicing.py:154)
+        max_clips = P * (max_onsets - 1)
+        clips = self._empty((max_clips, sp.clip_len), torch.float32)
+        table = self._empty((max_clips, 4), torch.int64)
+        with self._on_device():
+            for p0 in range(0, P, 65535):
+                if p0:
+                    raise ValueError("segment_batch: at most 65535 signals per call")
+                self.lib.check(self.lib.gat_segment_batch(
+                    self._ctx, _lib.ptr(Y), P, L, C.byref(sp), max_onsets, _lib.ptr(out["onsets"]), _lib.ptr(out["n_onsets"]),
+                    _lib.ptr(clips), max_clips, _lib.ptr(table), _lib.ptr(out["n_clips"]), self._stream()), ValueError)
+        k = int(out["n_clips"][P].item())
+        return {"onsets": out["onsets"], "n_onsets": out["n_onsets"], "clips": clips[:k], "table": table[:k],
+                "n_clips": out["n_clips"][:P], "params": sp}
 
 
 class _Null:

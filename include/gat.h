@@ -78,7 +78,11 @@ int gat_set_ensemble_weights(gat_ctx* ctx, float mlp_weight, float cnn_weight);
 /* ---- features ---------------------------------------------------------------------------------- */
 
 /* MelFeatureBuilder.extract_melspec_features per clip (features.py:296-316, :486-502):
- * out_dev[N][mel_n_mels][T], T = 1 + n / mel_hop.  normalize = NORMALIZE_AUDIO_VOLUME. */
+ * out_dev[N][mel_n_mels][T], T = 1 + n / mel_hop.  `normalize` is a bit set: GAT_MEL_NORMALIZE =
+ * NORMALIZE_AUDIO_VOLUME (features.py:311,:497); GAT_MEL_POWER = to_db / melspec_to_db False (features.py:313-316,
+ * :499-502): the mel POWER is written instead of 10 log10. */
+#define GAT_MEL_NORMALIZE 1
+#define GAT_MEL_POWER     2
 int gat_melspec_db(gat_ctx* ctx, const float* audio_dev, int64_t N, int64_t n, int32_t normalize,
                    float* out_dev, void* stream);
 
@@ -133,6 +137,19 @@ int gat_segment(gat_ctx* ctx, const float* y_dev, int64_t L, const gat_slicer_pa
                 int32_t* n_clips_dev, float* rms_db_dev, double* env_dev, int64_t* frames_dev,
                 int32_t* n_frames_dev, void* stream);
 
+/* gat_segment for P independent signals of L samples each (y_dev[P][L]) in ONE pass of batched kernels: the phrases /
+ * files a rank owns when a long recording is sharded across GPUs (SURVEY.md 8(e) option (i): every signal is sliced
+ * exactly as AudioSlicer.sliceNsave would slice it as a file of its own - its own dB maximum, percentile gate,
+ * envelope normalisation and min-sep scan, slicing.py:147-165).
+ * Outputs (device): onsets_dev int64[P][max_onsets], n_onsets_dev int32[P];
+ *                   clips_dev float32[max_clips][clip_len]: the kept clips of ALL signals, compacted in (signal, onset)
+ *                   order; clip_table_dev int64[max_clips][4] = (signal, onset index, start, end);
+ *                   n_clips_dev int32[P + 1]: kept clips per signal, then their total.  Clips past max_clips are counted
+ *                   but not written (the caller compares n_clips_dev[P] with max_clips). */
+int gat_segment_batch(gat_ctx* ctx, const float* y_dev, int64_t P, int64_t L, const gat_slicer_params* sp,
+                      int32_t max_onsets, int64_t* onsets_dev, int32_t* n_onsets_dev, float* clips_dev, int64_t max_clips,
+                      int64_t* clip_table_dev, int32_t* n_clips_dev, void* stream);
+
 /* AudioSlicer.detect_onsets(y, sr, hop_len, min_sep) on its own (slicing.py:106-122; the live prototype calls it
  * with hop 1024 on the un-gated microphone buffer, prototyping/source/transcribe_live.py:94-96): no gates, any even
  * hop.  Uses sp->onset_hop, the peak-pick fields and min_sep_samples; the signal is processed in float64 (a float32
@@ -147,7 +164,8 @@ int gat_detect_onsets(gat_ctx* ctx, const float* y_dev, int64_t L, const gat_sli
 #define GAT_SAMPLE_FLOAT32 1
 
 /* sf.write(.wav) + librosa.load of a clip (audio/slicing.py:144 then audio/loading.py:85): every sample goes
- * through PCM_16 once, x <- rint(x * 32767) / 32768, in place on `count` device floats. */
+ * through PCM_16 once.  python-soundfile enables SFC_SET_CLIPPING, so libsndfile's float -> PCM_16 conversion is
+ * q = lrintf(x * 2^31) >> 16 (saturating at +-full scale); the read is q / 32768.  In place on `count` device floats. */
 int gat_pcm16_roundtrip(gat_ctx* ctx, float* audio_dev, int64_t count, void* stream);
 
 /* librosa.load's decode + to_mono (audio/slicing.py:25): interleaved frames of `channels` samples
@@ -167,12 +185,17 @@ int gat_resample(gat_ctx* ctx, const float* in_dev, int64_t N, int64_t n_in, int
 #define GAT_FLAG_YIN_ON_NORMALIZED 1   /* transcribe_note path (features.py:473)                    */
 #define GAT_FLAG_APPLY_SCALER      2   /* transcribe(file) path (features.py:145-146)               */
 #define GAT_FLAG_SKIP_MLP          4   /* BASELINE config 2: mel-spectrogram + CNN only              */
+#define GAT_FLAG_NO_PITCH          8   /* MFCCConfig.ADD_PITCH_FEATURES = False (features.py:199,:471): rows have n_mfcc columns */
+#define GAT_FLAG_NO_NORMALIZE_MFCC 16  /* MFCCConfig.NORMALIZE_AUDIO_VOLUME = False (features.py:184,:459) */
+#define GAT_FLAG_NO_NORMALIZE_MEL  32  /* MelSpecConfig.NORMALIZE_AUDIO_VOLUME = False (features.py:310,:496) */
 
 /* Transcriber.transcribe_note batched over N equal-length clips already on the device
- * (transcribe.py:147-199 steps 1-2).  With GAT_FLAG_SKIP_MLP probs == cnn_probs. Optional outputs may be NULL. */
+ * (transcribe.py:147-199 steps 1-2).  With GAT_FLAG_SKIP_MLP probs == cnn_probs. Optional outputs may be NULL.
+ * Fails (no kernel launched) when the loaded MLP's input width differs from the feature row width
+ * n_mfcc + (pitch ? 1 : 0), or when GAT_FLAG_APPLY_SCALER is set and the scaler's width differs. */
 int gat_transcribe_clips(gat_ctx* ctx, const float* audio_dev, int64_t N, int64_t n, int32_t flags,
                          float* probs_dev, float* mlp_probs_dev, float* cnn_probs_dev, int64_t* index_dev,
-                         float* conf_dev, float* mfcc_dev /* [N][n_mfcc+1] */, float* mel_dev, double* yin_hz_dev,
+                         float* conf_dev, float* mfcc_dev /* [N][n_mfcc (+1)] */, float* mel_dev, double* yin_hz_dev,
                          void* stream);
 
 /* Same, HOST buffers in and out: copies the clips to the device in chunks (double-buffered against the

@@ -331,9 +331,11 @@ def transcribe_audio(mlp_ckpt, cnn_ckpt, y, sr=TARGET_SR, clip_duration=CLIP_DUR
 
 # ----------------------------------------------------------------------------- file pipeline
 def pcm16_roundtrip(clip):
-    """sf.write(.wav) (slicing.py:144, libsndfile PCM_16: rint(x * 0x7FFF)) then librosa.load (loading.py:85,
-    libsndfile read: / 0x8000), restated in oracle/soundfile_standin.py and librosa_shim.load."""
-    q = np.clip(np.rint(np.asarray(clip, dtype=np.float32) * np.float32(32767.0)), -32768, 32767).astype(np.int16)
+    """sf.write(.wav) (slicing.py:144; python-soundfile always enables clipping, so libsndfile's PCM_16 conversion
+    is lrintf(x * 2^31) >> 16 with saturation) then librosa.load (loading.py:85, libsndfile read: / 0x8000),
+    restated in oracle/soundfile_standin.py and librosa_shim.load."""
+    import soundfile_standin
+    q = soundfile_standin.float_to_pcm16(clip)
     return q.astype(np.float32) / np.float32(32768.0)
 
 

@@ -167,6 +167,7 @@ static inline float __fmul_rn(float a, float b) { volatile float r = a * b; retu
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+static inline int __float2int_rn(float a) { return (int)lrintf(a); }
 static inline float __fsqrt_rn(float a) { return sqrtf(a); }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }

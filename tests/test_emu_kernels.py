@@ -52,3 +52,26 @@ def test_emu_segmentation(emu_tr, golden_phrases):
     env = g["onset_env_1"]
     en = (env - env.min()) / ((env - env.min()).max() + np.finfo(np.float64).tiny)
     assert np.abs(r["env"].numpy() - en).max() <= ENV_ABS
+
+
+def test_emu_segment_batch_equals_per_signal(emu_tr, golden_phrases):
+    """gat_segment_batch over P phrases == gat_segment on each phrase alone == the reference's onsets / tables."""
+    from guitar_audio_transcriber_ai_b200 import synth
+    g = golden_phrases
+    seeds = [int(s) for s in g["seeds"]]
+    Y = np.stack([synth.phrase(s, sr=22050)[0] for s in seeds])
+    b = emu_tr.engine.segment_batch(Y, 0.5)
+    table = b["table"].numpy()
+    clips = b["clips"].numpy()
+    row = 0
+    for p, _ in enumerate(seeds):
+        k = int(b["n_onsets"][p])
+        assert b["onsets"][p, :k].numpy().tolist() == g[f"onsets_{p}"].tolist()
+        one = emu_tr.engine.segment(Y[p], 0.5)
+        m = one["clips"].shape[0]
+        assert int(b["n_clips"][p]) == m == g[f"table_{p}"].shape[0]
+        assert np.all(table[row:row + m, 0] == p)
+        assert np.array_equal(table[row:row + m, 1:], g[f"table_{p}"])
+        assert np.array_equal(clips[row:row + m], one["clips"].numpy())
+        row += m
+    assert row == table.shape[0]

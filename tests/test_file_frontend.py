@@ -42,6 +42,24 @@ def test_wav_reader_matches_scipy(tmp_path):
             assert np.array_equal(frames, (ref.astype(np.float32) - 128.0) / 128.0)
 
 
+def test_pcm16_quantiser_known_answers():
+    """soundfile.write always runs libsndfile's CLIPPING float -> PCM_16 converter (python-soundfile sets
+    SFC_SET_CLIPPING on every file): lrintf(x * 2^31) >> 16, saturating.  Known answers worked by hand from
+    src/pcm.c f2les_clip_array; rint(x * 32767), the non-clipping routine, gives 29490 for 0.9."""
+    import soundfile_standin
+    from guitar_audio_transcriber_ai_b200.audio import wavio
+    x = np.array([0.9, -0.9, 1.0, -1.0, 1.5, -1.5, 0.0, 0.5 / 32768, 1.0 / 32768, -0.25 / 32768, -1.0 / 32768,
+                  0.99998474, 32767.5 / 32768, -32767.5 / 32768], dtype=np.float32)
+    want = np.array([29491, -29492, 32767, -32768, 32767, -32768, 0, 0, 1, -1, -1, 32767, 32767, -32768], dtype=np.int16)
+    assert np.array_equal(wavio.float_to_pcm16(x), want)
+    assert np.array_equal(soundfile_standin.float_to_pcm16(x), want)
+    rng = np.random.default_rng(11)
+    r = rng.uniform(-1.2, 1.2, 100_000).astype(np.float32)
+    ref = np.clip(np.floor(np.rint(r.astype(np.float64) * 2147483648.0) / 65536.0), -32768, 32767).astype(np.int16)
+    assert np.array_equal(wavio.float_to_pcm16(r), ref)
+    assert np.array_equal(soundfile_standin.float_to_pcm16(r), ref)
+
+
 def test_wav_reader_24bit_extensible_and_errors(tmp_path):
     from guitar_audio_transcriber_ai_b200.audio import wavio
     vals = np.array([0, 1, -1, 8388607, -8388608, 123456, -654321], dtype=np.int32)
@@ -131,7 +149,7 @@ def test_emu_front_end_kernels(emu_lib):
     f3 = rng.standard_normal((1000, 3)).astype(np.float32)
     assert np.allclose(eng.decode_mono(f3).numpy(), np.mean(f3.T, axis=0), rtol=0, atol=1e-7)
     x = (0.9 * rng.uniform(-1, 1, (3, 5000))).astype(np.float32)
-    x[0, :5] = [1.0, -1.0, 0.5 / 32767, 1.5 / 32767, 2.5 / 32767]           # ties round to even
+    x[0, :5] = [1.0, -1.0, 0.5 / 32767, 1.5 / 32767, 2.5 / 32767]
     t = torch.from_numpy(x.copy())
     eng.pcm16_roundtrip_(t)
     assert np.array_equal(t.numpy(), np.stack([port.pcm16_roundtrip(r) for r in x]))
