@@ -69,12 +69,10 @@ class MelFeatureBuilder:
     def extract_melspec_features(self, audio_loader, n_mels: int = 128, n_fft: int = 1024, hop_length: int = 256,
                                  normalize_audio_volume: bool = False, to_db: bool = True):
         """-> (X torch float32 (N, 1, n_mels, T), y_encoded, num_classes, reverse_map)."""
-        if not to_db:
-            raise NotImplementedError("to_db=False is not implemented (every caller in the reference keeps the default)")
         wavs, _, labels, _ = audio_loader.load_audio_dataset(pad_to_max=True)
         clips = np.stack([np.asarray(w, dtype=np.float32) for w in wavs])
         eng = self._engine(audio_loader.target_sr, asdict(MFCCConfig()), {"N_MELS": n_mels, "N_FFT": n_fft, "HOP_LENGTH": hop_length})
-        X = eng.melspec_db(eng._clips(clips), normalize_audio_volume).cpu()
+        X = eng.melspec_db(eng._clips(clips), normalize_audio_volume, to_db).cpu()
         y_encoded, num_classes, reverse_map = self._labels(labels)
         print(f"Extracted Mel-spectrogram features for {X.shape[0]} samples. X shape: {tuple(X.shape)}")
         return X, y_encoded, num_classes, reverse_map
@@ -128,14 +126,24 @@ class MelFeatureBuilder:
     def extract_mfcc_features_batch(self, clips, sr, n_mfcc=64, normalize_audio_volume=True, add_pitch_features=True,
                                     yin_on_normalized=False, scaler=None, melspec_config=None):
         eng = self._engine(sr, {"N_MFCC": n_mfcc}, melspec_config or asdict(MelSpecConfig()))
-        if scaler is not None:
-            eng.set_scaler(scaler)
-        feats, hz = eng.mfcc_features(clips, normalize_audio_volume, add_pitch_features, yin_on_normalized, scaler is not None)
-        return feats, hz
+        return self._mfcc_with_scaler(eng, clips, normalize_audio_volume, add_pitch_features, yin_on_normalized, scaler)
 
-    def extract_melspec_features_batch(self, clips, sr, n_mels=64, n_fft=2048, hop_length=256, normalize_audio_volume=True):
+    @staticmethod
+    def _mfcc_with_scaler(eng, clips, normalize, add_pitch, yin_on_normalized, scaler):
+        """The engines handed out by shared_engine are shared process-wide and must stay stateless: a scaler is
+        installed for this call only."""
+        if scaler is None:
+            return eng.mfcc_features(clips, normalize, add_pitch, yin_on_normalized, False)
+        eng.set_scaler(scaler)
+        try:
+            return eng.mfcc_features(clips, normalize, add_pitch, yin_on_normalized, True)
+        finally:
+            eng.set_scaler(None)
+
+    def extract_melspec_features_batch(self, clips, sr, n_mels=64, n_fft=2048, hop_length=256, normalize_audio_volume=True,
+                                       to_db=True):
         eng = self._engine(sr, asdict(MFCCConfig()), {"N_MELS": n_mels, "N_FFT": n_fft, "HOP_LENGTH": hop_length})
-        return eng.melspec_db(clips, normalize_audio_volume)
+        return eng.melspec_db(clips, normalize_audio_volume, to_db)
 
     # ---- reference API
     def extract_inference_features(self, audio_loader, mfcc_config=None, melspec_config=None, scaler=None):
@@ -150,10 +158,8 @@ class MelFeatureBuilder:
         sr = audio_loader.target_sr
         eng = self._engine(sr, mfcc_config, melspec_config)
         dev = eng._clips(clips)
-        if scaler:
-            eng.set_scaler(scaler)
-        feats, _ = eng.mfcc_features(dev, mfcc_config["NORMALIZE_AUDIO_VOLUME"], mfcc_config["ADD_PITCH_FEATURES"],
-                                     yin_on_normalized=False, apply_scaler=bool(scaler))
+        feats, _ = self._mfcc_with_scaler(eng, dev, mfcc_config["NORMALIZE_AUDIO_VOLUME"], mfcc_config["ADD_PITCH_FEATURES"],
+                                          False, scaler if scaler else None)
         mel = eng.melspec_db(dev, melspec_config["NORMALIZE_AUDIO_VOLUME"])
         return feats.cpu().numpy(), mel.cpu()
 
@@ -165,11 +171,9 @@ class MelFeatureBuilder:
             mfcc_config = asdict(MFCCConfig())
         if melspec_config is None:
             melspec_config = asdict(MelSpecConfig())
-        if not melspec_to_db:
-            raise NotImplementedError("melspec_to_db=False is not implemented (the reference always passes True)")
         eng = self._engine(target_sr, mfcc_config, melspec_config)
         dev = eng._clips(np.asarray(audio, dtype=np.float32))
         feats, _ = eng.mfcc_features(dev, mfcc_config["NORMALIZE_AUDIO_VOLUME"], mfcc_config["ADD_PITCH_FEATURES"],
                                      yin_on_normalized=True, apply_scaler=False)
-        mel = eng.melspec_db(dev, melspec_config["NORMALIZE_AUDIO_VOLUME"])
+        mel = eng.melspec_db(dev, melspec_config["NORMALIZE_AUDIO_VOLUME"], bool(melspec_to_db))
         return feats.cpu().numpy(), mel.cpu().numpy()

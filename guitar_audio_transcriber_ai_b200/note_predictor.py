@@ -9,7 +9,6 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .dsp.yin import shared_engine
 from .training.cnn_trainer import CNN
 from .training.mlp_trainer import MLP
 
@@ -68,7 +67,11 @@ class NotePredictor:
             mel = {k: params[k] for k in ("N_MELS", "N_FFT", "HOP_LENGTH")}
         if mlp_cfg:
             mf = {"N_MFCC": mlp_cfg["features"]["params"]["N_MFCC"]}
-        return shared_engine(sr, self.device, mel, mf)
+        # A predictor owns its context: the weights live in the gat_ctx, so two predictors (an A/B comparison of
+        # checkpoints, say) must not share one.  The stateless helpers (AudioSlicer, YinDsp, MelFeatureBuilder) keep
+        # using the process-wide table-only engines of dsp.yin.shared_engine.
+        from .engine import Engine
+        return Engine(sr, mel, mf, device=self.device)
 
     def predict(self, mfcc_features=None, melspec_features=None):
         """note_predictor.py:84-135.  Like the reference, BOTH feature sets are needed (it reads an unassigned

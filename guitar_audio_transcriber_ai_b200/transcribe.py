@@ -59,12 +59,14 @@ class Transcriber:
             raise ValueError("[Transcriber] Target SR mismatch.")
         return self.model_configs["mlp"]["target_sr"]
 
-    def _feature_flags(self):
+    def _feature_flags(self) -> dict:
+        """The checkpoints' feature switches (features.py:184-185,:199,:310-311,:458-460,:471,:496-497) as keyword
+        arguments of Engine.transcribe_clips."""
         mf = self.model_configs["mlp"]["features"]["params"]
         mel = self.model_configs["cnn"]["features"]["params"]
-        if not (mf["NORMALIZE_AUDIO_VOLUME"] and mel["NORMALIZE_AUDIO_VOLUME"] and mf["ADD_PITCH_FEATURES"]):
-            raise NotImplementedError("the fused path implements the shipped configuration "
-                                      "(NORMALIZE_AUDIO_VOLUME and ADD_PITCH_FEATURES on)")
+        return {"add_pitch": bool(mf.get("ADD_PITCH_FEATURES", True)),
+                "normalize_mfcc": bool(mf.get("NORMALIZE_AUDIO_VOLUME", True)),
+                "normalize_mel": bool(mel.get("NORMALIZE_AUDIO_VOLUME", True))}
 
     # ------------------------------------------------------------------ reference API
     def transcribe_note(self, audio: np.ndarray, clip_duration: float = CLIP_DURATION, sr_in: int = TARGET_SR) -> dict:
@@ -81,7 +83,6 @@ class Transcriber:
         the clips are never read back, the device copy is already what a reload would return.  Clips come back in
         onset order (the reference's order is whatever ``os.listdir`` yields)."""
         ckpt_sr = self._target_sr()
-        self._feature_flags()
         slicer_engine = self.engine if int(target_sr) == int(ckpt_sr) else self.slicer.engine(target_sr)
         y, _ = self.slicer.load_wav(audio_path, target_sr)
         seg = slicer_engine.segment(y, clip_duration, SLICER_CONFIG)
@@ -106,26 +107,42 @@ class Transcriber:
             clips = torch.nn.functional.pad(clips, (0, fixed - clips.shape[1]))
         return self._predict_sliced(clips, seg)
 
-    def _predict_sliced(self, clips, seg) -> dict:
+    @staticmethod
+    def _dsp_info(hz) -> list:
+        """transcribe.py:139-143: (median YIN Hz, {"midi", "note_name", "midi_float"}) per clip; YinDsp.round_to_nearest_pitch
+        (dsp/yin.py:21-37) evaluated over the whole array at once (same numpy ufuncs, same values)."""
+        from .dsp.yin import _NOTES_UNICODE
+        hz = np.asarray(hz, dtype=np.float64).reshape(-1)
+        ok = ~np.isnan(hz) & (hz > 0)
+        with np.errstate(all="ignore"):
+            midi_float = 12 * (np.log2(hz) - np.log2(440.0)) + 69
+        rounded = np.where(ok, np.round(midi_float), 0).astype(np.int64)
+        info = []
+        for v, good, mf, mr in zip(hz.tolist(), ok.tolist(), midi_float.tolist(), rounded.tolist()):
+            if not good:
+                info.append((v, {"midi": None, "note_name": None, "midi_float": None}))
+            else:
+                info.append((v, {"midi": mr, "note_name": "{:s}{:0d}".format(_NOTES_UNICODE[mr % 12], int(mr / 12) - 1), "midi_float": mf}))
+        return info
+
+    def _ensemble_sliced(self, clips) -> dict:
+        """File-path features (scaler applied, YIN on the raw clips: features.py:145-146,:201) + ensemble, on device."""
         self.engine.set_ensemble_weights(self.predictor.mlp_weight, self.predictor.cnn_weight)
-        out = self.engine.transcribe_clips(clips, yin_on_normalized=False, apply_scaler=self.engine.has_scaler,
-                                           return_features=True)
+        return self.engine.transcribe_clips(clips, yin_on_normalized=False, apply_scaler=self.engine.has_scaler,
+                                            return_features=True, **self._feature_flags())
+
+    def _predict_sliced(self, clips, seg) -> dict:
+        out = self._ensemble_sliced(clips)
         result = self.predictor._result(out)
-        hz = out["yin_hz"].cpu().numpy()
-        result["dsp_info"] = []
-        for v in hz:
-            m, name, mf = YinDsp.round_to_nearest_pitch(float(v))
-            result["dsp_info"].append((float(v), {"midi": m, "note_name": name, "midi_float": mf}))
+        result["dsp_info"] = self._dsp_info(out["yin_hz"].cpu().numpy())
         result["onsets"] = [int(v) for v in seg["onsets"].cpu().numpy()]
         result["slice_table"] = seg["table"].cpu().numpy()
         return result
 
     # ------------------------------------------------------------------ batched additions
-    def transcribe_notes(self, audio, clip_duration: float = CLIP_DURATION, sr_in: int = TARGET_SR) -> dict:
-        """N clips at once ([N, n] array or device tensor); each clip follows transcribe_note exactly:
-        pad/trim to int(clip_duration*target_sr), features WITHOUT the scaler, YIN on the normalised audio."""
+    def transcribe_notes_device(self, audio, clip_duration: float = CLIP_DURATION, sr_in: int = TARGET_SR) -> dict:
+        """``transcribe_notes`` that leaves the result on the device (Engine.transcribe_clips' dict of tensors)."""
         target_sr = self._target_sr()
-        self._feature_flags()
         target_len = int(clip_duration * target_sr)
         a = self.engine._clips(audio if torch.is_tensor(audio) else np.asarray(audio, dtype=np.float32))
         if sr_in != target_sr:                                   # transcribe.py:172-173
@@ -135,14 +152,17 @@ class Transcriber:
         elif a.shape[1] > target_len:
             a = a[:, :target_len].contiguous()
         self.engine.set_ensemble_weights(self.predictor.mlp_weight, self.predictor.cnn_weight)
-        out = self.engine.transcribe_clips(a, yin_on_normalized=True, apply_scaler=False)
-        return self.predictor._result(out)
+        return self.engine.transcribe_clips(a, yin_on_normalized=True, apply_scaler=False, **self._feature_flags())
+
+    def transcribe_notes(self, audio, clip_duration: float = CLIP_DURATION, sr_in: int = TARGET_SR) -> dict:
+        """N clips at once ([N, n] array or device tensor); each clip follows transcribe_note exactly:
+        pad/trim to int(clip_duration*target_sr), features WITHOUT the scaler, YIN on the normalised audio."""
+        return self.predictor._result(self.transcribe_notes_device(audio, clip_duration, sr_in))
 
     def transcribe_audio(self, y, sr: int | None = None, clip_duration: float = CLIP_DURATION) -> dict:
         """transcribe.py:77-144 from memory: slice -> features (scaler applied, YIN on raw clips) -> predict ->
         per-clip YIN ``dsp_info``; plus ``onsets`` and ``slice_table``."""
         target_sr = self._target_sr()
-        self._feature_flags()
         yt = torch.as_tensor(np.asarray(y, dtype=np.float32) if not torch.is_tensor(y) else y)
         if sr is not None and sr != target_sr:
             yt = self.engine.resample(yt.reshape(-1), sr, target_sr)
@@ -151,3 +171,25 @@ class Transcriber:
         if clips.shape[0] == 0:
             raise FileNotFoundError("load_audio_dataset: No audio files found.")
         return self._predict_sliced(clips, seg)
+
+    # ------------------------------------------------------------------ sharded across the GPUs of one box
+    def transcribe_notes_sharded(self, audio, clip_duration: float = CLIP_DURATION, sr_in: int = TARGET_SR, group=None) -> dict:
+        """``transcribe_notes`` with the clips sharded over the ranks of ``group`` (one process per GPU): every rank
+        passes the SAME ``[N, n]`` batch, runs the pipeline on its contiguous block and receives everybody's labels
+        through one all-gather of per-clip records.  See parallel.transcribe_notes_sharded."""
+        from . import parallel
+        return parallel.transcribe_notes_sharded(self, audio, clip_duration, sr_in, group)
+
+    def transcribe_phrases_sharded(self, phrases, clip_duration: float = CLIP_DURATION, group=None) -> dict:
+        """A long recording given as P independent equal-length signals ``[P, L]`` (phrases / files): rank r slices
+        and transcribes its block of signals in batched kernels, then the slice tables and labels are all-gathered
+        (SURVEY 8(e) option (i)).  See parallel.transcribe_phrases_sharded."""
+        from . import parallel
+        return parallel.transcribe_phrases_sharded(self, phrases, clip_duration, group)
+
+    def transcribe_audio_sharded(self, y, sr: int | None = None, clip_duration: float = CLIP_DURATION, group=None) -> dict:
+        """``transcribe_audio`` for ONE contiguous signal: the whole-file onset chain has global dependencies and runs
+        (redundantly, identically) on every rank; the sliced clips are then sharded (SURVEY 8(e) option (ii)).
+        See parallel.transcribe_audio_sharded."""
+        from . import parallel
+        return parallel.transcribe_audio_sharded(self, y, sr, clip_duration, group)

@@ -95,6 +95,28 @@ def melspec_image(wave, sr, n_mels=64, n_fft=2048, hop_length=256, normalize=Tru
     return spec  # (1, n_mels, T)
 
 
+def extract_melspec_features(wavs, sr, n_mels=128, n_fft=1024, hop_length=256, normalize=False, to_db=True):
+    """audio/features.py:275-341, the BATCH path: the two torchaudio transforms are built ONCE (:296-303), then a
+    per-clip loop (:308-318) and right-zero-padding to the longest spectrogram (:320-331).  (The per-note path,
+    ``melspec_image`` above, rebuilds the transforms on every call as features.py:486-493 does.)
+    Returns X (N, 1, n_mels, T_max) float32."""
+    mel_transform = ta.transforms.MelSpectrogram(sample_rate=sr, n_fft=n_fft, hop_length=hop_length, n_mels=n_mels,
+                                                 power=2.0)
+    to_db_transform = ta.transforms.AmplitudeToDB(stype="power")
+    specs = []
+    for wave in wavs:
+        y = wave.astype(np.float32)
+        if normalize:
+            y = normalize_audio_volume(y)
+        spec = mel_transform(torch.from_numpy(y).unsqueeze(0))
+        if to_db:
+            spec = to_db_transform(spec)
+        specs.append(spec)
+    max_T = max(s.shape[-1] for s in specs)
+    padded = [F.pad(s, (0, max_T - s.shape[-1])) if s.shape[-1] < max_T else s[..., :max_T] for s in specs]
+    return torch.stack(padded, dim=0)
+
+
 def extract_inference_features_from_audio(audio, target_sr=TARGET_SR, mfcc_config=None, melspec_config=None,
                                           scaler=None, melspec_to_db=True):
     """audio/features.py:441-508.  NOTE the ``scaler`` argument is accepted and never applied there."""
@@ -120,11 +142,9 @@ def extract_inference_features(wavs, target_sr, mfcc_config=None, melspec_config
                                mfcc_config["ADD_PITCH_FEATURES"], yin_on_normalized=False) for w in wavs])
     if scaler:
         X = scaler.transform(X)
-    specs = [melspec_image(w, target_sr, melspec_config["N_MELS"], melspec_config["N_FFT"],
-                           melspec_config["HOP_LENGTH"], melspec_config["NORMALIZE_AUDIO_VOLUME"]) for w in wavs]
-    max_T = max(s.shape[-1] for s in specs)
-    specs = [F.pad(s, (0, max_T - s.shape[-1])) if s.shape[-1] < max_T else s for s in specs]
-    return X, torch.stack(specs, dim=0)
+    M = extract_melspec_features(wavs, target_sr, melspec_config["N_MELS"], melspec_config["N_FFT"],
+                                 melspec_config["HOP_LENGTH"], melspec_config["NORMALIZE_AUDIO_VOLUME"])
+    return X, M
 
 
 # ----------------------------------------------------------------------------- models

@@ -478,3 +478,242 @@ def test_context_lifecycle_releases_memory():
     torch.cuda.synchronize(); torch.cuda.empty_cache()
     free1, _ = torch.cuda.mem_get_info()
     assert free0 - free1 < 8 << 20, f"{(free0 - free1) / 2**20:.1f} MiB not returned after 10 create/destroy cycles"
+
+
+# ---------------------------------------------------------------------------------------- round 2: sharding, flags, CLI
+def test_segment_batch_matches_single_signal_and_golden(tr22, golden_phrases):
+    """gat_segment_batch over P phrases == gat_segment per phrase == the reference's onsets / slice tables, bit for bit;
+    also at a size with more signals than SMs and with one degenerate (silent) signal in the batch."""
+    from guitar_audio_transcriber_ai_b200 import synth
+    g = golden_phrases
+    seeds = [int(s) for s in g["seeds"]]
+    eng = tr22.engine
+    Y = np.stack([synth.phrase(s, sr=22050)[0] for s in seeds])
+    b = eng.segment_batch(Y, 0.5)
+    table, clips = b["table"].cpu().numpy(), b["clips"].cpu().numpy()
+    row = 0
+    for p in range(len(seeds)):
+        k = int(b["n_onsets"][p])
+        assert b["onsets"][p, :k].cpu().numpy().tolist() == g[f"onsets_{p}"].tolist()
+        m = g[f"table_{p}"].shape[0]
+        assert int(b["n_clips"][p]) == m and np.all(table[row:row + m, 0] == p)
+        assert np.array_equal(table[row:row + m, 1:], g[f"table_{p}"])
+        one = eng.segment(Y[p], 0.5)
+        assert np.array_equal(clips[row:row + m], one["clips"].cpu().numpy())
+        row += m
+    assert row == table.shape[0]
+    # 300 signals (> 148 SMs), signal 7 silent: every signal still equals its own single-signal run
+    big = np.stack([synth.phrase(100 + s, sr=22050, dur=3.0, n_notes=6)[0] for s in range(12)] * 25)
+    big[7] = 0.0
+    bb = eng.segment_batch(big, 0.5)
+    tb = bb["table"].cpu().numpy()
+    assert int(bb["n_clips"][7]) == 0 and int(bb["n_onsets"][7]) == eng.segment(big[7], 0.5)["onsets"].shape[0]
+    for p in (0, 5, 11, 12, 150, 299):
+        one = eng.segment(big[p], 0.5)
+        mine = tb[tb[:, 0] == p]
+        assert np.array_equal(mine[:, 1:], one["table"].cpu().numpy())
+        k = int(bb["n_onsets"][p])
+        assert torch.equal(bb["onsets"][p, :k], one["onsets"])
+    assert torch.equal(bb["clips"][: int(bb["n_clips"][0])], eng.segment(big[0], 0.5)["clips"])
+
+
+def _gpu_rank_worker(rank, world, port_no, q):
+    """One rank of a 2-rank run of the sharded entry points on CUDA.  With two GPUs: NCCL, one GPU per rank.  On a
+    one-GPU box both ranks share cuda:0 and the records travel over gloo (parallel._all_gather_into stages them)."""
+    import os
+    import torch.distributed as dist
+    from guitar_audio_transcriber_ai_b200 import Transcriber, synth
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no))
+    two = torch.cuda.device_count() >= 2
+    dev = f"cuda:{rank if two else 0}"
+    torch.cuda.set_device(dev)
+    if world > 1:
+        if two:
+            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+        else:
+            dist.init_process_group("gloo", rank=rank, world_size=world)
+    tr = Transcriber("mlp_synth_sr22050.ckpt", "cnn_synth_sr22050.ckpt", CKPT, CKPT, device=dev)
+    Y = np.stack([synth.phrase(s, sr=22050)[0] for s in range(9)])
+    a = tr.transcribe_phrases_sharded(Y, 0.5)
+    clips, _ = synth.clip_batch(301, 0.5, 22050, 40)
+    b = tr.transcribe_notes_sharded(clips, 0.5, 22050)
+    c = tr.transcribe_audio_sharded(Y.reshape(-1), 22050, 0.5)
+    keep = lambda r: {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in r.items() if k != "local_probs"}
+    q.put((rank, world, keep(a), keep(b), keep(c), dist.get_backend() if world > 1 else "none"))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def test_sharded_entry_points_two_ranks_equal_one(tr22, golden_phrases):
+    """N1: transcribe_phrases_sharded / transcribe_notes_sharded / transcribe_audio_sharded with two ranks return, on
+    both ranks, exactly what the single-GPU call returns (labels, confidences, slice tables, onsets, YIN), and the
+    gathered onsets / tables equal the reference's golden vectors."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gpu_rank_worker, args=(r, 2, 29621, q)) for r in range(2)]
+    procs.append(ctx.Process(target=_gpu_rank_worker, args=(0, 1, 29623, q)))
+    [p.start() for p in procs]
+    got = [q.get(timeout=900) for _ in procs]
+    [p.join(120) for p in procs]
+    strip = lambda r: {k: v for k, v in r.items() if k != "local_range"}
+    for part in (2, 3, 4):
+        ref = strip(got[0][part])
+        assert len(ref["labels"]) > 0
+        for g2 in got[1:]:
+            assert strip(g2[part]) == ref, part
+    a = got[0][2]
+    g = golden_phrases
+    tab = np.asarray(a["slice_table"])
+    for p in range(4):                                   # phrases 0..3 are the golden seeds
+        assert a["onsets"][p] == g[f"onsets_{p}"].tolist()
+        assert np.array_equal(tab[tab[:, 0] == p][:, 1:], g[f"table_{p}"])
+    # the two-rank run really split the work
+    two = [x for x in got if x[1] == 2]
+    assert sorted(x[2]["local_range"] for x in two) == [(0, 5), (5, 9)]
+    assert sorted(x[3]["local_range"] for x in two) == [(0, 151), (151, 301)]
+
+
+def test_feature_switches_against_oracle(tr22):
+    """NORMALIZE_AUDIO_VOLUME / ADD_PITCH_FEATURES / TO_DB off (features.py:184-185,:199-206,:313-316,:458-502)."""
+    import port
+    from guitar_audio_transcriber_ai_b200 import synth
+    from guitar_audio_transcriber_ai_b200.audio.features import MelFeatureBuilder
+    eng = tr22.engine
+    clips, _ = synth.clip_batch(6, 0.5, 22050, seed0=77)
+    clips *= np.linspace(0.2, 1.0, 6, dtype=np.float32)[:, None]
+    mel_raw = eng.melspec_db(clips, normalize=False).cpu().numpy()
+    mel_pow = eng.melspec_db(clips, normalize=True, to_db=False).cpu().numpy()
+    f_raw, _ = eng.mfcc_features(clips, normalize=False, add_pitch=False)
+    f_raw = f_raw.cpu().numpy()
+    assert f_raw.shape == (6, 64)
+    for i in range(6):
+        assert mel_ok(mel_raw[i], port.melspec_image(clips[i], 22050, normalize=False).numpy())
+        ref_p = port.melspec_image(clips[i], 22050, normalize=True, to_db=False).numpy()
+        assert np.all(np.abs(mel_pow[i] - ref_p) <= 1e-4 * np.maximum(np.abs(ref_p), 1e-5 * ref_p.max())), i
+        ref_f = port.mfcc_vector(clips[i], 22050, 64, normalize=False, add_pitch=False)
+        assert ref_f.shape == (64,) and mfcc_ok(f_raw[i], ref_f)
+    # the reference API with the switches in the config dicts
+    fb = MelFeatureBuilder(device="cuda:0")
+    mf_cfg = dict(N_MFCC=64, NORMALIZE_AUDIO_VOLUME=False, ADD_PITCH_FEATURES=False)
+    ms_cfg = dict(N_MELS=64, N_FFT=2048, HOP_LENGTH=256, NORMALIZE_AUDIO_VOLUME=False)
+    a, m = fb.extract_inference_features_from_audio(clips[2], 22050, mf_cfg, ms_cfg, None, melspec_to_db=False)
+    wa, wm = port.extract_inference_features_from_audio(clips[2], 22050, mf_cfg, ms_cfg, None, melspec_to_db=False)
+    assert a.shape == wa.shape == (1, 64) and m.shape == wm.shape
+    assert mfcc_ok(a[0], wa[0]) and np.all(np.abs(m - wm) <= 1e-4 * np.maximum(np.abs(wm), 1e-5 * wm.max()))
+    # fused path with the switches: an MLP without the pitch column
+    from guitar_audio_transcriber_ai_b200.engine import Engine
+    from guitar_audio_transcriber_ai_b200.checkpoint import load_checkpoint
+    from guitar_audio_transcriber_ai_b200.training.mlp_trainer import MLP
+    torch.manual_seed(0)
+    mlp = MLP(num_features=64, hidden_dim=128, num_hidden_layers=2, num_classes=47).eval()
+    cnn_ck = load_checkpoint(CKPT / "cnn_synth_sr22050.ckpt")
+    mlp_ck = {"model": mlp.state_dict(), "reverse_map": load_checkpoint(CKPT / "mlp_synth_sr22050.ckpt")["reverse_map"]}
+    e2 = Engine(22050, device="cuda:0")
+    e2.load_cnn(cnn_ck["model"]); e2.load_mlp(mlp_ck["model"])
+    with pytest.raises(ValueError, match="64 inputs"):
+        e2.transcribe_clips(clips)                                   # 65 feature columns into a 64-input MLP: refused
+    out = e2.transcribe_clips(clips, add_pitch=False, normalize_mfcc=False, normalize_mel=False, return_features=True)
+    X = np.vstack([port.mfcc_vector(c, 22050, 64, normalize=False, add_pitch=False) for c in clips])
+    M = port.extract_melspec_features(list(clips), 22050, 64, 2048, 256, normalize=False)
+    want = port.predict(mlp_ck, cnn_ck, X, M)
+    assert out["indices"].cpu().numpy().tolist() == want["indices"].tolist()
+    assert np.abs(out["probs"].cpu().numpy() - want["probs"]).max() <= 5e-5
+    e2.close()
+
+
+def test_mlp_width_is_checked_at_the_c_abi(tr22):
+    """gat_transcribe_clips must refuse an MLP whose input width differs from the feature row width."""
+    import ctypes as C
+    from guitar_audio_transcriber_ai_b200 import _lib
+    from guitar_audio_transcriber_ai_b200.engine import Engine
+    from guitar_audio_transcriber_ai_b200.checkpoint import load_checkpoint
+    eng = Engine(22050, mfcc_config={"N_MFCC": 32}, device="cuda:0")          # 33 feature columns
+    eng.load_cnn(load_checkpoint(CKPT / "cnn_synth_sr22050.ckpt")["model"])
+    eng.load_mlp(load_checkpoint(CKPT / "mlp_synth_sr22050.ckpt")["model"])   # 65 inputs
+    a = torch.zeros((2, 11025), device="cuda:0")
+    K = eng.num_classes
+    bufs = [torch.empty((2, K), device="cuda:0") for _ in range(3)]
+    idx, conf = torch.empty(2, dtype=torch.int64, device="cuda:0"), torch.empty(2, device="cuda:0")
+    rc = eng.lib.gat_transcribe_clips(eng._ctx, _lib.ptr(a), 2, 11025, 0, _lib.ptr(bufs[0]), _lib.ptr(bufs[1]), _lib.ptr(bufs[2]),
+                                      _lib.ptr(idx), _lib.ptr(conf), None, None, None, None)
+    assert rc != 0 and b"65 inputs" in eng.lib.gat_last_error()
+    with pytest.raises(ValueError):
+        eng.transcribe_clips(a)
+    eng.close()
+
+
+def test_two_predictors_do_not_share_weights():
+    """stand-alone NotePredictors own their contexts; loading a second one leaves the first intact."""
+    import port
+    from guitar_audio_transcriber_ai_b200 import synth
+    from guitar_audio_transcriber_ai_b200.note_predictor import NotePredictor
+    from guitar_audio_transcriber_ai_b200.checkpoint import load_checkpoint
+    mlp_ck, cnn_ck = load_checkpoint(CKPT / "mlp_synth_sr22050.ckpt"), load_checkpoint(CKPT / "cnn_synth_sr22050.ckpt")
+    clips, _ = synth.clip_batch(3, 0.5, 22050, seed0=5)
+    feats = [port.extract_inference_features_from_audio(c, 22050) for c in clips]
+    X = np.vstack([f[0] for f in feats]); M = np.concatenate([f[1] for f in feats])
+    p1 = NotePredictor(device="cuda:0"); p1.load_models(mlp_ck, cnn_ck)
+    before = p1.predict(X, M)
+    other = dict(cnn_ck); other["model"] = {k: (v * 0.5 if v.dtype.is_floating_point else v) for k, v in cnn_ck["model"].items()}
+    p2 = NotePredictor(device="cuda:0"); p2.load_models(mlp_ck, other)
+    assert p2.engine is not p1.engine
+    after = p1.predict(X, M)
+    assert np.array_equal(before["probs"], after["probs"])
+    assert not np.array_equal(p2.predict(X, M)["probs"], before["probs"])
+
+
+def test_cli_on_gpu(tmp_path, capsys):
+    """f3: transcribe_cli.main on a WAV file (transcribe_cli.py:16-114): console table, results file, clip files."""
+    import file_cases
+    from guitar_audio_transcriber_ai_b200 import transcribe_cli
+    from guitar_audio_transcriber_ai_b200.audio import wavio
+    from conftest import GOLD
+    g = np.load(GOLD / "files.npz")
+    wav = file_cases.write_case(tmp_path, "mono22050").rename(tmp_path / "take.wav")
+    res = transcribe_cli.main(["--audio", str(wav), "--out", str(tmp_path / "out"), "--save_results", "--save_clips",
+                               "--mlp_ckpt", "mlp_synth_sr22050.ckpt", "--cnn_ckpt", "cnn_synth_sr22050.ckpt",
+                               "--mlp_root", str(CKPT), "--cnn_root", str(CKPT), "--device", "cuda:0"])
+    printed = capsys.readouterr().out
+    labels = [str(s) for s in g["mono22050_labels"]]
+    assert [str(s) for s in res["labels"]] == labels
+    lines = [ln for ln in printed.splitlines() if ln[:3].isdigit()]
+    assert len(lines) == len(labels)
+    for i, (ln, lab) in enumerate(zip(lines, labels)):
+        assert ln.startswith(f"{i:03d}  {lab:>4}  (conf={res['confidences'][i]:.2f})  {res['dsp_info'][i][1]['note_name']}")
+    txt = (tmp_path / "out" / "take_transcription.txt").read_text(encoding="utf-8").splitlines()
+    assert txt[:len(labels)] == [f"{i},{lab},{res['confidences'][i]:.4f}" for i, lab in enumerate(labels)]
+    assert "Full result dict:" in txt
+    clips = sorted((tmp_path / "out").rglob("*_clip__*.wav")) or sorted((tmp_path / "out").rglob("*.wav"))
+    assert len(clips) == len(labels)
+    frames, sr = wavio.read_wav_frames(clips[0])
+    assert sr == 22050 and frames.dtype == np.int16 and frames.shape[0] == 11025
+    with pytest.raises(ValueError):
+        transcribe_cli.main(["--audio", str(tmp_path / "out" / "take_transcription.txt")])
+    with pytest.raises(FileNotFoundError):
+        transcribe_cli.main(["--audio", str(tmp_path / "missing.wav")])
+
+
+@pytest.mark.parametrize("n_fft", [1024, 4096])
+@pytest.mark.parametrize("dur", [2.0, 4.0])
+def test_sweep_corners_against_torchaudio(n_fft, dur):
+    """BASELINE config 5's corners (n_fft 1024 / 4096 x 2 s / 4 s): mel image vs genuine torchaudio, CNN labels and
+    probabilities vs torch."""
+    import port
+    from guitar_audio_transcriber_ai_b200 import synth
+    from guitar_audio_transcriber_ai_b200.engine import Engine
+    from guitar_audio_transcriber_ai_b200.checkpoint import load_checkpoint
+    cnn_ck = load_checkpoint(CKPT / "cnn_synth_sr22050.ckpt")
+    eng = Engine(22050, {"N_MELS": 64, "N_FFT": n_fft, "HOP_LENGTH": 256}, device="cuda:0")
+    eng.load_cnn(cnn_ck["model"])
+    clips, _ = synth.clip_batch(4, dur, 22050, seed0=int(n_fft + dur))
+    out = eng.transcribe_clips(clips, skip_mlp=True, return_features=True)
+    with torch.inference_mode():
+        X = port.extract_melspec_features(list(clips), 22050, 64, n_fft, 256, normalize=True)
+        probs = torch.softmax(port.cnn_forward(cnn_ck["model"], X), -1).numpy()
+    mel = out["mel"].cpu().numpy()
+    for i in range(len(clips)):
+        assert mel_ok(mel[i], X[i].numpy()), (n_fft, dur, i, np.abs(mel[i] - X[i].numpy()).max())
+    assert out["indices"].cpu().numpy().tolist() == probs.argmax(1).tolist()
+    assert np.abs(out["probs"].cpu().numpy() - probs).max() <= 5e-5
+    eng.close()

@@ -169,3 +169,50 @@ def test_label_all_gather_world_size_2():
     assert idx.tolist() == [i % 47 for i in range(n_total)]
     assert torch.allclose(conf, (torch.arange(n_total, dtype=torch.float32) + 0.5) / n_total)
     assert start.tolist() == [10 * i for i in range(n_total)] and end.tolist() == [10 * i + 5 for i in range(n_total)]
+
+
+def _sharded_worker(rank, world, port_no, q):
+    """One rank of the sharded entry points on CPU: gloo + the host-emulated kernels (tests/emu)."""
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT / "tests" / "emu"))
+    import emu_loader
+    emu_loader.install()
+    from guitar_audio_transcriber_ai_b200 import Transcriber, synth
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no))
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    ck = ROOT / "tests" / "golden" / "ckpt"
+    tr = Transcriber("mlp_synth_sr22050.ckpt", "cnn_synth_sr22050.ckpt", ck, ck, device="cpu")
+    Y = np.stack([synth.phrase(s, sr=22050, dur=2.0, n_notes=4)[0] for s in (0, 1, 2)])
+    a = tr.transcribe_phrases_sharded(Y, 0.5)
+    clips, _ = synth.clip_batch(5, 0.5, 22050, 40)
+    b = tr.transcribe_notes_sharded(clips, 0.5, 22050)
+    c = tr.transcribe_audio_sharded(Y[:2].reshape(-1), 22050, 0.5)
+    keep = lambda r: {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in r.items() if k not in ("local_probs",)}
+    q.put((rank, keep(a), keep(b), keep(c)))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def test_sharded_entry_points_world_size_2_equal_world_size_1():
+    """transcribe_phrases_sharded / transcribe_notes_sharded / transcribe_audio_sharded: both ranks of a world-size-2
+    gloo run return the same result, and it equals the single-process result bit for bit (labels, confidences, slice
+    tables, onsets, YIN) - the kernels run through the host emulation here, through CUDA in tests/test_gpu_parity.py."""
+    if torch.cuda.is_available():
+        pytest.skip("a real GPU is present: the CUDA 2-rank test covers this")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, 29613, q)) for r in range(2)]
+    procs.append(ctx.Process(target=_sharded_worker, args=(0, 1, 29615, q)))
+    [p.start() for p in procs]
+    got = [q.get(timeout=600) for _ in procs]
+    [p.join(60) for p in procs]
+    strip = lambda r: {k: v for k, v in r.items() if k != "local_range"}
+    for part in (1, 2, 3):
+        ref = strip(got[0][part])
+        assert len(ref["labels"]) > 0
+        for g in got[1:]:
+            assert strip(g[part]) == ref
+    ranges = sorted(g[1]["local_range"] for g in got)
+    assert ranges == [(0, 2), (0, 3), (2, 3)]
