@@ -2,8 +2,9 @@
 //
 //   reference call sites (paths under /root/reference/version_1/source):
 //     audio/features.py:124-126   _normalize_audio_volume          -> clip_scale_kernel
-//     audio/features.py:296-316   torchaudio MelSpectrogram + dB    -> stft_mel_kernel<float, kImage>
-//     audio/features.py:187-193   librosa.feature.mfcc + time-mean  -> stft_mel_kernel<float, kSpec> + mfcc_finish_kernel
+//     audio/features.py:296-316   torchaudio MelSpectrogram + dB    -> stft_frames_kernel (stft2.cuh) at n_fft 2048,
+//                                                                      stft_mel_kernel<float, kImage> at 512 / 1024 / 4096
+//     audio/features.py:187-193   librosa.feature.mfcc + time-mean  -> stft_frames_kernel (stft2.cuh; n_fft 2048)
 //     audio/slicing.py:107        librosa.onset.onset_strength      -> stft_mel_kernel<double, kSpec> (+ onset.cuh)
 //
 // One persistent kernel serves all three: a CTA takes (clip, chunk of frames) work items, stages the
@@ -290,45 +291,6 @@ __global__ void clip_scale_kernel(const float* __restrict__ audio, long long n, 
             const float mean = (float)(v / (double)n);
             scale_out[blockIdx.x] = __fadd_rn(sqrtf(mean), 1e-9f);
         }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// librosa.power_to_db top_db clamp (max over the clip) + time-mean + DCT-II(ortho), first n_mfcc rows.
-// DCT and time-mean are both linear, so mean_t DCT(S[:,t]) == DCT(mean_t S[:,t]): one 64x128 product per
-// CLIP instead of per frame.  One CTA (128 threads) per clip; thread m owns mel band m.
-struct MfccFinishParams {
-    const float* spec;        // [N][T][128] mel dB (before the top_db clamp)
-    const long long* spec_max;
-    int T;
-    int n_mels;               // 128
-    int n_mfcc;
-    const float* dct;         // [n_mfcc][n_mels]
-    float top_db;             // 80
-    float* out;               // [N][ld]
-    int ld;
-};
-
-__global__ void mfcc_finish_kernel(MfccFinishParams p) {
-    __shared__ float mean_s[128];
-    const int clip = blockIdx.x;
-    const int m = threadIdx.x;
-    const float floor_db = (float)from_ordered_bits(p.spec_max[clip]) - p.top_db;
-    if (m < p.n_mels) {
-        const float* s = p.spec + (long long)clip * p.T * p.n_mels + m;
-        float acc = 0.0f;
-        for (int t = 0; t < p.T; ++t) {
-            const float v = s[(long long)t * p.n_mels];
-            acc += v > floor_db ? v : floor_db;
-        }
-        mean_s[m] = acc / (float)p.T;
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < p.n_mfcc; k += blockDim.x) {
-        const float* d = p.dct + (long long)k * p.n_mels;
-        float acc = 0.0f;
-        for (int j = 0; j < p.n_mels; ++j) acc += d[j] * mean_s[j];
-        p.out[(long long)clip * p.ld + k] = acc;
     }
 }
 

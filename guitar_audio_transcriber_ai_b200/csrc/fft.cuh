@@ -16,7 +16,10 @@
 
 namespace gat {
 
-template <typename T> struct Cpx { T x, y; };
+// 2*sizeof(T)-aligned so that every complex load / store is ONE 64-bit (float) or 128-bit (double) access: with the
+// natural 4-byte alignment the compiler split them into pairs of 32-bit shared-memory accesses (2-way bank conflicts
+// on the stride-2 patterns, twice the LSU instructions).
+template <typename T> struct __align__(2 * sizeof(T)) Cpx { T x, y; };
 
 template <typename T> __device__ __forceinline__ Cpx<T> cadd(Cpx<T> a, Cpx<T> b) { return Cpx<T>{a.x + b.x, a.y + b.y}; }
 template <typename T> __device__ __forceinline__ Cpx<T> csub(Cpx<T> a, Cpx<T> b) { return Cpx<T>{a.x - b.x, a.y - b.y}; }

@@ -15,6 +15,7 @@ using std::min;
 #include "frontend.cuh"
 #include "infer.cuh"
 #include "onset.cuh"
+#include "stft2.cuh"
 #include "yin.cuh"
 
 #include <algorithm>
@@ -154,7 +155,7 @@ struct gat_ctx {
     gat_config cfg{};
     int64_t launches = 0;
     // tables
-    DevBuf tw32, w2_32, tw64, w2_64, tw_mel, w2_mel, win_mel, win_mel_half, win_mfcc, win64, dct;
+    DevBuf tw32, w2_32, tw64, w2_64, tw_mel, w2_mel, win_mel, win_mel_half, win_mfcc_half, win64, dct;
     SparseFbDev fb_mel, fb_mfcc;
     // models
     DevBuf mlp_params; int mlp_dims[kMlpMaxLayers + 1] = {0}; int mlp_n_linear = 0; int mlp_n_params = 0;
@@ -169,7 +170,7 @@ struct gat_ctx {
     DevBuf scaler_mean, scaler_scale; int scaler_n = 0;
     float w_mlp = 0.2f, w_cnn = 0.8f;
     // scratch
-    DevBuf clip_scale, spec, spec_max, f0, act1, act2, act3, hz_tmp, logits_cnn, logits_mlp;
+    DevBuf clip_scale, spec, spec_max, clip_count, f0, act1, act2, act3, hz_tmp, logits_cnn, logits_mlp;
     long long act_shape[3] = {0, 0, 0};   // (chunk, H, W) the zero borders of act1/act2 were prepared for
     DevBuf seg_small, seg_rms, seg_rms_med, seg_gate, seg_env, seg_envn, seg_cand, seg_peaks, seg_frames, seg_table,
            seg_keep, seg_dest, seg_base, seg_counts;
@@ -353,7 +354,8 @@ extern "C" int gat_ctx_create(const gat_config* cfg, int device, gat_ctx** out) 
     std::vector<float> win_half(cfg->mel_n_fft);
     for (int i = 0; i < cfg->mel_n_fft; ++i) win_half[i] = 0.5f * cfg->mel_window[i];
     rc |= upload(c->win_mel_half, win_half.data(), win_half.size());
-    rc |= upload(c->win_mfcc, win_mfcc.data(), 2048);
+    for (float& w : win_mfcc) w *= 0.5f;       // the Hermitian split's 1/2, exact
+    rc |= upload(c->win_mfcc_half, win_mfcc.data(), 2048);
     rc |= upload(c->win64, cfg->stft_window, 2048);
     rc |= upload(c->dct, cfg->dct, (size_t)cfg->mfcc_n_mfcc * cfg->mfcc_n_mels);
     rc |= build_sparse_fb(c->fb_mel, cfg->mel_fb, cfg->mel_n_mels, cfg->mel_n_fft / 2 + 1, 1, cfg->mel_n_mels);
@@ -365,7 +367,7 @@ extern "C" int gat_ctx_create(const gat_config* cfg, int device, gat_ctx** out) 
 
 extern "C" void gat_ctx_destroy(gat_ctx* c) {
     if (!c) return;
-    DevBuf* all[] = {&c->tw_mel, &c->w2_mel, &c->win_mel_half, &c->tw32, &c->w2_32, &c->tw64, &c->w2_64, &c->win_mel, &c->win_mfcc, &c->win64, &c->dct,
+    DevBuf* all[] = {&c->tw_mel, &c->w2_mel, &c->win_mel_half, &c->win_mfcc_half, &c->clip_count, &c->tw32, &c->w2_32, &c->tw64, &c->w2_64, &c->win_mel, &c->win64, &c->dct,
                      &c->fb_mel.start, &c->fb_mel.len, &c->fb_mel.off, &c->fb_mel.mel, &c->fb_mel.w,
                      &c->fb_mfcc.start, &c->fb_mfcc.len, &c->fb_mfcc.off, &c->fb_mfcc.mel, &c->fb_mfcc.w,
                      &c->mlp_params, &c->conv_w_tc[1], &c->conv_w_tc[2], &c->fc1_w_tc, &c->feat_planes, &c->hid, &c->tc_debug_buf, &c->conv_w[0], &c->conv_w[1], &c->conv_w[2], &c->conv_b[0], &c->conv_b[1], &c->conv_b[2],
@@ -520,11 +522,71 @@ int launch_stft_mel(gat_ctx* c, StftMelParams<T> p, void* stream) {
     return 0;
 }
 
+// Frame-per-warp kernel (csrc/stft2.cuh) for the float chains at n_fft 2048: image only, MFCC only, or both off one FFT.
+int launch_stft_frames(gat_ctx* c, StftFramesParams p, void* stream) {
+    const long long n_items = (long long)p.N * (p.fa + p.fb_items);
+    if (n_items <= 0) return 0;
+    const int nnz1 = p.img ? p.fb.nnz : 0, nnz2 = p.spec ? p.fb2.nnz : 0;
+    if (!p.img) p.fb.nnz = 0;
+    if (!p.spec) p.fb2.nnz = 0;
+    const size_t budget = 227 * 1024;
+    const int threads = stft_frames_smem_bytes(20, nnz1 + 3, nnz2 + 3) <= budget ? 640 : 512;
+    const size_t smem = stft_frames_smem_bytes(threads / 32, nnz1 + 3, nnz2 + 3);
+    if (smem > budget) return fail("stft_frames: %zu bytes of shared memory needed", smem);
+    // contiguous item ranges per CTA; enough CTAs that a short call (a single note) still spreads over the SMs
+    const int nwarps = threads / 32;
+    long long ctas = (n_items + nwarps - 1) / nwarps;
+    ctas = ctas < c->num_sms ? ctas : c->num_sms;
+    p.items_per_cta = (n_items + ctas - 1) / ctas;
+    ctas = (n_items + p.items_per_cta - 1) / p.items_per_cta;
+    KNAME(p.img && p.spec ? "stft_frames_dual" : (p.img ? "stft_frames_image" : "stft_frames_mfcc"));
+    if (threads == 640) {
+        auto kfn = stft_frames_kernel<640>;
+        GAT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LAUNCH(c, kfn, (unsigned)ctas, 640, smem, stream, p);
+    } else {
+        auto kfn = stft_frames_kernel<512>;
+        GAT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LAUNCH(c, kfn, (unsigned)ctas, 512, smem, stream, p);
+    }
+    return 0;
+}
+
+// Fills the chain-independent fields and the two chains' halves of StftFramesParams.
+void stft_frames_common(gat_ctx* c, StftFramesParams& p, const float* audio, int64_t N, int64_t n, bool dual_or_img) {
+    p.audio = audio; p.n = n; p.N = (int)N; p.clip_scale = c->clip_scale.as<float>();
+    p.window_half = dual_or_img ? c->win_mel_half.as<float>() : c->win_mfcc_half.as<float>();
+    p.tw = c->tw32.as<Cpx<float>>(); p.w2 = c->w2_32.as<Cpx<float>>();
+    p.amin = 1e-10f;
+}
+void stft_frames_image(gat_ctx* c, StftFramesParams& p, int64_t n, bool normalize, bool power_out, float* out) {
+    p.img = 1; p.hop = c->cfg.mel_hop; p.T = (int)(1 + n / c->cfg.mel_hop); p.fb = c->fb_mel.view();
+    p.norm_img = normalize ? 1 : 0; p.power_out = power_out ? 1 : 0; p.out = out; p.fa = p.T;
+}
+int stft_frames_spec(gat_ctx* c, StftFramesParams& p, int64_t N, int64_t n, bool normalize, float* out, int ld, void* stream) {
+    const int T2 = (int)(1 + n / 512);
+    if (c->spec.ensure((size_t)N * T2 * 128 * sizeof(float)) || c->clip_count.ensure((size_t)N * sizeof(unsigned))) return 1;
+    GAT_CUDA(cudaMemsetAsync(c->clip_count.p, 0, (size_t)N * sizeof(unsigned), (cudaStream_t)stream));
+    p.spec = 1; p.T2 = T2; p.fb2 = c->fb_mfcc.view(); p.norm_spec = normalize ? 1 : 0;
+    p.spec_scratch = c->spec.as<float>(); p.clip_count = c->clip_count.as<unsigned>();
+    p.dct = c->dct.as<float>(); p.n_mfcc = c->cfg.mfcc_n_mfcc; p.top_db = 80.0f; p.mfcc_out = out; p.ld = ld;
+    p.share_stride = 0; p.u_lo = 0; p.u_hi = 0; p.fb_items = T2;
+    return 0;
+}
+
 int run_melspec(gat_ctx* c, const float* audio, int64_t N, int64_t n, bool normalize, bool scale_ready, float* out, void* stream,
                 bool power_out = false) {
     const int n_fft = c->cfg.mel_n_fft;
     if (n <= n_fft / 2) return fail("melspec: clips of %lld samples are too short for reflect padding of %d", (long long)n, n_fft / 2);
     if (normalize && !scale_ready && launch_clip_scale(c, audio, N, n, stream)) return 1;
+#ifndef GAT_CPU_EMU_OLD_STFT
+    if (n_fft == kStft2N) {      // the reference's N_FFT: frame-per-warp kernel
+        StftFramesParams q{};
+        stft_frames_common(c, q, audio, N, n, true);
+        stft_frames_image(c, q, n, normalize, power_out, out);
+        return launch_stft_frames(c, q, stream);
+    }
+#endif
     StftMelParams<float> p{};
     p.audio = audio; p.n = n; p.N = (int)N; p.clip_scale = normalize ? c->clip_scale.as<float>() : nullptr;
     p.frame_gate = nullptr; p.sample_gate = 0.0f; p.gate_hop = 512;
@@ -542,22 +604,32 @@ int run_melspec(gat_ctx* c, const float* audio, int64_t N, int64_t n, bool norma
 }
 
 int run_mfcc(gat_ctx* c, const float* audio, int64_t N, int64_t n, bool normalize, bool scale_ready, float* out, int ld, void* stream) {
-    const int T = (int)(1 + n / 512);
     if (normalize && !scale_ready && launch_clip_scale(c, audio, N, n, stream)) return 1;
-    if (c->spec.ensure((size_t)N * T * 128 * sizeof(float)) || c->spec_max.ensure((size_t)N * sizeof(long long))) return 1;
-    GAT_CUDA(cudaMemsetAsync(c->spec_max.p, 0x80, (size_t)N * sizeof(long long), (cudaStream_t)stream));
-    StftMelParams<float> p{};
-    p.audio = audio; p.n = n; p.N = (int)N; p.clip_scale = normalize ? c->clip_scale.as<float>() : nullptr;
-    p.frame_gate = nullptr; p.sample_gate = 0.0f; p.gate_hop = 512;
-    p.hop = 512; p.n_frames = T; p.pad_mode = kPadZero;
-    p.window = c->win_mfcc.as<float>(); p.tw = c->tw32.as<Cpx<float>>(); p.w2 = c->w2_32.as<Cpx<float>>();
-    p.fb = c->fb_mfcc.view(); p.amin = 1e-10f; p.out = c->spec.as<float>(); p.spec_max = c->spec_max.as<long long>();
-    if (launch_stft_mel<float, kOutSpec, 512, 32>(c, p, stream)) return 1;
-    MfccFinishParams f{};
-    f.spec = c->spec.as<float>(); f.spec_max = c->spec_max.as<long long>(); f.T = T; f.n_mels = 128;
-    f.n_mfcc = c->cfg.mfcc_n_mfcc; f.dct = c->dct.as<float>(); f.top_db = 80.0f; f.out = out; f.ld = ld;
-    LAUNCH(c, mfcc_finish_kernel, (unsigned)N, 128, 0, stream, f);
-    return 0;
+    StftFramesParams q{};
+    stft_frames_common(c, q, audio, N, n, false);
+    if (stft_frames_spec(c, q, N, n, normalize, out, ld, stream)) return 1;
+    return launch_stft_frames(c, q, stream);
+}
+
+// Image + MFCC off ONE FFT per image frame (gat_transcribe_clips): possible when both chains transform 2048-sample
+// frames and the MFCC hop (512) is a multiple of the image hop.
+bool can_fuse_chains(const gat_ctx* c) { return c->cfg.mel_n_fft == kStft2N && c->cfg.mel_hop <= 512 && 512 % c->cfg.mel_hop == 0; }
+
+int run_dual(gat_ctx* c, const float* audio, int64_t N, int64_t n, bool norm_mel, bool norm_mfcc, float* mel, float* mfcc, int ld, void* stream) {
+    if (n <= kStft2N / 2) return fail("melspec: clips of %lld samples are too short for reflect padding of %d", (long long)n, kStft2N / 2);
+    StftFramesParams q{};
+    stft_frames_common(c, q, audio, N, n, true);
+    stft_frames_image(c, q, n, norm_mel, false, mel);
+    if (stft_frames_spec(c, q, N, n, norm_mfcc, mfcc, ld, stream)) return 1;
+    // spec frames [u_lo, u_hi) touch no padding and ride on image frame u * stride; the others get their own zero-padded FFT
+    q.share_stride = 512 / c->cfg.mel_hop;
+    const int u_lo = 2;                                                    // 512 u >= 1024
+    long long u_hi = n >= kStft2N ? (n - kStft2N / 2) / 512 + 1 : 0;       // 512 u + 1024 <= n
+    u_hi = u_hi > q.T2 ? q.T2 : u_hi;
+    q.u_lo = u_lo < q.T2 ? u_lo : q.T2;
+    q.u_hi = (int)(u_hi < q.u_lo ? q.u_lo : u_hi);
+    q.fb_items = q.u_lo + (q.T2 - q.u_hi);
+    return launch_stft_frames(c, q, stream);
 }
 
 template <int kLPT>
@@ -1033,7 +1105,9 @@ extern "C" int gat_transcribe_clips(gat_ctx* c, const float* audio, int64_t N, i
     // one RMS pass serves all three chains (the reference recomputes it per chain: features.py:185,311,460,497)
     const bool any_norm = norm_mel || (!skip_mlp && norm_mfcc);
     if (any_norm && launch_clip_scale(c, audio, N, n, stream)) return 1;
-    if (run_melspec(c, audio, N, n, norm_mel, true, mel, stream)) return 1;
+    const bool fused = !skip_mlp && can_fuse_chains(c);
+    if (fused) { if (run_dual(c, audio, N, n, norm_mel, norm_mfcc, mel, mfcc, F, stream)) return 1; }
+    else if (run_melspec(c, audio, N, n, norm_mel, true, mel, stream)) return 1;
     if (skip_mlp) {
         if (run_cnn(c, mel, N, T, probs, cnn_logits, stream)) return 1;
         if (cnn_probs && cnn_probs != probs)
@@ -1041,7 +1115,7 @@ extern "C" int gat_transcribe_clips(gat_ctx* c, const float* audio, int64_t N, i
         LAUNCH(c, argmax_kernel, (unsigned)((N + 7) / 8), 256, 0, stream, probs, (int)N, classes, (long long*)index, conf);
         return 0;
     }
-    if (run_mfcc(c, audio, N, n, norm_mfcc, true, mfcc, F, stream)) return 1;
+    if (!fused && run_mfcc(c, audio, N, n, norm_mfcc, true, mfcc, F, stream)) return 1;
     if (add_pitch || yin_hz) {
         // features.py:473 hands YIN the (normalised, when the MFCC chain normalises) clip; :201 the raw one
         const bool yn = norm_mfcc && (flags & GAT_FLAG_YIN_ON_NORMALIZED) != 0;

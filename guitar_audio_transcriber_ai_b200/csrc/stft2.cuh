@@ -1,0 +1,294 @@
+// Frame-per-warp STFT -> mel -> dB for the float32 feature chains at n_fft = 2048 (the reference's MelSpecConfig.N_FFT and
+// librosa's default), round 2 of the kernel behind
+//     audio/features.py:296-316, :486-502   torchaudio MelSpectrogram + AmplitudeToDB   (image chain, HTK mel, reflect pad)
+//     audio/features.py:187-193, :462-468   librosa.feature.mfcc(...).mean(axis=1)      (spec chain, Slaney mel-128, zero pad)
+//
+// What changed against stft_mel_kernel (features.cuh), which stays for the float64 onset chain and the other n_fft:
+//   * NO block-level staging and NO block barriers.  A warp owns a frame from the first load to the last store: its 2048
+//     samples come straight from global memory into the FFT's registers (32 coalesced 64-bit loads per lane; the 8x
+//     overlap between neighbouring frames is served by L1/L2, HBM still sees every sample once), so warps drift apart
+//     and one warp's shared-memory phases (transpose, mel gather) overlap another's butterflies.  The old kernel ran one
+//     frame per warp per 16-frame chunk between three __syncthreads, all warps in the same phase at the same time: ncu
+//     showed it waiting on the shared-memory pipe (951 wavefronts per frame, stalls: short scoreboard + MIO throttle).
+//   * Volume normalisation costs nothing: |FFT(x / c)|^2 = |FFT(x)|^2 / c^2, so the raw samples are transformed and the
+//     mel power is scaled by (1/c)^2 once per mel bin.  (Rounding differs from dividing every sample at the 1e-7
+//     relative level, three orders inside the stated dB tolerance.)  No per-sample IEEE division, no staging buffer.
+//   * ONE FFT, TWO filterbanks: interior MFCC frames (hop 512) see exactly the samples of every other image frame
+//     (hop 256), so in the fused call the Slaney-128 bank is applied to the spectrum the image frame already has; only
+//     the frames that touch the clip's ends (zero vs reflect padding: 2 + 2 of 44 at 1 s) get their own FFT.  The shared
+//     frames use the image chain's window (torch.hann_window, float32), which differs from librosa's float64 Hann by
+//     <= 2e-7: at -140 dB re the frame's peak, far below MFCC's 80 dB top_db clamp.
+//   * The MFCC finish (top_db clamp against the clip's maximum, time mean, DCT-II) runs in the same kernel: the warp that
+//     delivers a clip's last spectrum frame (global arrival counter) reads the clip's [T][128] mel-dB rows back while
+//     they are still in L2 and writes the 64 coefficients.  No second kernel, no HBM read of the intermediate.
+#pragma once
+#include "features.cuh"
+
+namespace gat {
+
+struct StftFramesParams {
+    const float* audio; long long n; int N;
+    const float* clip_scale;       // [N] c = rms + 1e-9, read when norm_img / norm_spec
+    const float* window_half;      // [2048] 0.5 * window (the Hermitian split's 1/2 folded in, exact)
+    const Cpx<float>* tw; const Cpx<float>* w2;
+    // ---- image chain: reflect padding, hop `hop`, out[(clip*n_mels + m)*T + t]
+    int img; int hop; int T;
+    SparseFb fb; int norm_img; int power_out; float amin; float* out;
+    // ---- spec chain (MFCC): zero padding, hop 512
+    int spec; int T2;
+    int share_stride;              // image frames per spec frame (512 / hop) when the chains share FFTs, else 0
+    int u_lo, u_hi;                // spec frames u in [u_lo, u_hi) touch no padding: they ride on image frame u * share_stride
+    SparseFb fb2; int norm_spec;
+    float* spec_scratch;           // [N][T2][128] mel dB (L2-resident between the write and the finish)
+    unsigned* clip_count;          // [N] arrival counters, zeroed by the launcher
+    const float* dct; int n_mfcc; float top_db; float* mfcc_out; int ld;
+    // ---- work items: per clip `fa` image frames then `fb_items` spec-only frames
+    int fa, fb_items;
+    long long items_per_cta;
+};
+
+constexpr int kStft2P = 32;
+constexpr int kStft2N = 2048;
+
+__host__ __device__ inline size_t stft_frames_smem_bytes(int nwarps, int nnz1, int nnz2) {
+    size_t b = sizeof(FftTables<float, kStft2P>) + kStft2N * sizeof(float);
+    b += (size_t)2 * 4 * kMaxMelsPerLane * 32 * sizeof(int) + ((size_t)nnz1 + nnz2) * sizeof(float) + 32;
+    b += (size_t)nwarps * FftGeom<kStft2P>::kXbufElems * sizeof(Cpx<float>);
+    return b + 64;
+}
+
+struct FbShared { const int* start; const int* len; const int* off; const int* mel; const float* w; };
+
+// Banded-sparse filterbank over the power spectrum `pf` (see SparseFb): lane-slot form, four bins per step, four
+// independent accumulators (the gather is latency-bound on its FFMA chain otherwise).
+template <typename Store>
+__device__ __forceinline__ void apply_filterbank(const float* pf, const FbShared& fb, int n_slots, int lane, float scale,
+                                                 float amin, bool power_out, Store&& store) {
+    for (int q = 0; q < n_slots; ++q) {
+        const int e = q * 32 + lane;
+        const int m = fb.mel[e];
+        const int ln = fb.len[e];
+        const float4* pb = reinterpret_cast<const float4*>(pf + fb.start[e]);
+        const float4* w = reinterpret_cast<const float4*>(fb.w + fb.off[e]);
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll 2
+        for (int k = 0; k < ln; ++k) {
+            const float4 pv = pb[k];
+            const float4 wv = w[k];
+            a0 = fmaf(pv.x, wv.x, a0); a1 = fmaf(pv.y, wv.y, a1);
+            a2 = fmaf(pv.z, wv.z, a2); a3 = fmaf(pv.w, wv.w, a3);
+        }
+        const float acc = ((a0 + a1) + (a2 + a3)) * scale;
+        if (m >= 0) store(m, power_out ? acc : db10(acc > amin ? acc : amin));
+    }
+}
+
+// librosa.power_to_db's top_db clamp over the clip + time mean + DCT-II (ortho) rows: one warp, after the clip's last
+// spectrum frame has arrived.  Same summation orders as mfcc_finish_kernel (per mel band sequential over frames, per
+// coefficient sequential over bands).
+__device__ __forceinline__ void mfcc_finish_warp(const StftFramesParams& p, int clip, float* scratch_smem /* >= 128 floats */) {
+    const int lane = lane_id();
+    const float4* rows = reinterpret_cast<const float4*>(p.spec_scratch + (long long)clip * p.T2 * 128);
+    float mx = -3.0e38f;
+    for (int t = 0; t < p.T2; ++t) {
+#ifndef GAT_CPU_EMU
+        const float4 v = __ldcg(rows + (long long)t * 32 + lane);
+#else
+        const float4 v = rows[(long long)t * 32 + lane];
+#endif
+        mx = fmaxf(fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)), mx);
+    }
+    mx = warp_max(mx);
+    const float floor_db = mx - p.top_db;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    for (int t = 0; t < p.T2; ++t) {
+#ifndef GAT_CPU_EMU
+        const float4 v = __ldcg(rows + (long long)t * 32 + lane);
+#else
+        const float4 v = rows[(long long)t * 32 + lane];
+#endif
+        s0 += v.x > floor_db ? v.x : floor_db; s1 += v.y > floor_db ? v.y : floor_db;
+        s2 += v.z > floor_db ? v.z : floor_db; s3 += v.w > floor_db ? v.w : floor_db;
+    }
+    const float inv = (float)p.T2;
+    __syncwarp();
+    reinterpret_cast<float4*>(scratch_smem)[lane] = make_float4(s0 / inv, s1 / inv, s2 / inv, s3 / inv);
+    __syncwarp();
+    for (int k = lane; k < p.n_mfcc; k += 32) {
+        const float* d = p.dct + (long long)k * 128;
+        float acc = 0.0f;
+#pragma unroll 4
+        for (int j = 0; j < 128; ++j) acc += __ldg(d + j) * scratch_smem[j];
+        p.mfcc_out[(long long)clip * p.ld + k] = acc;
+    }
+    __syncwarp();
+}
+
+// Real FFT of one 2048-sample frame held as 32 complex registers per lane -> power spectrum in shared memory; same
+// decomposition and arithmetic as warp_rfft_power<float, 32> (fft.cuh), but the two in-lane 32-point FFTs share ONE copy
+// of the butterfly code (a rolled two-trip loop).  Warps of this kernel run unsynchronised, each somewhere else in the
+// frame's code: the per-frame instruction footprint has to fit the 32 KB L1.5 instruction cache (the first version,
+// fully unrolled with an inlined padding path, was 166 KB and ncu's top stall was "no instruction").
+__device__ __forceinline__ void frame_fft_power(Cpx<float> (&v)[32], Cpx<float>* xbuf, const FftTables<float, kStft2P>* tab) {
+    constexpr int C = 1024;
+    const int lane = lane_id();
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        fft_dif<float, 32, 0, 32>(v);
+        if (pass == 0) {
+            // twiddle by W_C^(n1*k2), n1 = lane, and transpose: row k2, column n1
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const int k2 = bitrev5(r);
+                const Cpx<float> w = tab->tw[k2 * 32 + lane];
+                xbuf[k2 * kXbufStride + lane] = (k2 == 0) ? v[r] : cmul(v[r], w);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) v[n1] = xbuf[lane * kXbufStride + n1];
+            __syncwarp();
+        }
+    }
+    // v[bitrev5(k1)] = Z[32*k1 + lane]; Hermitian partner Z[C-k] sits in lane (32 - lane) % 32 at k1' = 31 - k1
+    // (lane 0 pairs with itself at k1' = (32 - k1) % 32).  Bins k and C-k share E and T: |E+T|^2, |E-T|^2.
+    float* pb = reinterpret_cast<float*>(xbuf);
+    const int partner = (32 - lane) & 31;
+    pb[lane] = 0.0f;                                           // kPbufLead zeros below bin 0
+    if (lane < 4) pb[kPbufLead + C + 1 + lane] = 0.0f;         // tail read (times zero weights) by the vectorised mel loop
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) {
+        const Cpx<float> other = v[bitrev5(31 - k1)];
+        const Cpx<float> self = v[bitrev5((32 - k1) & 31)];
+        const float bx = __shfl_sync(0xffffffffu, other.x, partner);
+        const float by = __shfl_sync(0xffffffffu, other.y, partner);
+        const Cpx<float> b = lane == 0 ? self : Cpx<float>{bx, by};
+        const int k = 32 * k1 + lane;
+        float p_lo, p_hi;
+        split_pair_power<float>(v[bitrev5(k1)], b, tab->w2[k], p_lo, p_hi);
+        pb[kPbufLead + k] = p_lo;
+        pb[kPbufLead + C - k] = p_hi;
+    }
+    if (lane == 0) {                                           // k = C/2 pairs with itself: W^(C/2) = -i
+        const Cpx<float> a = v[bitrev5(16)];
+        const float er = a.x + a.x, orr = a.y + a.y;
+        pb[kPbufLead + C / 2] = er * er + orr * orr;
+    }
+    __syncwarp();
+}
+
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads, 1) stft_frames_kernel(StftFramesParams p) {
+    using G = FftGeom<kStft2P>;
+    GAT_DYN_SMEM(smem_raw);
+    const int nwarps = kThreads / 32;
+    const int lane = lane_id(), warp = warp_id();
+    unsigned char* sp = smem_raw;
+    FftTables<float, kStft2P>* tab = reinterpret_cast<FftTables<float, kStft2P>*>(sp);  sp += sizeof(FftTables<float, kStft2P>);
+    float* win = reinterpret_cast<float*>(sp);                 sp += kStft2N * sizeof(float);
+    constexpr int kSlotEntries = kMaxMelsPerLane * 32;
+    int* fbi = reinterpret_cast<int*>(sp);                     sp += (size_t)2 * 4 * kSlotEntries * sizeof(int);
+    float* fbw1 = reinterpret_cast<float*>(sp);                sp += ((size_t)p.fb.nnz + 3) / 4 * 4 * sizeof(float);
+    float* fbw2 = reinterpret_cast<float*>(sp);                sp += ((size_t)p.fb2.nnz + 3) / 4 * 4 * sizeof(float);
+    Cpx<float>* xbuf = reinterpret_cast<Cpx<float>*>(sp) + (size_t)warp * G::kXbufElems;
+    float* pbuf = reinterpret_cast<float*>(xbuf);
+
+    fill_fft_tables<float, kStft2P>(tab, p.tw, p.w2);
+    for (int i = threadIdx.x; i < kStft2N; i += kThreads) win[i] = p.window_half[i];
+    for (int i = threadIdx.x; i < kSlotEntries; i += kThreads) {
+        const bool l1 = p.img && i < p.fb.n_slots * 32, l2 = p.spec && i < p.fb2.n_slots * 32;
+        fbi[0 * kSlotEntries + i] = l1 ? p.fb.start[i] : 0;  fbi[1 * kSlotEntries + i] = l1 ? p.fb.len[i] : 0;
+        fbi[2 * kSlotEntries + i] = l1 ? p.fb.off[i] : 0;    fbi[3 * kSlotEntries + i] = l1 ? p.fb.mel[i] : -1;
+        fbi[4 * kSlotEntries + i] = l2 ? p.fb2.start[i] : 0; fbi[5 * kSlotEntries + i] = l2 ? p.fb2.len[i] : 0;
+        fbi[6 * kSlotEntries + i] = l2 ? p.fb2.off[i] : 0;   fbi[7 * kSlotEntries + i] = l2 ? p.fb2.mel[i] : -1;
+    }
+    if (p.img) for (int i = threadIdx.x; i < p.fb.nnz; i += kThreads) fbw1[i] = p.fb.w[i];
+    if (p.spec) for (int i = threadIdx.x; i < p.fb2.nnz; i += kThreads) fbw2[i] = p.fb2.w[i];
+    __syncthreads();          // the only block barrier: from here on every warp runs on its own
+    const FbShared fb1{fbi, fbi + kSlotEntries, fbi + 2 * kSlotEntries, fbi + 3 * kSlotEntries, fbw1};
+    const FbShared fb2{fbi + 4 * kSlotEntries, fbi + 5 * kSlotEntries, fbi + 6 * kSlotEntries, fbi + 7 * kSlotEntries, fbw2};
+    const Cpx<float>* win2 = reinterpret_cast<const Cpx<float>*>(win);
+
+    const int ipc = p.fa + p.fb_items;                              // items per clip
+    const long long n_items = (long long)p.N * ipc;
+    const long long lo = (long long)blockIdx.x * p.items_per_cta;
+    long long hi = lo + p.items_per_cta;
+    hi = hi > n_items ? n_items : hi;
+    for (long long item = lo + warp; item < hi; item += nwarps) {
+        const int clip = (int)(item / ipc);
+        const int i = (int)(item - (long long)clip * ipc);
+        // which frame: image frame t (reflect padding), possibly carrying spec frame u too; or a spec-only frame u (zero padding)
+        bool do_img = false, do_spec = false;
+        int t = 0, u = 0;
+        long long s0;
+        if (i < p.fa) {
+            do_img = true; t = i;
+            s0 = (long long)t * p.hop - kStft2N / 2;
+            if (p.share_stride > 0 && t % p.share_stride == 0) {
+                u = t / p.share_stride;
+                do_spec = u >= p.u_lo && u < p.u_hi;
+            }
+        } else {
+            do_spec = true;
+            const int e = i - p.fa;
+            u = p.share_stride > 0 ? (e < p.u_lo ? e : p.u_hi + (e - p.u_lo)) : e;
+            s0 = (long long)u * 512 - kStft2N / 2;
+        }
+        const float* src = p.audio + (long long)clip * p.n;
+
+        // ---- load the frame into the FFT's registers: z[j] = (x[2j], x[2j+1]) * window/2, j = lane + 32 r
+        Cpx<float> v[G::V];
+        const bool interior = s0 >= 0 && s0 + kStft2N <= p.n;
+        const float2* g = reinterpret_cast<const float2*>(src + s0);          // generic pointer: global here, shared below
+        if (!(interior && ((reinterpret_cast<unsigned long long>(src + s0) & 7ull) == 0ull))) {
+            // the frame touches the clip's ends (or is not 8-byte aligned): stage it through this warp's scratch with a
+            // ROLLED loop - image frames mirror at the ends (torch.stft reflect), spec-only frames see zeros (librosa)
+            const bool reflect = do_img;
+#pragma unroll 1
+            for (int e = lane; e < kStft2N; e += 32) {
+                long long s = s0 + e;
+                bool inside = s >= 0 && s < p.n;
+                if (!inside && reflect) {            // one mirror suffices: the launcher requires n > n_fft / 2
+                    const long long m = s < 0 ? -s : 2 * (p.n - 1) - s;
+                    s = (m >= 0 && m < p.n) ? m : reflect_index(s, p.n);
+                    inside = true;
+                }
+                pbuf[e] = inside ? src[s] : 0.0f;
+            }
+            __syncwarp();
+            g = reinterpret_cast<const float2*>(pbuf);
+        }
+#pragma unroll
+        for (int r = 0; r < 32; ++r) { const float2 x = g[lane + 32 * r]; v[r] = Cpx<float>{x.x, x.y}; }
+#pragma unroll
+        for (int r = 0; r < 32; ++r) { const Cpx<float> w = win2[lane + 32 * r]; v[r].x *= w.x; v[r].y *= w.y; }
+        __syncwarp();                                // staged samples are consumed before the transpose reuses the scratch
+        frame_fft_power(v, xbuf, tab);
+        const float* pf = pbuf + kPbufLead;
+        float ic2 = 1.0f;
+        if ((do_img && p.norm_img) || (do_spec && p.norm_spec)) { const float ic = 1.0f / p.clip_scale[clip]; ic2 = ic * ic; }
+
+        if (do_img) {
+            float* dst = p.out + (long long)clip * p.fb.n_mels * p.T + t;
+            const int T = p.T;
+            apply_filterbank(pf, fb1, p.fb.n_slots, lane, p.norm_img ? ic2 : 1.0f, p.amin, p.power_out != 0,
+                             [&](int m, float val) { dst[(long long)m * T] = val; });
+        }
+        if (do_spec) {
+            float* dst = p.spec_scratch + ((long long)clip * p.T2 + u) * 128;
+            apply_filterbank(pf, fb2, p.fb2.n_slots, lane, p.norm_spec ? ic2 : 1.0f, p.amin, false,
+                             [&](int m, float val) { dst[m] = val; });
+            __threadfence();                          // this lane's rows are visible before the arrival is counted
+            __syncwarp();
+            unsigned prev = 0;
+            if (lane == 0) prev = atomicAdd(p.clip_count + clip, 1u);
+            prev = __shfl_sync(0xffffffffu, prev, 0);
+            if (prev == (unsigned)p.T2 - 1u) {        // the clip's last spectrum frame: finish its MFCC row
+                __threadfence();
+                mfcc_finish_warp(p, clip, pbuf);
+            }
+        }
+        __syncwarp();                                 // pbuf (= xbuf) is rewritten by the next frame's transpose
+    }
+}
+
+}  // namespace gat
