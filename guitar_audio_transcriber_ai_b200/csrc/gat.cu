@@ -164,8 +164,12 @@ struct gat_ctx {
     DevBuf conv_w_tc[3];   // conv2/conv3 weights in the tensor-core operand layout (wf | wb | wl stages, see conv_tc.cuh)
     DevBuf fc1_w_tc, feat_planes, hid, tc_debug_buf;
     bool tc_debug = false;
-    int conv_pass_mult = 16;  // clips per conv pass = conv_pass_mult * num_sms; measured on B200: long passes win (5.84 ms at 1, 5.21 at 14,
-                              // 5.15 at 28 per 4096 clips) - per-launch head/tail costs outweigh keeping activations inside the L2
+    int conv_pass_mult = 28;  // clips per conv pass = conv_pass_mult * num_sms; measured on B200: long passes win (round 1: 5.84 ms at 1,
+                              // 5.21 at 14, 5.15 at 28 per 4096 clips; round 2: 3.08 at 16, 3.05 at 28) - per-launch head/tail costs outweigh
+                              // keeping activations inside the L2.  (Round 2 also tried running conv1 of pass k+1 on a side stream beside
+                              // conv2 / conv3 of pass k, with the tensor-core kernels capped at 128 registers so that a conv1 CTA fits on the
+                              // same SM: conv1 overlapped, but conv2 slowed from 0.68 to 0.84 ms - its epilogue warps need the issue slots
+                              // conv1 takes - and the step did not move: 3.05-3.08 ms at every pass size.  Not kept.)
     int conv_ch[4] = {0, 0, 0, 0}; int hidden = 0, classes = 0; bool cnn_loaded = false;
     DevBuf scaler_mean, scaler_scale; int scaler_n = 0;
     float w_mlp = 0.2f, w_cnn = 0.8f;
@@ -720,7 +724,7 @@ namespace {
 #include "emu_run_cnn.inc"   // tests/emu: CUDA-core stand-in for the tensor-core CNN (host-emulation build only)
 #else
 // conv1 on CUDA cores (C_in = 1), conv2/conv3 as tcgen05 implicit GEMMs (csrc/conv_tc.cuh), head once per batch.
-// Clips go through the convs in passes of conv_pass_mult * num_sms (default 16 x 148 = 2368): act1 + act2 are hf / lb
+// Clips go through the convs in passes of conv_pass_mult * num_sms (default 28 x 148 = 4144): act1 + act2 are hf / lb
 // chunk planes, 4 bytes per element (~0.3 MB per clip at T = 87); measured, long passes beat keeping them inside L2.
 constexpr size_t kActGuard = 65536;   // bytes before/after the plane buffers: halo reads of edge groups stay in bounds
 

@@ -215,7 +215,7 @@ int gat_transcribe_clips_host_pcm16(gat_ctx* ctx, const int16_t* audio_host, int
 int gat_profile_begin(gat_ctx* ctx);
 int gat_profile_end(gat_ctx* ctx, char* buf, int64_t cap);
 
-/* Clips per CNN pass = mult * (number of SMs); default 16 (2368 clips, ~1.4 GB of activation planes at T = 87). */
+/* Clips per CNN pass = mult * (number of SMs); default 28 (4144 clips, ~1.3 GB of activation planes at T = 87). */
 int gat_set_conv_pass(gat_ctx* ctx, int32_t mult);
 
 /* Diagnostics for the tensor-core conv pipeline: call with out_host = NULL to switch the in-kernel cycle

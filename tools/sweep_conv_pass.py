@@ -10,7 +10,7 @@ eng = Engine(22050, device="cuda:0")
 eng.load_cnn(load_checkpoint(ck / "cnn_synth_sr22050.ckpt")["model"]); eng.load_mlp(load_checkpoint(ck / "mlp_synth_sr22050.ckpt")["model"])
 clips, _ = synth.clip_batch(256, 1.0, 22050, 0)
 a = torch.from_numpy(np.tile(clips, (16, 1))).cuda()
-for mult in (8, 14, 28):
+for mult in (2, 4, 7, 8, 14, 16, 28):
     eng.lib.check(eng.lib.gat_set_conv_pass(eng._ctx, mult))
     for _ in range(3): eng.transcribe_clips(a, skip_mlp=True)
     torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True); e0.record()
