@@ -79,6 +79,7 @@ _PROTOTYPES = {
     "gat_profile_end": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "gat_debug_tc_counters": (C.c_int, [_P, _P, C.c_int64]),
     "gat_set_conv_pass": (C.c_int, [_P, C.c_int32]),
+    "gat_set_host_chunks": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32]),
     "gat_debug_fma_peak": (C.c_int, [_P, C.c_int32, _P]),
     "gat_launch_count": (C.c_int64, [_P]),
     "gat_num_classes": (C.c_int32, [_P]),

@@ -182,6 +182,7 @@ struct gat_ctx {
     DevBuf e2e_audio[2], e2e_pcm[2], e2e_mel, e2e_mfcc, e2e_probs, e2e_mlp_probs, e2e_cnn_probs, e2e_index, e2e_conf;
     cudaStream_t e2e_stream[2] = {nullptr, nullptr};
     bool e2e_streams = false;
+    int host_chunk_mult[3] = {2, 8, 0};   // smallest / largest chunk of the host entry points (x num_sms) and their order (gat_set_host_chunks)
 };
 
 extern "C" const char* gat_last_error(void) { return g_error.c_str(); }
@@ -267,6 +268,13 @@ extern "C" int gat_debug_fma_peak(gat_ctx* c, int32_t iters, float* tflops_host)
 extern "C" int gat_set_conv_pass(gat_ctx* c, int32_t mult) {
     if (!c || mult < 1 || mult > 64) return fail("gat_set_conv_pass: bad argument");
     c->conv_pass_mult = mult;
+    return 0;
+}
+
+extern "C" int gat_set_host_chunks(gat_ctx* c, int32_t min_mult, int32_t max_mult, int32_t order) {
+    if (!c || min_mult < 1 || max_mult < min_mult || max_mult > 64 || order < 0 || order > 2)
+        return fail("gat_set_host_chunks: bad argument");
+    c->host_chunk_mult[0] = min_mult; c->host_chunk_mult[1] = max_mult; c->host_chunk_mult[2] = order;
     return 0;
 }
 
@@ -770,15 +778,19 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
     const long long per_pass = (long long)c->num_sms * c->conv_pass_mult;
     const long long chunk = N < per_pass ? N : per_pass;
     const size_t P1 = (size_t)(H1 + 2) * (W1 + 2), P2 = (size_t)(H2 + 2) * (W2 + 2);
-    const size_t a1 = (size_t)chunk * 4 * P1 * 16, a2 = (size_t)chunk * 8 * P2 * 16;   // bytes of ONE of the two arrays (hf, lb)
+    // The plane buffers are laid out for `cap` clips: the largest pass seen at this image size.  A smaller call reuses
+    // them as they are (their zero borders stay valid: the kernels only ever write interiors), so the host entry
+    // points can mix short and long chunks without re-zeroing hundreds of megabytes at every change of size.
+    const bool same_geom = c->act_shape[1] == H0 && c->act_shape[2] == W0;
+    const long long cap = same_geom && c->act_shape[0] >= chunk ? c->act_shape[0] : chunk;
+    const size_t a1 = (size_t)cap * 4 * P1 * 16, a2 = (size_t)cap * 8 * P2 * 16;   // bytes of ONE of the two arrays (hf, lb)
     const size_t a3 = (size_t)N * H3 * W3 * 128 * 4;
-    const bool fresh = c->act1.cap < 2 * a1 + 2 * kActGuard || c->act2.cap < 2 * a2 + 2 * kActGuard ||
-                       c->act_shape[0] != chunk || c->act_shape[1] != H0 || c->act_shape[2] != W0;
+    const bool fresh = !same_geom || cap != c->act_shape[0] || c->act1.cap < 2 * a1 + 2 * kActGuard || c->act2.cap < 2 * a2 + 2 * kActGuard;
     if (c->act1.ensure(2 * a1 + 2 * kActGuard) || c->act2.ensure(2 * a2 + 2 * kActGuard) || c->act3.ensure(a3)) return 1;
-    if (fresh) {   // zero borders (and guards) once per geometry; the kernels only ever write interiors
+    if (fresh) {   // zero borders (and guards) once per geometry
         GAT_CUDA(cudaMemsetAsync(c->act1.p, 0, 2 * a1 + 2 * kActGuard, (cudaStream_t)stream));
         GAT_CUDA(cudaMemsetAsync(c->act2.p, 0, 2 * a2 + 2 * kActGuard, (cudaStream_t)stream));
-        c->act_shape[0] = chunk; c->act_shape[1] = H0; c->act_shape[2] = W0;
+        c->act_shape[0] = cap; c->act_shape[1] = H0; c->act_shape[2] = W0;
     }
     // each activation buffer: [hf | lb] chunk-plane arrays of a bytes each, between two guard bands
     auto arr = [](DevBuf& b, size_t a, int k) { return reinterpret_cast<unsigned short*>(b.as<unsigned char>() + kActGuard + (size_t)k * a); };
@@ -1014,7 +1026,7 @@ int segment_impl(gat_ctx* c, const float* y, int64_t P, int64_t L, const gat_sli
 
     // 1-3: sample gate (fused into the loads) -> frame RMS dB -> median-5 -> p20 + 6 dB frame gate
     RmsParams rp{y, (long long)L, T, sp->rms_hop, sp->sample_gate, c->seg_rms.as<float>()};
-    LAUNCH(c, rms_db_kernel, dim3((unsigned)ceil_div(T, 128), (unsigned)P), 128, 0, st, rp);
+    LAUNCH(c, rms_db_kernel, dim3((unsigned)ceil_div(T, kRmsFramesPerCta), (unsigned)P), 128, 0, st, rp);
     LAUNCH(c, median5_kernel, dim3((unsigned)ceil_div(T, 256), (unsigned)P), 256, 0, st, c->seg_rms.as<float>(), c->seg_rms_med.as<float>(), T);
     GateParams gp{c->seg_rms_med.as<float>(), T, sp->p20_k, sp->p20_gamma, sp->gate_offset_db, c->seg_gate.as<unsigned char>(), sc.gate_val};
     LAUNCH(c, rms_gate_kernel, (unsigned)P, T >= 4096 ? 1024 : 256, 0, st, gp);
@@ -1146,12 +1158,34 @@ int transcribe_host(gat_ctx* c, const void* audio_host_v, int sample_bytes, int6
         c->e2e_streams = true;
     }
     const int classes = c->classes;
-    // 4 x num_sms clips per chunk (592 clips = 52 MB at 1 s).  Measured on B200 at 4096 x 1 s clips, float32 / PCM_16 host
-    // clips: 2x 7.14 / 6.37 ms, 3x 7.25 / 5.98, 4x 7.25 / 5.58, 5x 7.34 / 5.60.  With float32 clips the step is copy-bound
-    // (361 MB at the ~51 GB/s this host link sustains) and the chunk size hardly matters; with PCM_16 clips the kernels
-    // are the bound and larger chunks amortise their fixed cost.
-    const int64_t want = 4 * (int64_t)c->num_sms;
-    const int64_t chunk = N < want ? N : want;
+    // Chunk schedule.  Chunk k's kernels start when its copy has landed, and the copy of chunk k+1 runs beside them.
+    //   float32 clips: the link is the bound (361 MB at the 55.6 GB/s profiles/r02_h2d_probe_*.json measure = 6.50 ms against
+    //   ~3 ms of kernels), so the call ends one chunk's kernels after the LAST byte lands: sizes HALVE towards the end
+    //   (..., 8, 4, 2, 1 x SMs) - each chunk's kernels finish under the next, shorter copy and the tail is the smallest chunk.
+    //   PCM_16 clips: half the bytes, the kernels are the bound, the call ends sum(kernels) after the FIRST chunk lands:
+    //   sizes DOUBLE from the start (1, 2, 4, 8 x SMs, ...) so the kernels start early and then run on efficient batches.
+    // Round 1 used equal chunks of 4 x SMs (7.20 / 5.17 ms); long chunks at the end of a copy-bound call cost their whole
+    // kernel time as tail (measured: 7.45 ms with 8 x SMs in the middle), hence the geometric schedules: 7.11 / 4.53 ms at
+    // 2..8 x SMs.  What is left above the copy itself (6.60 ms measured inside this call) is the last chunk's kernel chain
+    // (nine launches, ~0.25 ms however few clips) plus the result copies; the PCM_16 call pays ~1.4 ms of small-batch
+    // inefficiency over the 3.05 ms the same kernels take on one resident 4096-clip batch.
+    std::vector<int64_t> sizes;
+    {
+        const int64_t sm = c->num_sms;
+        const int64_t lo = c->host_chunk_mult[0] * sm, cap = c->host_chunk_mult[1] * sm;
+        int order = c->host_chunk_mult[2];
+        if (order == 0) order = sample_bytes == 2 ? 1 : 2;                 // 1: increasing, 2: decreasing
+        int64_t left = N, sz = lo;
+        while (left > 0) {
+            const int64_t take = left < sz + lo / 2 ? left : sz;            // fold a small remainder into the last chunk
+            sizes.push_back(take);
+            left -= take;
+            sz = sz * 2 > cap ? cap : sz * 2;
+        }
+        if (order == 2) std::reverse(sizes.begin(), sizes.end());
+    }
+    int64_t chunk = 0;
+    for (int64_t v : sizes) chunk = v > chunk ? v : chunk;
     if (sample_bytes == 2 && (c->e2e_pcm[0].ensure((size_t)chunk * n * 2) || c->e2e_pcm[1].ensure((size_t)chunk * n * 2))) return 1;
     if (c->e2e_audio[0].ensure((size_t)chunk * n * 4) || c->e2e_audio[1].ensure((size_t)chunk * n * 4) ||
         c->e2e_probs.ensure((size_t)N * classes * 4) || c->e2e_mlp_probs.ensure((size_t)N * classes * 4) ||
@@ -1164,13 +1198,19 @@ int transcribe_host(gat_ctx* c, const void* audio_host_v, int sample_bytes, int6
         GAT_CUDA(cudaEventCreateWithFlags(&consumed[i], cudaEventDisableTiming));
     }
     int rc = 0;
-    int64_t k = 0;
-    for (int64_t c0 = 0; c0 < N && !rc; c0 += chunk, ++k) {
+    int64_t c0 = 0;
+    for (size_t k = 0; k < sizes.size() && !rc; c0 += sizes[k], ++k) {
         const int b = (int)(k & 1);
-        const int64_t nc = N - c0 < chunk ? N - c0 : chunk;
+        const int64_t nc = sizes[k];
         if (k >= 2) GAT_CUDA(cudaStreamWaitEvent(c->e2e_stream[1], consumed[b], 0));
         void* landing = sample_bytes == 2 ? c->e2e_pcm[b].p : c->e2e_audio[b].p;
+        cudaEvent_t pc0 = nullptr, pc1 = nullptr;
+        if (c->profiling) {          // the copies appear in gat_profile_end's table as "h2d_copy"
+            GAT_CUDA(cudaEventCreate(&pc0)); GAT_CUDA(cudaEventCreate(&pc1));
+            GAT_CUDA(cudaEventRecord(pc0, c->e2e_stream[1]));
+        }
         GAT_CUDA(cudaMemcpyAsync(landing, audio_host + (size_t)c0 * n * sample_bytes, (size_t)nc * n * sample_bytes, cudaMemcpyHostToDevice, c->e2e_stream[1]));
+        if (c->profiling) { GAT_CUDA(cudaEventRecord(pc1, c->e2e_stream[1])); c->prof.push_back(ProfRec{"h2d_copy", pc0, pc1}); }
         GAT_CUDA(cudaEventRecord(copied[b], c->e2e_stream[1]));
         GAT_CUDA(cudaStreamWaitEvent(c->e2e_stream[0], copied[b], 0));
         if (sample_bytes == 2) {

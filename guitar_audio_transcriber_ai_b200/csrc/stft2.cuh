@@ -239,17 +239,19 @@ __global__ void __launch_bounds__(kThreads, 1) stft_frames_kernel(StftFramesPara
         Cpx<float> v[G::V];
         const bool interior = s0 >= 0 && s0 + kStft2N <= p.n;
         const float2* g = reinterpret_cast<const float2*>(src + s0);          // generic pointer: global here, shared below
-        if (!(interior && ((reinterpret_cast<unsigned long long>(src + s0) & 7ull) == 0ull))) {
-            // the frame touches the clip's ends (or is not 8-byte aligned): stage it through this warp's scratch with a
-            // ROLLED loop - image frames mirror at the ends (torch.stft reflect), spec-only frames see zeros (librosa)
+        const bool aligned = (reinterpret_cast<unsigned long long>(src + s0) & 7ull) == 0ull;
+        if (!interior) {
+            // the frame touches the clip's ends: stage it through this warp's scratch with a ROLLED loop - image frames
+            // mirror at the ends (torch.stft reflect), spec-only frames see zeros (librosa)
             const bool reflect = do_img;
+            const int n32 = (int)p.n, s32 = (int)s0;          // a clip has fewer than 2^31 samples
 #pragma unroll 1
             for (int e = lane; e < kStft2N; e += 32) {
-                long long s = s0 + e;
-                bool inside = s >= 0 && s < p.n;
+                int s = s32 + e;
+                bool inside = s >= 0 && s < n32;
                 if (!inside && reflect) {            // one mirror suffices: the launcher requires n > n_fft / 2
-                    const long long m = s < 0 ? -s : 2 * (p.n - 1) - s;
-                    s = (m >= 0 && m < p.n) ? m : reflect_index(s, p.n);
+                    const int m = s < 0 ? -s : 2 * (n32 - 1) - s;
+                    s = (m >= 0 && m < n32) ? m : (int)reflect_index(s, p.n);
                     inside = true;
                 }
                 pbuf[e] = inside ? src[s] : 0.0f;
@@ -257,8 +259,15 @@ __global__ void __launch_bounds__(kThreads, 1) stft_frames_kernel(StftFramesPara
             __syncwarp();
             g = reinterpret_cast<const float2*>(pbuf);
         }
+        if (interior && !aligned) {
+            // clips with an odd sample count start on odd 4-byte boundaries every other clip: 32-bit loads, same registers
+            const float* g1 = src + s0 + 2 * lane;
 #pragma unroll
-        for (int r = 0; r < 32; ++r) { const float2 x = g[lane + 32 * r]; v[r] = Cpx<float>{x.x, x.y}; }
+            for (int r = 0; r < 32; ++r) v[r] = Cpx<float>{g1[64 * r], g1[64 * r + 1]};
+        } else {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) { const float2 x = g[lane + 32 * r]; v[r] = Cpx<float>{x.x, x.y}; }
+        }
 #pragma unroll
         for (int r = 0; r < 32; ++r) { const Cpx<float> w = win2[lane + 32 * r]; v[r].x *= w.x; v[r].y *= w.y; }
         __syncwarp();                                // staged samples are consumed before the transpose reuses the scratch

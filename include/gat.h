@@ -218,6 +218,11 @@ int gat_profile_end(gat_ctx* ctx, char* buf, int64_t cap);
 /* Clips per CNN pass = mult * (number of SMs); default 28 (4144 clips, ~1.3 GB of activation planes at T = 87). */
 int gat_set_conv_pass(gat_ctx* ctx, int32_t mult);
 
+/* Chunk schedule of the host entry points: chunk sizes grow geometrically from min_mult x SMs to max_mult x SMs.
+ * order 1 = increasing (kernel-bound calls: start early, then efficient batches), 2 = decreasing (copy-bound calls: the tail
+ * after the last byte is the smallest chunk), 0 = pick by sample format (PCM_16: 1, float32: 2).  Default 2 / 8 / 0. */
+int gat_set_host_chunks(gat_ctx* ctx, int32_t min_mult, int32_t max_mult, int32_t order);
+
 /* Diagnostics for the tensor-core conv pipeline: call with out_host = NULL to switch the in-kernel cycle
  * counters on; call again with a buffer of 2*148*8 int64 to read them (conv2 then conv3; per CTA:
  * MMA-thread total, wait acc_empty, wait a_full, wait w_full, epilogue total, epilogue wait acc_full). */
