@@ -372,32 +372,38 @@ __global__ void __launch_bounds__(256, 4) conv1_pool_planes_kernel(Conv1PlanesPa
     const long long pix = (long long)(py + 1) * (Wq + 2) + px + 1;
 #pragma unroll
     for (int ch8 = 0; ch8 < 4; ++ch8) {
-        // eight channels x four pre-pool positions; the weights of a tap come as two 128-bit broadcast loads
-        float acc[8][4];
+        // eight channels x four pre-pool positions; the weights of a tap come as two 128-bit broadcast loads.  The
+        // accumulators are channel PAIRS updated with the packed FFMA2 of sm_100 (fma.rn.f32x2: two IEEE fp32 FMAs per
+        // issued instruction - the kernel is issue-bound, not FMA-pipe-bound); every lane of a pair sees exactly the
+        // fmaf(pv, w, acc) it saw before.
+        float2 acc[4][4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
+        for (int e = 0; e < 4; ++e)
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) acc[e][q4] = 0.0f;
+            for (int q4 = 0; q4 < 4; ++q4) acc[e][q4] = make_float2(0.0f, 0.0f);
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
                 const float4 w0 = *reinterpret_cast<const float4*>(ws + (ky * 3 + kx) * 32 + ch8 * 8);
                 const float4 w1 = *reinterpret_cast<const float4*>(ws + (ky * 3 + kx) * 32 + ch8 * 8 + 4);
-                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                const float2 wv[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
 #pragma unroll
                 for (int a = 0; a < 2; ++a)
 #pragma unroll
                     for (int b = 0; b < 2; ++b) {
                         const float pv = patch[a + ky][b + kx];
+                        const float2 pv2 = make_float2(pv, pv);
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) acc[e][a * 2 + b] = fmaf(pv, wv[e], acc[e][a * 2 + b]);
+                        for (int e = 0; e < 4; ++e) acc[e][a * 2 + b] = __ffma2_rn(pv2, wv[e], acc[e][a * 2 + b]);
                     }
             }
         float o[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const float best = fmaxf(fmaxf(acc[e][0], acc[e][1]), fmaxf(acc[e][2], acc[e][3]));
+            const float a0 = (e & 1) ? acc[e >> 1][0].y : acc[e >> 1][0].x, a1 = (e & 1) ? acc[e >> 1][1].y : acc[e >> 1][1].x;
+            const float a2 = (e & 1) ? acc[e >> 1][2].y : acc[e >> 1][2].x, a3 = (e & 1) ? acc[e >> 1][3].y : acc[e >> 1][3].x;
+            const float best = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
             const float z = best + bs[ch8 * 8 + e];
             o[e] = z > 0.0f ? z : z * p.slope;
         }

@@ -23,6 +23,18 @@ template <typename T> struct __align__(2 * sizeof(T)) Cpx { T x, y; };
 
 template <typename T> __device__ __forceinline__ Cpx<T> cadd(Cpx<T> a, Cpx<T> b) { return Cpx<T>{a.x + b.x, a.y + b.y}; }
 template <typename T> __device__ __forceinline__ Cpx<T> csub(Cpx<T> a, Cpx<T> b) { return Cpx<T>{a.x - b.x, a.y - b.y}; }
+#ifndef GAT_CPU_EMU
+// float32: a complex add / subtract is ONE packed instruction on sm_100 (FADD2 = add.rn.f32x2; the subtraction is
+// fma(b, -1, a): the product is exact, so it rounds once like a - b).  Same IEEE results, half the issue slots.
+__device__ __forceinline__ Cpx<float> cadd(Cpx<float> a, Cpx<float> b) {
+    const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    return Cpx<float>{r.x, r.y};
+}
+__device__ __forceinline__ Cpx<float> csub(Cpx<float> a, Cpx<float> b) {
+    const float2 r = __ffma2_rn(make_float2(b.x, b.y), make_float2(-1.0f, -1.0f), make_float2(a.x, a.y));
+    return Cpx<float>{r.x, r.y};
+}
+#endif
 template <typename T> __device__ __forceinline__ Cpx<T> cmul(Cpx<T> a, Cpx<T> b) {
     return Cpx<T>{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
 }

@@ -70,8 +70,18 @@ __device__ __forceinline__ void apply_filterbank(const float* pf, const FbShared
         const int ln = fb.len[e];
         const float4* pb = reinterpret_cast<const float4*>(pf + fb.start[e]);
         const float4* w = reinterpret_cast<const float4*>(fb.w + fb.off[e]);
-        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#ifndef GAT_CPU_EMU
+        float2 a01 = make_float2(0.0f, 0.0f), a23 = make_float2(0.0f, 0.0f);     // two packed FFMA2 per step
 #pragma unroll 2
+        for (int k = 0; k < ln; ++k) {
+            const float4 pv = pb[k];
+            const float4 wv = w[k];
+            a01 = __ffma2_rn(make_float2(pv.x, pv.y), make_float2(wv.x, wv.y), a01);
+            a23 = __ffma2_rn(make_float2(pv.z, pv.w), make_float2(wv.z, wv.w), a23);
+        }
+        const float acc = ((a01.x + a01.y) + (a23.x + a23.y)) * scale;
+#else
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
         for (int k = 0; k < ln; ++k) {
             const float4 pv = pb[k];
             const float4 wv = w[k];
@@ -79,6 +89,7 @@ __device__ __forceinline__ void apply_filterbank(const float* pf, const FbShared
             a2 = fmaf(pv.z, wv.z, a2); a3 = fmaf(pv.w, wv.w, a3);
         }
         const float acc = ((a0 + a1) + (a2 + a3)) * scale;
+#endif
         if (m >= 0) store(m, power_out ? acc : db10(acc > amin ? acc : amin));
     }
 }
@@ -269,7 +280,15 @@ __global__ void __launch_bounds__(kThreads, 1) stft_frames_kernel(StftFramesPara
             for (int r = 0; r < 32; ++r) { const float2 x = g[lane + 32 * r]; v[r] = Cpx<float>{x.x, x.y}; }
         }
 #pragma unroll
-        for (int r = 0; r < 32; ++r) { const Cpx<float> w = win2[lane + 32 * r]; v[r].x *= w.x; v[r].y *= w.y; }
+        for (int r = 0; r < 32; ++r) {
+            const Cpx<float> w = win2[lane + 32 * r];
+#ifndef GAT_CPU_EMU
+            const float2 m = __fmul2_rn(make_float2(v[r].x, v[r].y), make_float2(w.x, w.y));      // packed multiply, same products
+            v[r] = Cpx<float>{m.x, m.y};
+#else
+            v[r].x *= w.x; v[r].y *= w.y;
+#endif
+        }
         __syncwarp();                                // staged samples are consumed before the transpose reuses the scratch
         frame_fft_power(v, xbuf, tab);
         const float* pf = pbuf + kPbufLead;

@@ -168,6 +168,9 @@ static inline float __fadd_rn(float a, float b) { volatile float r = a + b; retu
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 static inline int __float2int_rn(float a) { return (int)lrintf(a); }
+static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return float2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
+static inline float2 __fadd2_rn(float2 a, float2 b) { volatile float x = a.x + b.x, y = a.y + b.y; return float2{x, y}; }
+static inline float2 __fmul2_rn(float2 a, float2 b) { volatile float x = a.x * b.x, y = a.y * b.y; return float2{x, y}; }
 static inline float __fsqrt_rn(float a) { return sqrtf(a); }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }

@@ -273,8 +273,9 @@ def test_other_n_fft_against_torchaudio(n_fft):
         if n_fft >= 1024:
             assert mel_ok(mel[i], ref), (n_fft, i, np.abs(mel[i] - ref).max())
         else:   # 64 mel bands over 257 bins: the lowest filters weigh a fraction of ONE weak bin, where the two float32
-                # FFTs' rounding noise is a larger share of the value; not a BASELINE configuration, checked loosely
-            assert np.abs(mel[i] - ref).max() <= 2e-2, (n_fft, i, np.abs(mel[i] - ref).max())
+                # FFTs' rounding noise is a larger share of the value.  profiles/r02_parity.json (256 clips): max 1.5e-2 dB =
+                # 2.8e-4 of max(|ref|, 20 dB), all of it in mel band 0, p99 7e-6 -> bound at 5e-4 (was 2e-2 dB absolute)
+            assert np.all(np.abs(mel[i] - ref) <= 5e-4 * np.maximum(np.abs(ref), 20.0)), (n_fft, i, np.abs(mel[i] - ref).max())
     eng.close()
 
 
@@ -327,15 +328,15 @@ def test_full_size_properties(tr22):
     mel = out1["mel"].view(reps, 64, -1)
     assert float((mel - mel[0:1]).abs().max()) < 2e-2
     assert torch.all(torch.isfinite(out1["probs"])) and float((out1["probs"].sum(1) - 1).abs().max()) < 1e-5
-    # and the first 64 agree with the CPU oracle
+    # and the first 64 agree with the CPU oracle (the bench run compares another 1024 labels; tools/parity_report.py all 4096)
     import port
     from guitar_audio_transcriber_ai_b200.checkpoint import load_checkpoint
     cnn_ck = load_checkpoint(CKPT / "cnn_synth_sr22050.ckpt")
     with torch.inference_mode():
-        imgs = torch.stack([port.melspec_image(base[i] * gains[0], 22050) for i in range(16)])
+        imgs = port.extract_melspec_features([base[i] * gains[0] for i in range(64)], 22050, 64, 2048, 256, normalize=True)
         probs = torch.softmax(port.cnn_forward(cnn_ck["model"], imgs), -1).numpy()
-    assert np.abs(out1["probs"][:16].cpu().numpy() - probs).max() <= 5e-5
-    assert out1["indices"][:16].cpu().numpy().tolist() == probs.argmax(1).tolist()
+    assert np.abs(out1["probs"][:64].cpu().numpy() - probs).max() <= PROB_ABS
+    assert out1["indices"][:64].cpu().numpy().tolist() == probs.argmax(1).tolist()
 
 
 def test_host_buffer_entry_point(tr22):
@@ -402,6 +403,7 @@ def test_transcribe_notes_resamples_like_the_reference(tr22):
     mlp_ck, cnn_ck = ref_env.load_ckpt(CKPT / "mlp_synth_sr22050.ckpt"), ref_env.load_ckpt(CKPT / "cnn_synth_sr22050.ckpt")
     # 16 kHz input leaves the mel bins above 8 kHz at the float32 rounding floor of the FFT (about -140 dB re the
     # peak): there the dB image is implementation noise in ANY float32 FFT, and the CNN sees it -> looser bound.
+    # Distribution over 32 clips (profiles/r02_parity.json): per-clip max |d probs| p50 5.7e-4, max 6.6e-3, labels 32 / 32.
     for seed, sr_in, tol in ((3, 44100, 5e-5), (5, 32000, 5e-5), (4, 16000, 1e-2)):
         a = synth.note(float(synth.midi_to_hz(synth.random_midi(seed))), 0.5, sr_in, seed)
         want = port.transcribe_note(mlp_ck, cnn_ck, a, 0.5, sr_in)

@@ -42,9 +42,15 @@ def main():
     ap.add_argument("--librosa-clips", type=int, default=1024)
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count() or 1)
+    clips, midi = synth.clip_batch(a.clips, 1.0, SR, 0)
+    # the librosa-restated rows first, in forked workers, BEFORE this process touches CUDA
+    m = min(a.librosa_clips, a.clips)
+    sel = np.linspace(0, a.clips - 1, m).astype(int)
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(os.cpu_count() or 1) as pool:
+        rows = pool.map(_librosa_row, [(clips[i],) for i in sel], chunksize=8)
     tr = Transcriber("mlp_synth_sr22050.ckpt", "cnn_synth_sr22050.ckpt", CK, CK, device="cuda:0")
     mlp_ck, cnn_ck = tr.model_ckpts["mlp"], tr.model_ckpts["cnn"]
-    clips, midi = synth.clip_batch(a.clips, 1.0, SR, 0)
     out = tr.engine.transcribe_clips(torch.from_numpy(clips).cuda(), yin_on_normalized=True, return_features=True)
     got = {k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in out.items()}
     rep = {"clips": a.clips, "workload": "BASELINE configs[1]/[2]: 4096 x 1 s clips, sr 22050, seed = clip index"}
@@ -65,11 +71,6 @@ def main():
                         "label_mismatches": int((got["cnn_probs"].argmax(1) != cnn_probs.argmax(1)).sum())}
 
     # ---- MFCC + YIN vs the librosa restatement
-    m = min(a.librosa_clips, a.clips)
-    sel = np.linspace(0, a.clips - 1, m).astype(int)
-    import multiprocessing as mp
-    with mp.get_context("fork").Pool(os.cpu_count() or 1) as pool:
-        rows = pool.map(_librosa_row, [(clips[i],) for i in sel], chunksize=8)
     vec = np.stack([r[0] for r in rows]); hz = np.array([r[1] for r in rows], dtype=np.float64)
     dm = np.abs(got["mfcc"][sel, :64] - vec[:, :64])
     rep["mfcc"] = {"abs": dist(dm), "rel_to_max_ref_1": dist(dm / np.maximum(np.abs(vec[:, :64]), 1.0)), "tolerance": "1e-4 * max(|ref|, 1)",
