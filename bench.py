@@ -489,7 +489,12 @@ class PhraseConfig:
             return self.parallel.phrases_rows_device(self.tr, Y, 0.5, signal_offset=self.lo, gather=False)
         if self.mode == "file":
             return self.parallel.audio_rows_device(self.tr, Y.reshape(-1), 0.5)
-        return self.parallel.phrases_rows_device(self.tr, Y, 0.5, signal_offset=self.lo)
+        return self.parallel.phrases_rows_device(self.tr, Y, 0.5, signal_offset=self.lo,
+                                                 signals_per_rank=-(-self.P // self.env.world))
+
+    def _valid(self):
+        """The last step's gathered rows without the all-gather's padding."""
+        return self.parallel.valid_rows(self.last)
 
     def step_resident(self):
         self.k += 1
@@ -507,7 +512,7 @@ class PhraseConfig:
         self._rows(self.dev[0])
 
     def work(self):
-        n_clips = int(self.last.shape[0]) if self.last is not None else 0
+        n_clips = int(self._valid().shape[0]) if self.last is not None else 0
         mine = n_clips if (self.single or self.mode == "file") else max(1, n_clips // self.env.world)
         n = int(0.5 * SR)
         t = work_table(mine, n, 1 + n // 256, full=True)
@@ -521,10 +526,10 @@ class PhraseConfig:
         return t
 
     def checksum(self):
-        return int(self.last[:, 4].sum().item())
+        return int(self._valid()[:, 4].sum().item())
 
     def config_extra(self):
-        d = {"phrases": self.P, "phrase_seconds": PHRASE_SECONDS, "sample_rate": SR, "clips_found": int(self.last.shape[0]),
+        d = {"phrases": self.P, "phrase_seconds": PHRASE_SECONDS, "sample_rate": SR, "clips_found": int(self._valid().shape[0]),
              "l2": f"{len(self.dev)} device copies of the input rotated between steps (> 126 MB L2 in total)"}
         if self.single:
             d["parallelism"] = f"replicas x{self.env.world} (one phrase per GPU, no collective)"
@@ -543,7 +548,7 @@ class PhraseConfig:
         t0 = time.perf_counter()
         res = cpu_phrases(phrases, self.mlp_ck, self.cnn_ck)
         dt = time.perf_counter() - t0
-        rows = self.last.cpu().numpy()
+        rows = self._valid().cpu().numpy()
         mism = compared = 0
         table_ok = True
         if not (self.mode == "file" and not self.single):      # whole-file segmentation is not comparable phrase by phrase

@@ -277,10 +277,17 @@ __global__ void clip_scale_kernel(const float* __restrict__ audio, long long n, 
     __shared__ double red[32];
     const float* y = audio + (long long)blockIdx.x * n;
     double acc = 0.0;
-    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-        const float v = y[i];
-        acc += (double)__fmul_rn(v, v);
+    // 128-bit loads over the 16-byte aligned body of the clip (clips with an odd sample count start anywhere), scalars at the ends
+    const long long head = min(n, (long long)((4 - ((reinterpret_cast<unsigned long long>(y) >> 2) & 3)) & 3));
+    const long long body = (n - head) / 4;
+    const float4* y4 = reinterpret_cast<const float4*>(y + head);
+    for (long long i = threadIdx.x; i < body; i += blockDim.x) {
+        const float4 v = y4[i];
+        acc += (double)__fmul_rn(v.x, v.x); acc += (double)__fmul_rn(v.y, v.y);
+        acc += (double)__fmul_rn(v.z, v.z); acc += (double)__fmul_rn(v.w, v.w);
     }
+    for (long long i = threadIdx.x; i < head; i += blockDim.x) acc += (double)__fmul_rn(y[i], y[i]);
+    for (long long i = head + 4 * body + threadIdx.x; i < n; i += blockDim.x) acc += (double)__fmul_rn(y[i], y[i]);
     acc = warp_sum(acc);
     if (lane_id() == 0) red[warp_id()] = acc;
     __syncthreads();

@@ -38,6 +38,21 @@ __device__ __forceinline__ Cpx<float> csub(Cpx<float> a, Cpx<float> b) {
 template <typename T> __device__ __forceinline__ Cpx<T> cmul(Cpx<T> a, Cpx<T> b) {
     return Cpx<T>{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
 }
+// d * (c - i s) with real constants c, s (a butterfly's twiddle)
+template <typename T> __device__ __forceinline__ Cpx<T> ctwid(Cpx<T> d, T c, T s) {
+    return Cpx<T>{d.x * c + d.y * s, d.y * c - d.x * s};
+}
+#ifndef GAT_CPU_EMU
+// float32: one packed multiply by the broadcast scalar, then two FMAs - three instructions instead of four.
+__device__ __forceinline__ Cpx<float> cmul(Cpx<float> a, Cpx<float> b) {
+    const float2 t = __fmul2_rn(make_float2(b.x, b.y), make_float2(a.x, a.x));
+    return Cpx<float>{fmaf(-a.y, b.y, t.x), fmaf(a.y, b.x, t.y)};
+}
+__device__ __forceinline__ Cpx<float> ctwid(Cpx<float> d, float c, float s) {
+    const float2 t = __fmul2_rn(make_float2(d.x, d.y), make_float2(c, c));
+    return Cpx<float>{fmaf(d.y, s, t.x), fmaf(-d.x, s, t.y)};
+}
+#endif
 
 // cos(2*pi*j/64), j = 0..16
 template <typename T> __host__ __device__ constexpr T cos64_tab(int j) {
@@ -92,7 +107,7 @@ __device__ __forceinline__ void butterfly(Cpx<T>& a, Cpx<T>& b) {
     } else {
         constexpr T c = cos64<T>(J);
         constexpr T s_ = sin64<T>(J);
-        b = Cpx<T>{d.x * c + d.y * s_, d.y * c - d.x * s_};   // d * (c - i s)
+        b = ctwid(d, c, s_);                                   // d * (c - i s)
     }
 }
 

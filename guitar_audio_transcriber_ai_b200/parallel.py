@@ -70,25 +70,27 @@ def _world(group=None) -> tuple[int, int]:
     return 1, 0
 
 
-def gather_rows(rows: torch.Tensor, group=None) -> torch.Tensor:
-    """All-gather of ``[k_r, C]`` int64 rows whose count differs per rank: counts first, then one padded
-    ``all_gather_into_tensor``; returns the rows of all ranks in rank order."""
+def gather_rows(rows: torch.Tensor, cap: int, group=None) -> torch.Tensor:
+    """All-gather of ``[k_r, C]`` int64 rows whose count differs per rank, WITHOUT exchanging the counts: every rank
+    pads its block to the same static ``cap`` rows (a bound all ranks can compute from the call's arguments) with rows
+    whose first column is -1, and ONE ``all_gather_into_tensor`` moves them.  No host synchronisation: the result
+    ``[G * cap, C]`` stays on the device, padding included; ``valid_rows`` drops it."""
     world, _ = _world(group)
     if world == 1:
         return rows
-    counts = torch.zeros(world, dtype=torch.int64, device=rows.device)
-    mine = torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)
-    _all_gather_into(counts, mine, group)
-    counts = counts.cpu().tolist()
-    per = max(counts)
     C = rows.shape[1]
-    if per == 0:
-        return rows
-    padded = torch.zeros((per, C), dtype=torch.int64, device=rows.device)
+    if rows.shape[0] > cap:
+        raise ValueError(f"gather_rows: {rows.shape[0]} rows exceed the static bound {cap}")
+    padded = torch.full((cap, C), -1, dtype=torch.int64, device=rows.device)
     padded[: rows.shape[0]] = rows
-    out = torch.empty((world * per, C), dtype=torch.int64, device=rows.device)
+    out = torch.empty((world * cap, C), dtype=torch.int64, device=rows.device)
     _all_gather_into(out, padded, group)
-    return torch.cat([out[r * per: r * per + counts[r]] for r in range(world)], dim=0)
+    return out
+
+
+def valid_rows(rows: torch.Tensor) -> torch.Tensor:
+    """Drops the padding rows of ``gather_rows`` (first column < 0); rank order and row order are preserved."""
+    return rows[rows[:, 0] >= 0]
 
 
 def _f32_bits(x: torch.Tensor) -> torch.Tensor:
@@ -102,19 +104,13 @@ def _f64_bits(x: torch.Tensor) -> torch.Tensor:
 def clip_rows(table4: torch.Tensor, out: dict) -> torch.Tensor:
     """[k, 7] int64 rows per clip: signal, onset index, start, end, label index, float32 confidence bits,
     float64 YIN median bits.  ``table4`` is gat_segment_batch's table (or an equivalent built by the caller)."""
-    k = table4.shape[0]
-    rows = torch.zeros((k, 7), dtype=torch.int64, device=table4.device)
-    rows[:, :4] = table4
-    rows[:, 4] = out["indices"]
-    rows[:, 5] = _f32_bits(out["confidences"])
     hz = out.get("yin_hz")
-    if hz is not None:
-        rows[:, 6] = _f64_bits(hz)
-    return rows
+    hz_bits = _f64_bits(hz) if hz is not None else torch.zeros_like(out["indices"])
+    return torch.cat([table4, out["indices"][:, None], _f32_bits(out["confidences"])[:, None], hz_bits[:, None]], dim=1)
 
 
 def _result_from_rows(tr, rows: torch.Tensor, with_hz: bool) -> dict:
-    rows = rows.cpu()
+    rows = valid_rows(rows).cpu()
     idx = rows[:, 4].numpy()
     res = {
         "indices": idx,
@@ -146,7 +142,7 @@ def transcribe_notes_sharded(tr, audio, clip_duration, sr_in, group=None) -> dic
         rows[:, 1] = torch.arange(lo, hi, device=eng.device)
         rows[:, 4] = local["indices"]
         rows[:, 5] = _f32_bits(local["confidences"])
-    res = _result_from_rows(tr, gather_rows(rows, group), with_hz=False)
+    res = _result_from_rows(tr, gather_rows(rows, -(-N // world) if N else 0, group), with_hz=False)
     del res["slice_table"]
     res["local_range"] = (lo, hi)
     res["local_probs"] = local["probs"].cpu().numpy() if local is not None else None
@@ -154,15 +150,20 @@ def transcribe_notes_sharded(tr, audio, clip_duration, sr_in, group=None) -> dic
 
 
 def phrases_rows_device(tr, signals, clip_duration, signal_offset: int = 0, gather: bool = True, group=None,
-                        want_onsets: bool = False):
+                        want_onsets: bool = False, signals_per_rank: int | None = None):
     """The device half of transcribe_phrases_sharded for the signals THIS rank owns (``signals[P_r, L]``, global
     index of the first one = ``signal_offset``): ONE gat_segment_batch, ONE batched ensemble + YIN over the kept
-    clips, then (``gather``) the all-gather of the [k, 7] int64 rows.  Returns the rows on the device (and the
-    per-signal onset rows [P, 1 + max_onsets] = (count, onsets...) when ``want_onsets``)."""
+    clips, then (``gather``) ONE all-gather of the [k, 7] int64 rows, padded to the static bound
+    ``signals_per_rank * (max_onsets - 1)`` (K onsets yield at most K - 1 clips) so that no count has to be exchanged.
+    Returns the rows on the device, padding rows (first column -1) included - ``valid_rows`` drops them - and, with
+    ``want_onsets``, the per-signal onset rows [P, 1 + max_onsets] = (count, onsets...)."""
     eng = tr.engine
     Y = signals if torch.is_tensor(signals) else torch.as_tensor(signals)
+    sp = eng.slicer_params(Y.shape[1], clip_duration)
+    max_onsets = max(2, Y.shape[1] // max(1, sp.min_sep_samples) + 2)
+    per_rank = Y.shape[0] if signals_per_rank is None else signals_per_rank
     rows = torch.zeros((0, 7), dtype=torch.int64, device=eng.device)
-    onset_rows = None
+    onset_rows = torch.zeros((0, 1 + max_onsets), dtype=torch.int64, device=eng.device)
     if Y.shape[0]:
         seg = eng.segment_batch(Y, clip_duration)
         if seg["clips"].shape[0]:
@@ -173,14 +174,10 @@ def phrases_rows_device(tr, signals, clip_duration, signal_offset: int = 0, gath
         if want_onsets:
             onset_rows = torch.cat([seg["n_onsets"].to(torch.int64)[:, None], seg["onsets"]], dim=1)
     if gather:
-        rows = gather_rows(rows, group)
+        rows = gather_rows(rows, per_rank * (max_onsets - 1), group)
     if not want_onsets:
         return rows
-    if onset_rows is None:                                  # this rank owns no signal: the width must still match
-        sp = eng.slicer_params(Y.shape[1], clip_duration)
-        width = max(2, Y.shape[1] // max(1, sp.min_sep_samples) + 2)
-        onset_rows = torch.zeros((0, 1 + width), dtype=torch.int64, device=eng.device)
-    return rows, (gather_rows(onset_rows, group) if gather else onset_rows)
+    return rows, (gather_rows(onset_rows, per_rank, group) if gather else onset_rows)
 
 
 def transcribe_phrases_sharded(tr, phrases, clip_duration, group=None) -> dict:
@@ -195,9 +192,10 @@ def transcribe_phrases_sharded(tr, phrases, clip_duration, group=None) -> dict:
         raise ValueError("transcribe_phrases_sharded: phrases must be [P, L]")
     P = Y.shape[0]
     lo, hi = shard_bounds(P, world, rank)
-    rows, on = phrases_rows_device(tr, Y[lo:hi], clip_duration, signal_offset=lo, gather=True, group=group, want_onsets=True)
+    rows, on = phrases_rows_device(tr, Y[lo:hi], clip_duration, signal_offset=lo, gather=True, group=group, want_onsets=True,
+                                   signals_per_rank=-(-P // world) if P else 0)
     res = _result_from_rows(tr, rows, with_hz=True)
-    on = on.cpu().numpy()
+    on = valid_rows(on).cpu().numpy()
     res["onsets"] = [on[p, 1:1 + int(on[p, 0])].tolist() for p in range(P)]
     res["local_range"] = (lo, hi)
     return res
@@ -217,7 +215,7 @@ def audio_rows_device(tr, y, clip_duration, group=None, want_seg: bool = False):
         table = torch.zeros((hi - lo, 4), dtype=torch.int64, device=eng.device)
         table[:, 1:] = seg["table"][lo:hi]
         rows = clip_rows(table, out)
-    rows = gather_rows(rows, group)
+    rows = gather_rows(rows, -(-K // world) if K else 0, group)       # every rank knows K: the segmentation ran on all of them
     return (rows, seg, (lo, hi)) if want_seg else rows
 
 
