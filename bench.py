@@ -70,7 +70,8 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed regions run (a 20-step resident region
+    lasts ~55 ms, so the sampler stays on through the end-to-end regions as well: same kernels, same load)."""
     FIELDS = ["clocks.sm", "clocks.max.sm", "clocks_event_reasons.hw_slowdown", "clocks_event_reasons.hw_thermal_slowdown",
               "clocks_event_reasons.sw_thermal_slowdown", "clocks_event_reasons.sw_power_cap"]
 
@@ -82,7 +83,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", "--query-gpu=" + ",".join(self.FIELDS), "--format=csv,noheader,nounits", "-lms", "200"],
+                ["nvidia-smi", f"--id={self.index}", "--query-gpu=" + ",".join(self.FIELDS), "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -307,6 +308,7 @@ def work_table(n_clips: int, n: int, T: int, n_fft: int = 2048, full: bool = Fal
     t = {
         "clip_scale_kernel": ("hbm", n_clips * (4 * n + 4), None),
         "stft_mel_f32_image": ("hbm", n_clips * (4 * n + 4 * 64 * T), n_clips * T * stft_flops_per_frame(n_fft)),
+        "stft_frames_image": ("hbm", n_clips * (4 * n + 4 * 64 * T), n_clips * T * stft_flops_per_frame(n_fft)),
         "conv1_pool_planes_kernel": ("hbm", n_clips * (4 * 64 * T + 4 * H1 * W1 * 32), None),
         "conv2_tc_32_64": ("tensor", n_clips * 2.0 * H1 * W1 * 64 * 32 * 9, None),
         "conv12_tc_1_32_64": ("tensor", n_clips * 2.0 * H1 * W1 * 64 * 32 * 9, None),
@@ -320,7 +322,9 @@ def work_table(n_clips: int, n: int, T: int, n_fft: int = 2048, full: bool = Fal
         t.update({
             "stft_mel_f32_spec": ("hbm", n_clips * (4 * n + 4 * 65), n_clips * T512 * stft_flops_per_frame(2048)),
             "mfcc_finish_kernel": ("hbm", n_clips * (4 * 128 * T512 + 4 * 64), None),
-            "stft_mel_dual_kernel": ("hbm", n_clips * (4 * n + 4 * 64 * T + 4 * 65), n_clips * (T * stft_flops_per_frame(n_fft) + T512 * 4.0 * 1025)),
+            # one FFT per image frame + 4 edge frames of the MFCC chain; the Slaney bank rides on every other image frame
+            "stft_frames_dual": ("hbm", n_clips * (4 * n + 4 * 64 * T + 4 * 65), n_clips * ((T + 4) * stft_flops_per_frame(n_fft) + T512 * 4.0 * 1025)),
+            "stft_frames_mfcc": ("hbm", n_clips * (4 * n + 4 * 65), n_clips * T512 * stft_flops_per_frame(2048)),
             "yin_kernel": ("hbm", n_clips * (4 * n + 8 * T512), n_clips * T512 * 2.0 * 1024 * lags),
             "yin_median_kernel": ("hbm", n_clips * (8 * T512 + 12), None),
             "mlp_ensemble_kernel": ("hbm", n_clips * (4 * 65 + 4 * 47 * 3 + 12), None),
@@ -685,13 +689,14 @@ def run_ours(args):
     env.barrier()
     launches0 = sum(e.launch_count for e in cfg.engines)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(env.local_rank) as clocks:
-        env.barrier()
-        e0.record()
-        for _ in range(args.steps):
-            cfg.step_resident()
-        e1.record()
-        env.barrier()
+    clocks = ClockSampler(env.local_rank)
+    clocks.__enter__()
+    env.barrier()
+    e0.record()
+    for _ in range(args.steps):
+        cfg.step_resident()
+    e1.record()
+    env.barrier()
     launches = sum(e.launch_count for e in cfg.engines) - launches0
     ms = env.max_over_ranks(e0.elapsed_time(e1))
     value = cfg.audio_seconds() * args.steps / (ms * 1e-3)
@@ -705,6 +710,7 @@ def run_ours(args):
         h2d, d2h = cfg.step_host()
     torch.cuda.synchronize(env.device)
     e2e_s = env.max_over_ranks(time.perf_counter() - t0)
+    clocks.__exit__(None, None, None)
     h2d, d2h = env.sum_over_ranks(h2d), env.sum_over_ranks(d2h)
     e2e = {"value": cfg.audio_seconds() * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "ms_per_step": 1e3 * e2e_s / args.steps}

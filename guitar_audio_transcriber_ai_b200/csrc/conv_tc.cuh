@@ -37,7 +37,16 @@ __host__ __device__ constexpr int conv_tc_threads(int epi) { return 32 * (3 + 4 
 // Two groups of four epilogue warps work on alternate 32-channel blocks with their own staging tiles: conv3 has a single
 // accumulator set (TMEM), so its epilogue is exposed, and conv2's epilogue was 93 % busy once the MMAs issued at speed.
 __host__ __device__ constexpr int conv_tc_epi_groups(int cout) { return cout >= 64 ? 2 : 1; }
-constexpr int kTcStageStride = 33;                // floats per staged pixel (32 channels + 1 pad)
+constexpr int kTcStageStride = 33;                // floats per pooled pixel of the mode-2 maps (32 channels + 1 pad)
+// Epilogue staging tile of one 32-channel block, CHANNEL-major: [32 channels][kTcStagePlane floats].  A channel's plane holds
+// the group's pixels row by row with an EVEN row stride (seg rounded up) and one float of lead, so the two horizontal
+// neighbours of every 2x2 pooling window are one 8-byte aligned float2: a lane per pooled pixel reads them with LDS.64 at
+// unit stride - no bank conflicts.  (Round 1 staged pixel-major with a 33-float stride; the pooling reads, two pixels apart,
+// were 2-way conflicted: ncu counted 90 M conflict wavefronts of 115 M in conv2, on the shared-memory port the tensor core
+// fetches its operands through.)
+constexpr int kTcStagePlane = kTcGroupPix + 20;   // 384 pixels + one float of padding per row (R <= kTcMaxRows) + lead, even
+constexpr int kTcMaxRows = kTcStagePlane - kTcGroupPix - 2;      // image rows per group the staged planes have room for
+constexpr int kTcStageFloats = 32 * kTcStagePlane;
 constexpr int kTcPooledPix = kTcGroupPix / 4;     // pooled pixels of one group (epilogue mode 2 keeps them in shared memory)
 
 struct ConvTcParams {
@@ -68,7 +77,7 @@ __host__ __device__ inline size_t conv_tc_smem_bytes(int seg, int nstage) {
     constexpr int EPI = conv_tc_epi_groups(COUT);
     return (size_t)8 * conv_tc_plane_pixels(seg) * 16              // A: 4 + 4 chunk planes (hf, lb) of a 32-channel K block
          + (size_t)nstage * 6 * COUT * 16                          // weight ring (one stage = one tap of one K half)
-         + (size_t)EPI * kTcGroupPix * kTcStageStride * 4          // epilogue staging, one tile per epilogue group
+         + (size_t)EPI * kTcStageFloats * 4                        // epilogue staging, one tile per epilogue group
          + (COUT == 128 ? (size_t)EPI * kTcPooledPix * kTcStageStride * 4 : 0)   // pooled maps of the last conv layer (mode 2)
          + 256;                                                    // barriers, tmem slot, alignment
 }
@@ -91,8 +100,8 @@ __global__ void __launch_bounds__(conv_tc_threads(conv_tc_epi_groups(COUT)), 1) 
     unsigned char* a_buf = smem;                                   // planes 0-3: hf chunks, 4-7: lb chunks
     unsigned char* w_buf = a_buf + (size_t)8 * plane;
     float* staging = reinterpret_cast<float*>(w_buf + (size_t)NSTAGE * W_STAGE);
-    float* pooled = staging + (size_t)EPI * kTcGroupPix * kTcStageStride;   // only present (and used) when COUT == 128
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(staging) + (size_t)EPI * kTcGroupPix * kTcStageStride * 4
+    float* pooled = staging + (size_t)EPI * kTcStageFloats;   // only present (and used) when COUT == 128
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(staging) + (size_t)EPI * kTcStageFloats * 4
                                                  + (COUT == 128 ? (size_t)EPI * kTcPooledPix * kTcStageStride * 4 : 0));
     uint64_t* a_full = bars + 0; uint64_t* a_empty = bars + 2; uint64_t* acc_full = bars + 4; uint64_t* acc_empty = bars + 6;
     uint64_t* w_full = bars + 8; uint64_t* w_empty = bars + 8 + NSTAGE;
@@ -235,7 +244,8 @@ __global__ void __launch_bounds__(conv_tc_threads(conv_tc_epi_groups(COUT)), 1) 
         const int quarter = warp & 3;                       // the TMEM lanes this warp may read: 32*quarter ..
         const int eg = (warp - 2) >> 2;                     // epilogue group: handles channel blocks eg, eg + EPI, ...
         const int et = ((warp - 2) & 3) * 32 + lane;        // thread index inside the group
-        float* const stage_g = staging + (size_t)eg * kTcGroupPix * kTcStageStride;
+        float* const stage_g = staging + (size_t)eg * kTcStageFloats;
+        const int RS = (seg + 1) & ~1;                      // even row stride of the staged planes
         float* const pooled_g = pooled + (size_t)eg * kTcPooledPix * kTcStageStride;
         constexpr int kLastCb = COUT / 32 - 1;
         const int Hpool = p.H / 2, Wpool = p.W / 2;
@@ -261,9 +271,13 @@ __global__ void __launch_bounds__(conv_tc_threads(conv_tc_epi_groups(COUT)), 1) 
                 for (int g = 0; g < kTcTiles; ++g) {
                     float v[32];
                     tmem_ld32(t_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * COUT + cb * 32), v);
-                    float* dst = stage_g + (size_t)(g * 128 + quarter * 32 + lane) * kTcStageStride;
+                    const int pixel = g * 128 + quarter * 32 + lane;      // this thread's accumulator row
+                    const int prow_ = pixel / seg;
+                    float* dst = stage_g + prow_ * RS + (pixel - prow_ * seg) + 1;
+                    if (prow_ < p.R) {                                    // tile slots past the group's R rows hold nothing
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) dst[j] = v[j];
+                        for (int j = 0; j < 32; ++j) dst[j * kTcStagePlane] = v[j];
+                    }
                 }
                 if (cb + EPI > kLastCb) {                   // this group's last block is out of TMEM: (with the others) the next MMAs may start
                     fence_before_thread_sync();
@@ -277,12 +291,14 @@ __global__ void __launch_bounds__(conv_tc_threads(conv_tc_epi_groups(COUT)), 1) 
                     const int rest = item / pcol;
                     const int r = rest % prow, ch8 = rest / prow;
                     const int px = colb * (p.cw / 2) + pxl;
-                    const float* s00 = stage_g + (size_t)(2 * r * seg + 1 + 2 * pxl) * kTcStageStride + ch8 * 8;
-                    const float* s10 = s00 + (size_t)seg * kTcStageStride;
+                    // window = columns 1 + 2 pxl, 2 + 2 pxl of rows 2r, 2r + 1: two aligned float2 per channel
+                    const float* s00 = stage_g + (size_t)(ch8 * 8) * kTcStagePlane + 2 * r * RS + 2 + 2 * pxl;
                     float o[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
-                        const float m = fmaxf(fmaxf(s00[e], s00[kTcStageStride + e]), fmaxf(s10[e], s10[kTcStageStride + e]));
+                        const float2 top = *reinterpret_cast<const float2*>(s00 + e * kTcStagePlane);
+                        const float2 bot = *reinterpret_cast<const float2*>(s00 + e * kTcStagePlane + RS);
+                        const float m = fmaxf(fmaxf(top.x, top.y), fmaxf(bot.x, bot.y));
                         const float z = m * p.w_unscale + __ldg(p.bias + cb * 32 + ch8 * 8 + e);    // exact power-of-two rescale
                         o[e] = z > 0.0f ? z : z * p.slope;
                     }

@@ -756,7 +756,8 @@ ConvTiling conv_tc_tiling(int H, int W, int nstage) {
         if (2 * seg > kTcGroupPix || conv_tc_smem_bytes<COUT>(seg, nstage) > budget) continue;
         ConvTiling t{};
         t.seg = seg; t.cw = cw; t.col_blocks = (W + cw - 1) / cw;
-        const int R = 2 * (kTcGroupPix / (2 * seg));
+        int R = 2 * (kTcGroupPix / (2 * seg));
+        R = R < kTcMaxRows ? R : kTcMaxRows;                          // the epilogue's staged planes pad every row by one float
         t.R = R < hmax ? R : hmax;
         if (t.R < 2) continue;
         t.groups_per_clip = ceil_div(H / 2, t.R / 2) * t.col_blocks;
