@@ -44,21 +44,46 @@ __global__ void __launch_bounds__(128) rms_db_kernel(RmsParams p) {
     const long long base = (long long)(live ? t : 0) * p.hop - 1024;
     const bool interior = base >= 0 && base + 2048 <= p.L;
     float bsum[16];
+    if (interior) {
+        // no padding inside the frame (all but the first and last two): straight indices, fully unrolled
+        const float* f = y + base + sub;
+#pragma unroll
+        for (int blk = 0; blk < 16; ++blk) {
+            float r = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float v = f[blk * 128 + i * 8];
+                if (!(fabsf(v) >= p.sample_gate)) v = 0.0f;
+                const float sq = __fmul_rn(v, v);
+                r = i == 0 ? sq : __fadd_rn(r, sq);            // the first eight values of a block initialise the accumulators
+            }
+            bsum[blk] = r;
+        }
+    } else {
+        // reflect padding (librosa.feature.rms, pad_mode "reflect"): same order, ROLLED - the mirror arithmetic must not be
+        // inlined 256 times into the hot path (it was: 23 k instructions, the kernel ran 10x under its issue rate)
+#pragma unroll
+        for (int blk = 0; blk < 16; ++blk) bsum[blk] = 0.0f;
+#pragma unroll 1
+        for (int blk = 0; blk < 16; ++blk) {
+            float r = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                long long s = base + blk * 128 + i * 8 + sub;
+                // one mirror: the entry points require L > 1024, the padding on each side (gat_segment refuses shorter signals)
+                s = s < 0 ? -s : (s >= p.L ? 2 * (p.L - 1) - s : s);
+                float v = y[s];
+                if (!(fabsf(v) >= p.sample_gate)) v = 0.0f;
+                const float sq = __fmul_rn(v, v);
+                r = i == 0 ? sq : __fadd_rn(r, sq);
+            }
+#pragma unroll
+            for (int b = 0; b < 16; ++b) bsum[b] = b == blk ? r : bsum[b];      // register array: no dynamic indexing
+        }
+    }
 #pragma unroll
     for (int blk = 0; blk < 16; ++blk) {
-        float r = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            long long s = base + blk * 128 + i * 8 + sub;
-            if (!interior && (s < 0 || s >= p.L)) {            // one mirror is enough unless the signal is shorter than the padding
-                const long long m = s < 0 ? -s : 2 * (p.L - 1) - s;
-                s = (m >= 0 && m < p.L) ? m : reflect_index(s, p.L);
-            }
-            float v = y[s];
-            if (!(fabsf(v) >= p.sample_gate)) v = 0.0f;
-            const float sq = __fmul_rn(v, v);
-            r = i == 0 ? sq : __fadd_rn(r, sq);                // the first eight values of a block initialise the accumulators
-        }
+        float r = bsum[blk];
         r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
         r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
         r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));

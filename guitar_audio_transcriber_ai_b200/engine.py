@@ -56,6 +56,7 @@ class Engine:
             self.lib.check(self.lib.gat_ctx_create(C.byref(cfg), self.device.index or 0, C.byref(handle)), ValueError)
         self._ctx = handle
         self._resample_cache = {}
+        self._slicer_cache = {}
         self._host_out = None
         self.mlp_in = 0
 
@@ -340,6 +341,16 @@ class Engine:
 
     def slicer_params(self, L: int, length_sec: float, cfg=None) -> _lib.GatSlicerParams:
         cfg = cfg or SLICER_CONFIG
+        key = (int(L), float(length_sec), float(cfg.MIN_IN_DB_THRESHOLD), float(cfg.MIN_SLICE_RMS_DB), int(cfg.HOP_LEN),
+               float(cfg.MIN_SEP), float(cfg.ATTACK_SKIP_SEC))
+        hit = self._slicer_cache.get(key)
+        if hit is None:
+            if len(self._slicer_cache) > 256:
+                self._slicer_cache.clear()
+            hit = self._slicer_cache[key] = self._slicer_params(L, length_sec, cfg)
+        return hit
+
+    def _slicer_params(self, L: int, length_sec: float, cfg) -> _lib.GatSlicerParams:
         sr = self.sample_rate
         rms_hop = int(cfg.HOP_LEN)
         T = 1 + L // rms_hop

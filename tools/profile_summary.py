@@ -8,7 +8,25 @@ from collections import defaultdict
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 P = pathlib.Path(__file__).resolve().parent.parent / "profiles"
 out = [f"# Profiles `{tag}` (B200, sm_100a)", "",
-       "All captures are of `python bench.py --steps K --warmup W --no-cpu-baseline` (BASELINE configs[1]: 4096 x 1 s clips, mel + CNN).", ""]
+       "The launch list and the live table are of `python bench.py --steps K --warmup W --no-cpu-baseline` (BASELINE configs[1]: 4096 x 1 s clips, "
+       "mel + CNN); the full capture is of `python tools/stft_only.py full` (the same 4096 clips: image chain, MFCC chain, then the fused full "
+       "ensemble), one launch per kernel.", ""]
+INDEX = """## Files of this round
+
+| file | what |
+|---|---|
+| `r02_bench.json`, `r02_bench_reference.json` | the driver's two arms for cfg 2 (`bench.py`, `bench.py --impl reference`) as run by the builder at HEAD |
+| `r02_bench_cfg1.json`, `_cfg3.json`, `_cfg4.json`, `_cfg4_file.json`, `_cfg5_1gpu.json` | `bench.py --config 1 / 3 / 4 / 4 --cfg4-mode file / 5` on one B200 |
+| `r02_cfg4_{1,2,4,8}gpu.json`, `r02_cfg4_file_8gpu.json` | BASELINE configs[3]: one hour of audio at 1 / 2 / 4 / 8 GPUs (phrases sharded; one contiguous file) |
+| `r02_cfg5_8gpu.json`, `r02_cfg3_8gpu.json` | BASELINE configs[4] sweep with the CPU column, and the full ensemble, on 8 GPUs |
+| `r02_h2d_probe.json` | pure pinned H2D copies at 1 / 2 / 4 / 8 ranks (`tools/h2d_probe.py`): the end-to-end ceiling |
+| `r02_parity.json` | error distribution of every stage over all 4096 bench clips (`tools/parity_report.py`) |
+| `r02_launches.csv`, `r02_ncu_full_raw.csv` | ncu launch list and `--set full` raw page at HEAD |
+| `r02_sass_tc.txt` | per-kernel counts of UTCHMMA / LDTM / UBLKCP / UTCBAR / packed-FP32 instructions in the shipped `libgat.so` |
+| `traffic.json` | DRAM bytes per launch from the full capture (bench.py's `roofline.traffic`) |
+| `r02_v1_*`, `r02_v2_*` | earlier states of this round (v1: round-1 kernels + new bench; v2: frame kernel before the packed twiddles) |
+| `r01_*` | round 1 |
+"""
 
 
 def csv_rows(path):
@@ -60,7 +78,8 @@ if fp.exists():
             ("issue active %", "sm__issue_active.avg.pct_of_peak_sustained_elapsed"),
             ("fma pipe %", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
             ("lsu pipe %", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"), ("regs", "launch__registers_per_thread"),
-            ("smem wavefronts", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"), ("warp instructions", "smsp__inst_executed.sum")]
+            ("smem wavefronts", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"), ("smem conflicts", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
+            ("L1 data pipe %", "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed"), ("warp instructions", "smsp__inst_executed.sum")]
     units = rows[0] if rows and not rows[0].get("ID", "").isdigit() else {}
     out += [f"## ncu --set full (one launch each; `profiles/{tag}_ncu_full_raw.csv` holds every metric)", "",
             "| kernel | " + " | ".join(c for c, _ in cols) + " |", "|---|" + "---|" * len(cols)]
@@ -82,5 +101,6 @@ if yp.exists():
             f"inner loop); issue slots {float(g('sm__issue_active.avg.pct_of_peak_sustained_elapsed')):.0f} %, FMA pipe "
             f"{float(g('sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active')):.0f} %, FP64 pipe "
             f"{float(g('sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active')):.1f} %, {g('launch__registers_per_thread')} registers.", ""]
+out.append(INDEX)
 (P / "README.md").write_text("\n".join(out) + "\n")
 print("\n".join(out)[:3000])
