@@ -658,6 +658,22 @@ int launch_yin(gat_ctx* c, const YinParams& p, void* stream) {
     return 0;
 }
 
+// packed-FMA variant (yin_pair_kernel): lags interleaved by parity across the two half-warps
+template <int kLPT>
+int launch_yin_pair(gat_ctx* c, const YinParams& p, void* stream) {
+    const int threads = 384;
+    const size_t per_warp = (yin_pair_smem_per_warp<kLPT>() + 15) / 16 * 16;
+    const size_t smem = (size_t)(threads / 32) * per_warp + 64;
+    auto kfn = yin_pair_kernel<kLPT>;
+    GAT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long work = (long long)p.N * ((p.T + p.seg_frames - 1) / p.seg_frames);
+    const long long ctas = (work + threads / 32 - 1) / (threads / 32);
+    const unsigned grid = (unsigned)(ctas < c->num_sms ? ctas : c->num_sms);
+    KNAME("yin_kernel");
+    LAUNCH(c, kfn, grid, threads, smem, stream, p);
+    return 0;
+}
+
 int run_yin(gat_ctx* c, const float* audio, int64_t N, int64_t n, bool normalize, bool scale_ready, double* hz, double* f0_frames,
             float* feat, int ld, int col, void* stream) {
     const int T = (int)(1 + n / 512);
@@ -681,8 +697,8 @@ int run_yin(gat_ctx* c, const float* audio, int64_t N, int64_t n, bool normalize
     p.seg_frames = T < seg ? T : seg;
     const int lags = p.max_period + 1;
     int rc;
-    if (lags <= 7 * 32) rc = launch_yin<7>(c, p, stream);
-    else if (lags <= 15 * 32) rc = launch_yin<15>(c, p, stream);
+    if (lags <= 7 * 32) rc = launch_yin_pair<7>(c, p, stream);
+    else if (lags <= 15 * 32) rc = launch_yin_pair<15>(c, p, stream);
     else rc = launch_yin<33>(c, p, stream);
     if (rc) return 1;
     YinMedianParams m{f0, (int)N, T, hz, feat, ld, col};

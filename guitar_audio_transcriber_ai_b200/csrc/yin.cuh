@@ -39,6 +39,71 @@ __host__ __device__ inline size_t yin_smem_per_warp() {
     return kYinBuf * sizeof(float) + (size_t)32 * kLPT * sizeof(double);
 }
 
+// Tail of one frame, shared by both difference-function kernels: lane `lane` holds d[tau] for the kLPT CONSECUTIVE lags
+// b .. b + kLPT - 1.  Cumulative-mean normalisation (float32 cumulative sum, float64 division as numpy promotes), first
+// trough under the threshold else the global minimum, parabolic refinement, f0 = sr / period.
+template <int kLPT>
+__device__ __forceinline__ void yin_finish_frame(const float (&dl)[kLPT], int b, const YinParams& p, double* yv, int nl, int clip, int t) {
+    const int lane = lane_id();
+    const double tiny = 1.1754943508222875e-38;                    // np.finfo(float32).tiny
+    // cumulative sum over tau = 1..max_period (blocked: in-lane sequential + warp scan of lane totals)
+    float run = 0.0f, cl[kLPT];
+#pragma unroll
+    for (int i = 0; i < kLPT; ++i) {
+        const int tau = b + i;
+        if (tau >= 1 && tau <= p.max_period) run += dl[i];
+        cl[i] = run;
+    }
+    float offs = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float u = __shfl_up_sync(0xffffffffu, offs, o);
+        if (lane >= o) offs += u;
+    }
+    offs -= run;                                        // exclusive prefix of lane totals
+#pragma unroll
+    for (int i = 0; i < kLPT; ++i) {
+        const int tau = b + i;
+        if (tau >= p.min_period && tau <= p.max_period) {
+            const double cm = (double)(offs + cl[i]) / (double)tau;
+            yv[tau - p.min_period] = (double)dl[i] / (cm + tiny);
+        }
+    }
+    __syncwarp();
+    // first trough under the threshold, else the global minimum (first occurrence)
+    int first = 0x7fffffff;
+    double best = 1e300; int best_i = 0x7fffffff;
+    for (int i = lane; i < nl; i += 32) {
+        const double y0 = yv[i];
+        bool trough;
+        if (i == 0) trough = nl > 1 && y0 < yv[1];
+        else if (i == nl - 1) trough = y0 < yv[i - 1];
+        else trough = (y0 < yv[i - 1]) && (y0 <= yv[i + 1]);
+        if (trough && y0 < p.trough_threshold && i < first) first = i;
+        if (y0 < best) { best = y0; best_i = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int f2 = __shfl_xor_sync(0xffffffffu, first, o);
+        first = f2 < first ? f2 : first;
+        const double b2 = __shfl_xor_sync(0xffffffffu, best, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (b2 < best || (b2 == best && i2 < best_i)) { best = b2; best_i = i2; }
+    }
+    if (lane == 0) {
+        const int idx = first != 0x7fffffff ? first : (best_i != 0x7fffffff ? best_i : 0);
+        double shift = 0.0;
+        if (idx > 0 && idx < nl - 1) {
+            const double ym = yv[idx - 1], y0 = yv[idx], yp = yv[idx + 1];
+            const double aa = yp + ym - 2.0 * y0;
+            const double bb = (yp - ym) / 2.0;
+            if (!(fabs(bb) >= fabs(aa))) shift = -bb / aa;
+        }
+        p.f0[(long long)clip * p.T + t] = (double)p.sr / ((double)(p.min_period + idx) + shift);
+    }
+    __syncwarp();
+}
+
 template <int kLPT>
 __global__ void __launch_bounds__(384, 1) yin_kernel(YinParams p) {
     GAT_DYN_SMEM(smem_raw);
@@ -48,7 +113,6 @@ __global__ void __launch_bounds__(384, 1) yin_kernel(YinParams p) {
     float* buf = reinterpret_cast<float*>(base);
     double* yv = reinterpret_cast<double*>(buf + kYinBuf);          // CMND, index tau - min_period
     const int nl = p.max_period - p.min_period + 1;
-    const double tiny = 1.1754943508222875e-38;                    // np.finfo(float32).tiny
     // samples a block needs, counted from the start of the PREVIOUS block (whose frame is finalised with it)
     constexpr int kSpan = 2 * kYinBlock + 33 * kLPT + 1;
     constexpr int kBlocksPerFill = (kYinBuf - kSpan) / kYinBlock + 1;
@@ -155,65 +219,165 @@ __global__ void __launch_bounds__(384, 1) yin_kernel(YinParams p) {
                     const float xin = fx[tau + kYinWin + 1], xout = fx[tau + 1];
                     e_tau = e_tau + xin * xin - xout * xout;
                 }
-                // cumulative sum over tau = 1..max_period (blocked: in-lane sequential + warp scan of lane totals)
-                float run = 0.0f, cl[kLPT];
-#pragma unroll
-                for (int i = 0; i < kLPT; ++i) {
-                    const int tau = b + i;
-                    if (tau >= 1 && tau <= p.max_period) run += dl[i];
-                    cl[i] = run;
-                }
-                float offs = run;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const float u = __shfl_up_sync(0xffffffffu, offs, o);
-                    if (lane >= o) offs += u;
-                }
-                offs -= run;                                        // exclusive prefix of lane totals
-#pragma unroll
-                for (int i = 0; i < kLPT; ++i) {
-                    const int tau = b + i;
-                    if (tau >= p.min_period && tau <= p.max_period) {
-                        const double cm = (double)(offs + cl[i]) / (double)tau;
-                        yv[tau - p.min_period] = (double)dl[i] / (cm + tiny);
-                    }
-                }
-                __syncwarp();
-                // first trough under the threshold, else the global minimum (first occurrence)
-                int first = 0x7fffffff;
-                double best = 1e300; int best_i = 0x7fffffff;
-                for (int i = lane; i < nl; i += 32) {
-                    const double y0 = yv[i];
-                    bool trough;
-                    if (i == 0) trough = nl > 1 && y0 < yv[1];
-                    else if (i == nl - 1) trough = y0 < yv[i - 1];
-                    else trough = (y0 < yv[i - 1]) && (y0 <= yv[i + 1]);
-                    if (trough && y0 < p.trough_threshold && i < first) first = i;
-                    if (y0 < best) { best = y0; best_i = i; }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const int f2 = __shfl_xor_sync(0xffffffffu, first, o);
-                    first = f2 < first ? f2 : first;
-                    const double b2 = __shfl_xor_sync(0xffffffffu, best, o);
-                    const int i2 = __shfl_xor_sync(0xffffffffu, best_i, o);
-                    if (b2 < best || (b2 == best && i2 < best_i)) { best = b2; best_i = i2; }
-                }
-                if (lane == 0) {
-                    const int idx = first != 0x7fffffff ? first : (best_i != 0x7fffffff ? best_i : 0);
-                    double shift = 0.0;
-                    if (idx > 0 && idx < nl - 1) {
-                        const double ym = yv[idx - 1], y0 = yv[idx], yp = yv[idx + 1];
-                        const double aa = yp + ym - 2.0 * y0;
-                        const double bb = (yp - ym) / 2.0;
-                        if (!(fabs(bb) >= fabs(aa))) shift = -bb / aa;
-                    }
-                    p.f0[(long long)clip * p.T + t] = (double)p.sr / ((double)(p.min_period + idx) + shift);
-                }
+                yin_finish_frame<kLPT>(dl, b, p, yv, nl, clip, t);
                 __syncwarp();
             }
 #pragma unroll
             for (int q = 0; q < kLPT; ++q) prev_acc[q] = acc[q];
+            prev_e = e_blk;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The same difference function with the packed FP32 FMA of sm_100 (FFMA2, fma.rn.f32x2): round 2.
+// The scalar kernel above issues one FFMA per (sample j, lag); ncu had it at 66 % issue utilisation with the FMA pipe half
+// busy.  Here a lane's accumulators are PAIRS over two consecutive samples, (sum over odd j, sum over even j), updated by
+//     (accA, accB)[lag] += (x[j], x[j+1]) * (x[j+lag], x[j+1+lag])
+// - one instruction for two products.  The right-hand pair starts at index j + lag; for it to stay an aligned register pair
+// while j advances by two, a lane owns lags of ONE parity, two apart: lane = 16*parity + m owns 2*(kLPT*m + i) + parity.
+// The window of 2*kLPT samples lives in kLPT register pairs (a ring, as before).  acf = accA + accB at the end of a block:
+// the summation order differs from the scalar kernel's (and from librosa's FFT autocorrelation) at float32 rounding level.
+// After a frame's two blocks the d values go through shared memory once so that the cumulative sum runs with the
+// consecutive-lag lane mapping of yin_finish_frame.
+constexpr int kYinPairBuf = 3072;
+
+template <int kLPT>
+__host__ __device__ inline size_t yin_pair_smem_per_warp() {
+    return (kYinPairBuf + 2) * sizeof(float) + (size_t)32 * kLPT * sizeof(double) + (size_t)(32 * kLPT + 2) * sizeof(float);
+}
+
+template <int kLPT>
+__global__ void __launch_bounds__(384, 1) yin_pair_kernel(YinParams p) {
+    GAT_DYN_SMEM(smem_raw);
+    const int nwarps = blockDim.x >> 5;
+    const int lane = lane_id(), warp = warp_id();
+    unsigned char* base = smem_raw + (size_t)warp * ((yin_pair_smem_per_warp<kLPT>() + 15) / 16 * 16);
+    float* buf = reinterpret_cast<float*>(base);                            // buf[i] = padded[buf_base - 1 + i]: sample 512*blk + 1 sits at an even index
+    double* yv = reinterpret_cast<double*>(buf + kYinPairBuf + 2);          // CMND, index tau - min_period
+    float* dsm = reinterpret_cast<float*>(yv + 32 * kLPT);                  // d[tau] of the frame being finished
+    const int nl = p.max_period - p.min_period + 1;
+    constexpr int kLags = 32 * kLPT;
+    // samples a block needs, counted from the start of the PREVIOUS block (whose frame is finalised with it): the energy
+    // slide of the finish reads fx[tau + 1026] with fx = xs - 512, the inner loop xs[512 + kLags + 1]
+    constexpr int kSpan = 2 * kYinBlock + kLags + 2 * kLPT + 4;
+    constexpr int kBlocksPerFill = (kYinPairBuf - kSpan) / kYinBlock + 1;
+    static_assert(kSpan <= kYinPairBuf, "kYinPairBuf too small for this lag tile");
+
+    const int par = lane >> 4, m = lane & 15;
+    const int b = 2 * kLPT * m + par;                                       // this lane's first lag; its lags are b, b + 2, ...
+
+    const int n_seg = (p.T + p.seg_frames - 1) / p.seg_frames;
+    const long long n_work = (long long)p.N * n_seg;
+    for (long long work = (long long)blockIdx.x * nwarps + warp; work < n_work; work += (long long)gridDim.x * nwarps) {
+        const int clip = (int)(work / n_seg);
+        const int f0 = (int)(work % n_seg) * p.seg_frames;
+        const int nf = min(p.seg_frames, p.T - f0);
+        const float* src = p.audio + (long long)clip * p.n;
+        const float c = p.clip_scale ? p.clip_scale[clip] : 1.0f;
+        auto padded = [&](long long i) {                            // centre-padded, normalised signal
+            const long long s = i - kYinFrame / 2;
+            float v = (s >= 0 && s < p.n) ? src[s] : 0.0f;
+            if (p.clip_scale) v = __fdiv_rn(v, c);
+            return v;
+        };
+        float prev_acc[kLPT], prev_e = 0.0f;
+#pragma unroll
+        for (int q = 0; q < kLPT; ++q) prev_acc[q] = 0.0f;
+        long long buf_base = 0;                                     // padded index of buf[1]
+        int fill_left = 0;
+
+        for (int blk = f0; blk <= f0 + nf; ++blk) {
+            // ---- keep padded[512*(blk-1) .. +kSpan) resident (buf[0] is the sample before it)
+            if (fill_left == 0) {
+                __syncwarp();
+                const long long nb = (long long)kYinBlock * (blk - 1);
+                auto fill = [&](int first) {
+                    for (int i0 = first + lane; i0 < kYinPairBuf; i0 += 32 * 8) {
+                        float v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) { const int i = i0 + 32 * u; v[u] = i < kYinPairBuf ? padded(nb - 1 + i) : 0.0f; }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) { const int i = i0 + 32 * u; if (i < kYinPairBuf) buf[i] = v[u]; }
+                    }
+                };
+                if (blk == f0) {
+                    fill(0);
+                } else {                                            // slide: keep the tail, load the rest (shift is a multiple of 32)
+                    const int keep = (int)(buf_base + kYinPairBuf - nb), off = kYinPairBuf - keep;
+                    for (int i = lane; i < keep; i += 32) buf[i] = buf[i + off];
+                    fill(keep);
+                }
+                buf_base = nb;
+                fill_left = kBlocksPerFill;
+                __syncwarp();
+            }
+            --fill_left;
+            const float* xs = buf + 1 + (int)((long long)kYinBlock * blk - buf_base);    // xs[j] = padded[512*blk + j]; &xs[1] is 8-byte aligned
+
+            // ---- block partials over sample pairs (j, j+1), j = 1, 3, ..., 511
+            float2 ring[kLPT], acc[kLPT];
+#pragma unroll
+            for (int q = 0; q < kLPT; ++q) { ring[q] = make_float2(xs[1 + b + 2 * q], xs[2 + b + 2 * q]); acc[q] = make_float2(0.0f, 0.0f); }
+            float2 e2 = make_float2(0.0f, 0.0f);
+            constexpr int kSteps = kYinBlock / 2;                   // 256 sample pairs
+            constexpr int kFull = kSteps / kLPT;
+            for (int it = 0; it < kFull; ++it) {
+                const int j0 = 1 + 2 * it * kLPT;
+#pragma unroll
+                for (int s = 0; s < kLPT; ++s) {
+                    const int j = j0 + 2 * s;
+                    const float2 xp = *reinterpret_cast<const float2*>(xs + j);          // broadcast load
+#pragma unroll
+                    for (int i = 0; i < kLPT; ++i) acc[i] = __ffma2_rn(xp, ring[(s + i) % kLPT], acc[i]);
+                    e2 = __ffma2_rn(ring[s], ring[s], e2);
+                    ring[s] = make_float2(xs[j + b + 2 * kLPT], xs[j + b + 2 * kLPT + 1]);
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < kSteps - kFull * kLPT; ++s) {       // the last, partial round
+                const int j = 1 + 2 * (kFull * kLPT + s);
+                const float2 xp = *reinterpret_cast<const float2*>(xs + j);
+#pragma unroll
+                for (int i = 0; i < kLPT; ++i) acc[i] = __ffma2_rn(xp, ring[(s + i) % kLPT], acc[i]);
+                e2 = __ffma2_rn(ring[s], ring[s], e2);
+                ring[s] = make_float2(xs[j + b + 2 * kLPT], xs[j + b + 2 * kLPT + 1]);
+            }
+            float accs[kLPT];
+#pragma unroll
+            for (int q = 0; q < kLPT; ++q) accs[q] = acc[q].x + acc[q].y;
+            const float e_blk = e2.x + e2.y;                        // sum_{j=1..512} xs[j + b]^2
+            if (blk > f0) {
+                // ---- frame t = blk - 1: acf = previous block + this block
+                const int t = blk - 1;
+                const float* fx = xs - kYinBlock;                   // fx[j] = padded[512*t + j]
+                float e_b = prev_e + e_blk;                         // E[b] = sum_{j=1..1024} x[j+b]^2
+                float e0 = __shfl_sync(0xffffffffu, e_b, 0);        // lane 0 owns lag 0
+                if (fabsf(e0) < 1e-6f) e0 = 0.0f;
+                float e_tau = e_b;
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < kLPT; ++i) {
+                    const int tau = b + 2 * i;
+                    float a = prev_acc[i] + accs[i];
+                    if (fabsf(a) < 1e-6f) a = 0.0f;
+                    float e = e_tau;
+                    if (fabsf(e) < 1e-6f) e = 0.0f;
+                    dsm[tau] = __fsub_rn(__fadd_rn(e0, e), __fmul_rn(2.0f, a));
+                    // slide the energy window two lags on: E[tau+1] = E[tau] + x[tau+1025]^2 - x[tau+1]^2, twice
+                    const float in1 = fx[tau + kYinWin + 1], out1 = fx[tau + 1];
+                    e_tau = e_tau + in1 * in1 - out1 * out1;
+                    const float in2 = fx[tau + kYinWin + 2], out2 = fx[tau + 2];
+                    e_tau = e_tau + in2 * in2 - out2 * out2;
+                }
+                __syncwarp();
+                float dl[kLPT];
+#pragma unroll
+                for (int i = 0; i < kLPT; ++i) dl[i] = dsm[kLPT * lane + i];
+                yin_finish_frame<kLPT>(dl, kLPT * lane, p, yv, nl, clip, t);
+            }
+#pragma unroll
+            for (int q = 0; q < kLPT; ++q) prev_acc[q] = accs[q];
             prev_e = e_blk;
         }
     }
