@@ -993,15 +993,29 @@ int onset_chain(gat_ctx* c, const float* y, int64_t P, int64_t L, const gat_slic
     if (c->spec.ensure(PT * 128 * sizeof(double)) || c->seg_env.ensure(PT * 8) || c->seg_envn.ensure(PT * 8) ||
         c->seg_cand.ensure((size_t)P * words * 4) || c->seg_peaks.ensure(PT * 4) || c->seg_frames.ensure(PT * 8) ||
         c->seg_table.ensure((size_t)P * max_onsets * 3 * 8)) return 1;
-    StftMelParams<double> p{};
-    p.audio = y; p.n = L; p.N = (int)P; p.clip_scale = nullptr;
-    p.frame_gate = gated ? c->seg_gate.as<unsigned char>() : nullptr;
-    p.gate_stride = 1 + L / sp->rms_hop;
-    p.sample_gate = gated ? sp->sample_gate : 0.0f; p.gate_hop = sp->rms_hop;
-    p.hop = sp->onset_hop; p.n_frames = To; p.pad_mode = kPadZero;
-    p.window = c->win64.as<double>(); p.tw = c->tw64.as<Cpx<double>>(); p.w2 = c->w2_64.as<Cpx<double>>();
-    p.fb = c->fb_mfcc.view(); p.amin = 1e-10; p.out = c->spec.as<double>(); p.spec_max = sc.spec_max;
-    if (launch_stft_mel<double, kOutSpec, 192, 32>(c, p, st)) return 1;
+    {   // float64 STFT -> Slaney mel-128 -> dB, one warp per frame (csrc/stft2.cuh)
+        OnsetFramesParams q{};
+        q.audio = y; q.n = L; q.N = (int)P;
+        q.frame_gate = gated ? c->seg_gate.as<unsigned char>() : nullptr;
+        q.gate_stride = 1 + L / sp->rms_hop; q.gate_hop = sp->rms_hop; q.sample_gate = gated ? sp->sample_gate : 0.0f;
+        q.gate_shift = -1;
+        for (int sh = 0; sh < 30; ++sh) if ((1 << sh) == sp->rms_hop) q.gate_shift = sh;
+        q.hop = sp->onset_hop; q.T = To;
+        q.window = c->win64.as<double>(); q.tw = c->tw64.as<Cpx<double>>(); q.w2 = c->w2_64.as<Cpx<double>>();
+        q.fb = c->fb_mfcc.view(); q.amin = 1e-10; q.out = c->spec.as<double>(); q.spec_max = sc.spec_max;
+        constexpr int kOnsetThreads = 256;
+        const size_t smem = onset_frames_smem_bytes(kOnsetThreads / 32, q.fb.nnz + 3);
+        if (smem > 227 * 1024) return fail("onset_frames: %zu bytes of shared memory needed", smem);
+        const long long n_items = (long long)P * To;
+        long long ctas = (n_items + kOnsetThreads / 32 - 1) / (kOnsetThreads / 32);
+        ctas = ctas < c->num_sms ? ctas : c->num_sms;
+        q.items_per_cta = (n_items + ctas - 1) / ctas;
+        ctas = (n_items + q.items_per_cta - 1) / q.items_per_cta;
+        auto kfn = onset_frames_kernel<kOnsetThreads>;
+        GAT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KNAME("stft_mel_f64_spec");
+        LAUNCH(c, kfn, (unsigned)ctas, kOnsetThreads, smem, st, q);
+    }
 
     // flux envelope -> normalise + candidate peaks -> sequential wait rule
     const dim3 frames_grid((unsigned)ceil_div(To, 128), (unsigned)P);

@@ -140,18 +140,19 @@ __device__ __forceinline__ void mfcc_finish_warp(const StftFramesParams& p, int 
 // of the butterfly code (a rolled two-trip loop).  Warps of this kernel run unsynchronised, each somewhere else in the
 // frame's code: the per-frame instruction footprint has to fit the 32 KB L1.5 instruction cache (the first version,
 // fully unrolled with an inlined padding path, was 166 KB and ncu's top stall was "no instruction").
-__device__ __forceinline__ void frame_fft_power(Cpx<float> (&v)[32], Cpx<float>* xbuf, const FftTables<float, kStft2P>* tab) {
+template <typename T>
+__device__ __forceinline__ void frame_fft_power(Cpx<T> (&v)[32], Cpx<T>* xbuf, const FftTables<T, kStft2P>* tab) {
     constexpr int C = 1024;
     const int lane = lane_id();
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
-        fft_dif<float, 32, 0, 32>(v);
+        fft_dif<T, 32, 0, 32>(v);
         if (pass == 0) {
             // twiddle by W_C^(n1*k2), n1 = lane, and transpose: row k2, column n1
 #pragma unroll
             for (int r = 0; r < 32; ++r) {
                 const int k2 = bitrev5(r);
-                const Cpx<float> w = tab->tw[k2 * 32 + lane];
+                const Cpx<T> w = tab->tw[k2 * 32 + lane];
                 xbuf[k2 * kXbufStride + lane] = (k2 == 0) ? v[r] : cmul(v[r], w);
             }
             __syncwarp();
@@ -162,26 +163,26 @@ __device__ __forceinline__ void frame_fft_power(Cpx<float> (&v)[32], Cpx<float>*
     }
     // v[bitrev5(k1)] = Z[32*k1 + lane]; Hermitian partner Z[C-k] sits in lane (32 - lane) % 32 at k1' = 31 - k1
     // (lane 0 pairs with itself at k1' = (32 - k1) % 32).  Bins k and C-k share E and T: |E+T|^2, |E-T|^2.
-    float* pb = reinterpret_cast<float*>(xbuf);
+    T* pb = reinterpret_cast<T*>(xbuf);
     const int partner = (32 - lane) & 31;
-    pb[lane] = 0.0f;                                           // kPbufLead zeros below bin 0
-    if (lane < 4) pb[kPbufLead + C + 1 + lane] = 0.0f;         // tail read (times zero weights) by the vectorised mel loop
+    pb[lane] = (T)0;                                           // kPbufLead zeros below bin 0
+    if (lane < 4) pb[kPbufLead + C + 1 + lane] = (T)0;         // tail read (times zero weights) by the vectorised mel loop
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) {
-        const Cpx<float> other = v[bitrev5(31 - k1)];
-        const Cpx<float> self = v[bitrev5((32 - k1) & 31)];
-        const float bx = __shfl_sync(0xffffffffu, other.x, partner);
-        const float by = __shfl_sync(0xffffffffu, other.y, partner);
-        const Cpx<float> b = lane == 0 ? self : Cpx<float>{bx, by};
+        const Cpx<T> other = v[bitrev5(31 - k1)];
+        const Cpx<T> self = v[bitrev5((32 - k1) & 31)];
+        const T bx = __shfl_sync(0xffffffffu, other.x, partner);
+        const T by = __shfl_sync(0xffffffffu, other.y, partner);
+        const Cpx<T> b = lane == 0 ? self : Cpx<T>{bx, by};
         const int k = 32 * k1 + lane;
-        float p_lo, p_hi;
-        split_pair_power<float>(v[bitrev5(k1)], b, tab->w2[k], p_lo, p_hi);
+        T p_lo, p_hi;
+        split_pair_power<T>(v[bitrev5(k1)], b, tab->w2[k], p_lo, p_hi);
         pb[kPbufLead + k] = p_lo;
         pb[kPbufLead + C - k] = p_hi;
     }
     if (lane == 0) {                                           // k = C/2 pairs with itself: W^(C/2) = -i
-        const Cpx<float> a = v[bitrev5(16)];
-        const float er = a.x + a.x, orr = a.y + a.y;
+        const Cpx<T> a = v[bitrev5(16)];
+        const T er = a.x + a.x, orr = a.y + a.y;
         pb[kPbufLead + C / 2] = er * er + orr * orr;
     }
     __syncwarp();
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) stft_frames_kernel(StftFramesPara
 #endif
         }
         __syncwarp();                                // staged samples are consumed before the transpose reuses the scratch
-        frame_fft_power(v, xbuf, tab);
+        frame_fft_power<float>(v, xbuf, tab);
         const float* pf = pbuf + kPbufLead;
         float ic2 = 1.0f;
         if ((do_img && p.norm_img) || (do_spec && p.norm_spec)) { const float ic = 1.0f / p.clip_scale[clip]; ic2 = ic * ic; }
@@ -316,6 +317,151 @@ __global__ void __launch_bounds__(kThreads, 1) stft_frames_kernel(StftFramesPara
             }
         }
         __syncwarp();                                 // pbuf (= xbuf) is rewritten by the next frame's transpose
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The float64 mel spectrogram of the onset chain (audio/slicing.py:107, librosa.onset.onset_strength on the float64 gated
+// signal) in the same frame-per-warp form: zero centre padding, any even hop, the two gates of sliceNsave fused into the
+// loads (sample gate |y| >= g, per-block frame gate), Slaney mel-128, 10 log10, per-signal running maximum.
+// The chunked kernel it replaces (stft_mel_kernel<double>) ran six warps in lock step between block barriers and was the
+// largest kernel of the hour-long configuration; FP64 arithmetic is latency-bound at this occupancy (255 registers), so
+// what helps is two more warps (no staging buffers) and warps that do not wait for each other.
+struct OnsetFramesParams {
+    const float* audio; long long n; int N;          // [N][n] signals
+    const unsigned char* frame_gate;                 // [N][gate_stride] keep flags per gate_hop samples, or nullptr
+    long long gate_stride; int gate_hop; float sample_gate;   // sample_gate == 0 disables both gates
+    int gate_shift;                                  // log2(gate_hop) when it is a power of two (512), else -1
+    int hop; int T;                                  // frames per signal = 1 + n / hop
+    const double* window;                            // [2048] float64 Hann (scipy)
+    const Cpx<double>* tw; const Cpx<double>* w2;
+    SparseFb fb; double amin;
+    double* out;                                     // [N][T][n_mels] mel dB
+    long long* spec_max;                             // [N] ordered-integer encoded maxima
+    long long items_per_cta;
+};
+
+__host__ __device__ inline size_t onset_frames_smem_bytes(int nwarps, int nnz) {
+    return sizeof(FftTables<double, kStft2P>) + kStft2N * sizeof(double) + (size_t)4 * kMaxMelsPerLane * 32 * sizeof(int)
+         + ((size_t)nnz + 3) / 4 * 4 * sizeof(float) + (size_t)nwarps * FftGeom<kStft2P>::kXbufElems * sizeof(Cpx<double>) + 64;
+}
+
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads, 1) onset_frames_kernel(OnsetFramesParams p) {
+    using G = FftGeom<kStft2P>;
+    GAT_DYN_SMEM(smem_raw);
+    const int nwarps = kThreads / 32;
+    const int lane = lane_id(), warp = warp_id();
+    unsigned char* sp = smem_raw;
+    FftTables<double, kStft2P>* tab = reinterpret_cast<FftTables<double, kStft2P>*>(sp);  sp += sizeof(FftTables<double, kStft2P>);
+    double* win = reinterpret_cast<double*>(sp);               sp += kStft2N * sizeof(double);
+    constexpr int kSlotEntries = kMaxMelsPerLane * 32;
+    int* fb_start = reinterpret_cast<int*>(sp);                sp += kSlotEntries * sizeof(int);
+    int* fb_len = reinterpret_cast<int*>(sp);                  sp += kSlotEntries * sizeof(int);
+    int* fb_off = reinterpret_cast<int*>(sp);                  sp += kSlotEntries * sizeof(int);
+    int* fb_mel = reinterpret_cast<int*>(sp);                  sp += kSlotEntries * sizeof(int);
+    float* fb_w = reinterpret_cast<float*>(sp);                sp += ((size_t)p.fb.nnz + 3) / 4 * 4 * sizeof(float);
+    Cpx<double>* xbuf = reinterpret_cast<Cpx<double>*>(sp) + (size_t)warp * G::kXbufElems;
+    double* pbuf = reinterpret_cast<double*>(xbuf);
+    float* stage = reinterpret_cast<float*>(xbuf);             // 2048 floats of the warp's scratch while a padded frame is staged
+
+    fill_fft_tables<double, kStft2P>(tab, p.tw, p.w2);
+    for (int i = threadIdx.x; i < kStft2N; i += kThreads) win[i] = 0.5 * p.window[i];     // 1/2 of the Hermitian split, exact
+    for (int i = threadIdx.x; i < kSlotEntries; i += kThreads) {
+        const bool live = i < p.fb.n_slots * 32;
+        fb_start[i] = live ? p.fb.start[i] : 0; fb_len[i] = live ? p.fb.len[i] : 0;
+        fb_off[i] = live ? p.fb.off[i] : 0;     fb_mel[i] = live ? p.fb.mel[i] : -1;
+    }
+    for (int i = threadIdx.x; i < p.fb.nnz; i += kThreads) fb_w[i] = p.fb.w[i];
+    __syncthreads();
+    const Cpx<double>* win2 = reinterpret_cast<const Cpx<double>*>(win);
+    const bool gated = p.sample_gate > 0.0f;
+
+    const long long n_items = (long long)p.N * p.T;
+    const long long lo = (long long)blockIdx.x * p.items_per_cta;
+    long long hi = lo + p.items_per_cta;
+    hi = hi > n_items ? n_items : hi;
+    for (long long item = lo + warp; item < hi; item += nwarps) {
+        const int clip = (int)(item / p.T);
+        const int t = (int)(item - (long long)clip * p.T);
+        const long long s0 = (long long)t * p.hop - kStft2N / 2;
+        const float* src = p.audio + (long long)clip * p.n;
+        const unsigned char* fg = p.frame_gate ? p.frame_gate + (long long)clip * p.gate_stride : nullptr;
+        // apply_db_threshold then apply_rms_threshold (slicing.py:30-39, :78-91); positions inside a signal fit 32 bits, and
+        // the block index is a shift for the reference's hop of 512 (a 64-bit division per sample dominated the first version)
+        auto gate = [&](float v, int s) {
+            if (gated) {
+                if (!(fabsf(v) >= p.sample_gate)) v = 0.0f;
+                if (fg && !fg[p.gate_shift >= 0 ? (s >> p.gate_shift) : (s / p.gate_hop)]) v = 0.0f;
+            }
+            return v;
+        };
+        Cpx<double> v[G::V];
+        const bool interior = s0 >= 0 && s0 + kStft2N <= p.n;
+        const bool aligned = (reinterpret_cast<unsigned long long>(src + s0) & 7ull) == 0ull;
+        if (interior && aligned && (!fg || (p.gate_shift >= 1))) {       // other gate hops go through the staged path below
+            const float2* g = reinterpret_cast<const float2*>(src + s0);
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const int j = lane + 32 * r;
+                const float2 x = g[j];
+                const Cpx<double> w = win2[j];
+                const int s = (int)s0 + 2 * j;                // both samples of the pair lie in the same gate block (hop even)
+                float gx = x.x, gy = x.y;
+                if (gated) {
+                    if (!(fabsf(gx) >= p.sample_gate)) gx = 0.0f;
+                    if (!(fabsf(gy) >= p.sample_gate)) gy = 0.0f;
+                    if (fg && !fg[s >> p.gate_shift]) { gx = 0.0f; gy = 0.0f; }
+                }
+                v[r] = Cpx<double>{(double)gx * w.x, (double)gy * w.y};
+            }
+        } else {
+            // padded (zeros outside the signal) or misaligned: stage the gated samples as floats through the warp's scratch
+#pragma unroll 1
+            for (int e = lane; e < kStft2N; e += 32) {
+                const long long s = s0 + e;
+                stage[e] = (s >= 0 && s < p.n) ? gate(src[s], (int)s) : 0.0f;
+            }
+            __syncwarp();
+            const float2* g = reinterpret_cast<const float2*>(stage);
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const int j = lane + 32 * r;
+                const float2 x = g[j];
+                const Cpx<double> w = win2[j];
+                v[r] = Cpx<double>{(double)x.x * w.x, (double)x.y * w.y};
+            }
+            __syncwarp();
+        }
+        frame_fft_power<double>(v, xbuf, tab);
+        const double* pf = pbuf + kPbufLead;
+        // banded-sparse Slaney filterbank, sequential accumulation per filter (the order of the kernel this replaces)
+        double wmax = -1e300;
+        double* dst = p.out + ((long long)clip * p.T + t) * p.fb.n_mels;
+        for (int q = 0; q < p.fb.n_slots; ++q) {
+            const int e = q * 32 + lane;
+            const int m = fb_mel[e];
+            const int ln = fb_len[e];
+            const Vec4<double>* pb = reinterpret_cast<const Vec4<double>*>(pf + fb_start[e]);
+            const float4* w = reinterpret_cast<const float4*>(fb_w + fb_off[e]);
+            double acc = 0.0;
+            for (int k = 0; k < ln; ++k) {
+                const Vec4<double> pv = pb[k];
+                const float4 wv = w[k];
+                acc += pv.x * (double)wv.x;
+                acc += pv.y * (double)wv.y;
+                acc += pv.z * (double)wv.z;
+                acc += pv.w * (double)wv.w;
+            }
+            if (m >= 0) {
+                const double db = db10(acc > p.amin ? acc : p.amin);
+                dst[m] = db;
+                wmax = db > wmax ? db : wmax;
+            }
+        }
+        wmax = warp_max(wmax);
+        if (lane == 0) atomicMax(p.spec_max + clip, ordered_bits(wmax));
+        __syncwarp();                                 // pbuf (= xbuf) is rewritten by the next frame
     }
 }
 
