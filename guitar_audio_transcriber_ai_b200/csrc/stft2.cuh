@@ -225,8 +225,9 @@ __global__ void __launch_bounds__(kThreads, 1) stft_frames_kernel(StftFramesPara
     const long long lo = (long long)blockIdx.x * p.items_per_cta;
     long long hi = lo + p.items_per_cta;
     hi = hi > n_items ? n_items : hi;
+    const bool small = n_items <= 0x7fffffffLL;                     // 32-bit item arithmetic (a 64-bit division costs ~100 instructions)
     for (long long item = lo + warp; item < hi; item += nwarps) {
-        const int clip = (int)(item / ipc);
+        const int clip = small ? (int)((unsigned)item / (unsigned)ipc) : (int)(item / ipc);
         const int i = (int)(item - (long long)clip * ipc);
         // which frame: image frame t (reflect padding), possibly carrying spec frame u too; or a spec-only frame u (zero padding)
         bool do_img = false, do_spec = false;
@@ -258,15 +259,21 @@ __global__ void __launch_bounds__(kThreads, 1) stft_frames_kernel(StftFramesPara
             const bool reflect = do_img;
             const int n32 = (int)p.n, s32 = (int)s0;          // a clip has fewer than 2^31 samples
 #pragma unroll 1
-            for (int e = lane; e < kStft2N; e += 32) {
-                int s = s32 + e;
-                bool inside = s >= 0 && s < n32;
-                if (!inside && reflect) {            // one mirror suffices: the launcher requires n > n_fft / 2
-                    const int m = s < 0 ? -s : 2 * (n32 - 1) - s;
-                    s = (m >= 0 && m < n32) ? m : (int)reflect_index(s, p.n);
-                    inside = true;
+            for (int e0 = lane; e0 < kStft2N; e0 += 32 * 8) {        // eight loads in flight per lane: the loop is latency-bound
+                float val[8];
+#pragma unroll
+                for (int u8 = 0; u8 < 8; ++u8) {
+                    int s = s32 + e0 + 32 * u8;
+                    bool inside = s >= 0 && s < n32;
+                    if (!inside && reflect) {        // one mirror suffices: the launcher requires n > n_fft / 2
+                        const int m = s < 0 ? -s : 2 * (n32 - 1) - s;
+                        inside = m >= 0 && m < n32;
+                        s = m;
+                    }
+                    val[u8] = inside ? src[s] : 0.0f;
                 }
-                pbuf[e] = inside ? src[s] : 0.0f;
+#pragma unroll
+                for (int u8 = 0; u8 < 8; ++u8) pbuf[e0 + 32 * u8] = val[u8];
             }
             __syncwarp();
             g = reinterpret_cast<const float2*>(pbuf);
@@ -381,8 +388,9 @@ __global__ void __launch_bounds__(kThreads, 1) onset_frames_kernel(OnsetFramesPa
     const long long lo = (long long)blockIdx.x * p.items_per_cta;
     long long hi = lo + p.items_per_cta;
     hi = hi > n_items ? n_items : hi;
+    const bool small = n_items <= 0x7fffffffLL;
     for (long long item = lo + warp; item < hi; item += nwarps) {
-        const int clip = (int)(item / p.T);
+        const int clip = small ? (int)((unsigned)item / (unsigned)p.T) : (int)(item / p.T);
         const int t = (int)(item - (long long)clip * p.T);
         const long long s0 = (long long)t * p.hop - kStft2N / 2;
         const float* src = p.audio + (long long)clip * p.n;
@@ -418,9 +426,18 @@ __global__ void __launch_bounds__(kThreads, 1) onset_frames_kernel(OnsetFramesPa
         } else {
             // padded (zeros outside the signal) or misaligned: stage the gated samples as floats through the warp's scratch
 #pragma unroll 1
-            for (int e = lane; e < kStft2N; e += 32) {
-                const long long s = s0 + e;
-                stage[e] = (s >= 0 && s < p.n) ? gate(src[s], (int)s) : 0.0f;
+            for (int e0 = lane; e0 < kStft2N; e0 += 32 * 8) {        // eight loads in flight per lane
+                float val[8];
+#pragma unroll
+                for (int u8 = 0; u8 < 8; ++u8) {
+                    const long long s = s0 + e0 + 32 * u8;
+                    val[u8] = (s >= 0 && s < p.n) ? src[s] : 0.0f;
+                }
+#pragma unroll
+                for (int u8 = 0; u8 < 8; ++u8) {
+                    const long long s = s0 + e0 + 32 * u8;
+                    stage[e0 + 32 * u8] = (s >= 0 && s < p.n) ? gate(val[u8], (int)s) : 0.0f;
+                }
             }
             __syncwarp();
             const float2* g = reinterpret_cast<const float2*>(stage);

@@ -65,8 +65,11 @@ __device__ __forceinline__ void yin_finish_frame(const float (&dl)[kLPT], int b,
     for (int i = 0; i < kLPT; ++i) {
         const int tau = b + i;
         if (tau >= p.min_period && tau <= p.max_period) {
-            const double cm = (double)(offs + cl[i]) / (double)tau;
-            yv[tau - p.min_period] = (double)dl[i] / (cm + tiny);
+            // d / (cumsum / tau + tiny) with ONE float64 division: d * tau / (cumsum + tiny * tau).  d * tau is exact in
+            // float64 (24 + 10 bits); the quotient differs from numpy's two-division form by at most an ulp of float64,
+            // nine orders below the float32 noise of d itself.  (The two divisions were ~17 % of the kernel.)
+            const double dt = (double)tau;
+            yv[tau - p.min_period] = ((double)dl[i] * dt) / ((double)(offs + cl[i]) + tiny * dt);
         }
     }
     __syncwarp();
