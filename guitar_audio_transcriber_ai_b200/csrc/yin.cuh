@@ -322,7 +322,9 @@ __global__ void __launch_bounds__(384, 1) yin_pair_kernel(YinParams p) {
             float2 ring[kLPT], acc[kLPT];
 #pragma unroll
             for (int q = 0; q < kLPT; ++q) { ring[q] = make_float2(xs[1 + b + 2 * q], xs[2 + b + 2 * q]); acc[q] = make_float2(0.0f, 0.0f); }
-            float2 e2 = make_float2(0.0f, 0.0f);
+            // four independent energy accumulators: one would be a serial FFMA2 chain (the compiler groups the fifteen
+            // updates of a round back to back: ncu's top stall was the fixed-latency wait on it)
+            float2 e2[4] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
             constexpr int kSteps = kYinBlock / 2;                   // 256 sample pairs
             constexpr int kFull = kSteps / kLPT;
             for (int it = 0; it < kFull; ++it) {
@@ -333,7 +335,7 @@ __global__ void __launch_bounds__(384, 1) yin_pair_kernel(YinParams p) {
                     const float2 xp = *reinterpret_cast<const float2*>(xs + j);          // broadcast load
 #pragma unroll
                     for (int i = 0; i < kLPT; ++i) acc[i] = __ffma2_rn(xp, ring[(s + i) % kLPT], acc[i]);
-                    e2 = __ffma2_rn(ring[s], ring[s], e2);
+                    e2[s & 3] = __ffma2_rn(ring[s], ring[s], e2[s & 3]);
                     ring[s] = make_float2(xs[j + b + 2 * kLPT], xs[j + b + 2 * kLPT + 1]);
                 }
             }
@@ -343,13 +345,13 @@ __global__ void __launch_bounds__(384, 1) yin_pair_kernel(YinParams p) {
                 const float2 xp = *reinterpret_cast<const float2*>(xs + j);
 #pragma unroll
                 for (int i = 0; i < kLPT; ++i) acc[i] = __ffma2_rn(xp, ring[(s + i) % kLPT], acc[i]);
-                e2 = __ffma2_rn(ring[s], ring[s], e2);
+                e2[s & 3] = __ffma2_rn(ring[s], ring[s], e2[s & 3]);
                 ring[s] = make_float2(xs[j + b + 2 * kLPT], xs[j + b + 2 * kLPT + 1]);
             }
             float accs[kLPT];
 #pragma unroll
             for (int q = 0; q < kLPT; ++q) accs[q] = acc[q].x + acc[q].y;
-            const float e_blk = e2.x + e2.y;                        // sum_{j=1..512} xs[j + b]^2
+            const float e_blk = ((e2[0].x + e2[0].y) + (e2[1].x + e2[1].y)) + ((e2[2].x + e2[2].y) + (e2[3].x + e2[3].y));   // sum_{j=1..512} xs[j + b]^2
             if (blk > f0) {
                 // ---- frame t = blk - 1: acf = previous block + this block
                 const int t = blk - 1;
