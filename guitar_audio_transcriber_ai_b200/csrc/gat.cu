@@ -698,6 +698,7 @@ int run_yin(gat_ctx* c, const float* audio, int64_t N, int64_t n, bool normalize
     const int lags = p.max_period + 1;
     int rc;
     if (lags <= 7 * 32) rc = launch_yin_pair<7>(c, p, stream);
+    else if (lags <= 14 * 32) rc = launch_yin_pair<14>(c, p, stream);     // sr 22050: 442 lags -> 448 computed (15 per lane would be 480)
     else if (lags <= 15 * 32) rc = launch_yin_pair<15>(c, p, stream);
     else rc = launch_yin<33>(c, p, stream);
     if (rc) return 1;
@@ -721,6 +722,7 @@ extern "C" int gat_mfcc_features(gat_ctx* c, const float* audio, int64_t N, int6
     const int F = c->cfg.mfcc_n_mfcc + (add_pitch ? 1 : 0);
     if (ld < F) return fail("gat_mfcc_features: ld=%d < %d feature columns", ld, F);
     if (n < 1) return fail("gat_mfcc_features: empty clips");
+    if (apply_scaler && c->scaler_n != F) return fail("gat_mfcc_features: scaler has %d columns, features have %d", c->scaler_n, F);
     if (run_mfcc(c, audio, N, n, normalize != 0, false, out, ld, stream)) return 1;
     if (add_pitch) {
         const bool yn = normalize && yin_on_normalized;
@@ -1024,7 +1026,7 @@ int onset_chain(gat_ctx* c, const float* y, int64_t P, int64_t L, const gat_slic
     PeakParams pp{c->seg_env.as<double>(), sc.env_minmax, To, sp->pre_max, sp->post_max, sp->pre_avg, sp->post_avg, sp->wait,
                   (double)sp->delta, c->seg_envn.as<double>(), c->seg_cand.as<unsigned>(), sc.n_peaks, c->seg_peaks.as<int>(), sc.any_nonzero, words};
     LAUNCH(c, peak_candidates_kernel, frames_grid, 128, 0, st, pp);
-    LAUNCH(c, peak_select_kernel, (unsigned)P, 32, 0, st, pp);
+    LAUNCH(c, peak_select_kernel, (unsigned)P, kPeakThreads, 0, st, pp);
     if (env_out) GAT_CUDA(cudaMemcpyAsync(env_out, c->seg_envn.p, PT * 8, cudaMemcpyDeviceToDevice, st));
 
     // backtrack, min separation, slice table
