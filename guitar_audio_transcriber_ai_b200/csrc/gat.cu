@@ -661,7 +661,7 @@ int launch_yin(gat_ctx* c, const YinParams& p, void* stream) {
 // packed-FMA variant (yin_pair_kernel): lags interleaved by parity across the two half-warps
 template <int kLPT>
 int launch_yin_pair(gat_ctx* c, const YinParams& p, void* stream) {
-    const int threads = 384;
+    const int threads = 512;
     const size_t per_warp = (yin_pair_smem_per_warp<kLPT>() + 15) / 16 * 16;
     const size_t smem = (size_t)(threads / 32) * per_warp + 64;
     auto kfn = yin_pair_kernel<kLPT>;
@@ -691,7 +691,7 @@ int run_yin(gat_ctx* c, const float* audio, int64_t N, int64_t n, bool normalize
     p.trough_threshold = c->cfg.yin_trough_threshold; p.f0 = f0;
     // A warp walks `seg_frames` frames of a clip with seg_frames + 1 blocks of work (12/11 blocks per frame at 11).  With
     // few clips (a single note) shorter segments trade redundant blocks for parallelism: latency, not throughput.
-    const long long warps = (long long)c->num_sms * 12;
+    const long long warps = (long long)c->num_sms * 16;
     int seg = 11;
     while (seg > 1 && (long long)N * ((T + seg - 1) / seg) < warps) seg = (seg + 1) / 2;
     p.seg_frames = T < seg ? T : seg;

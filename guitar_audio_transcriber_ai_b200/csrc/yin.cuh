@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(384, 1) yin_kernel(YinParams p) {
 // the summation order differs from the scalar kernel's (and from librosa's FFT autocorrelation) at float32 rounding level.
 // After a frame's two blocks the d values go through shared memory once so that the cumulative sum runs with the
 // consecutive-lag lane mapping of yin_finish_frame.
-constexpr int kYinPairBuf = 3072;
+constexpr int kYinPairBuf = 2048;      // two blocks per refill; 13.6 KB of shared memory per warp -> 16 warps per SM
 
 template <int kLPT>
 __host__ __device__ inline size_t yin_pair_smem_per_warp() {
@@ -251,7 +251,7 @@ __host__ __device__ inline size_t yin_pair_smem_per_warp() {
 }
 
 template <int kLPT>
-__global__ void __launch_bounds__(384, 1) yin_pair_kernel(YinParams p) {
+__global__ void __launch_bounds__(512, 1) yin_pair_kernel(YinParams p) {
     GAT_DYN_SMEM(smem_raw);
     const int nwarps = blockDim.x >> 5;
     const int lane = lane_id(), warp = warp_id();
