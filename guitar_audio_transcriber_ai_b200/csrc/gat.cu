@@ -674,6 +674,37 @@ int launch_yin_pair(gat_ctx* c, const YinParams& p, void* stream) {
     return 0;
 }
 
+// block-FFT variant (yin_fft_kernel): one forward transform per 512-sample block, one inverse per frame pair
+template <int kLPT>
+int launch_yin_fft(gat_ctx* c, YinParams p, int64_t N, void* stream) {
+    constexpr int nwarps = yin_fft_warps<kLPT>();
+    const size_t smem = yin_fft_smem_bytes<kLPT>();
+    auto kfn = yin_fft_kernel<kLPT>;
+    GAT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // Segment length: a segment of s frames costs (s + 1) forward and ceil(s / 2) inverse transforms; warps take segments
+    // round-robin.  Minimise the transforms of the busiest warp (long segments amortise the extra block, short ones balance).
+    // Only EVEN lengths (or the whole clip): frames are then always paired as (2m, 2m + 1) whatever the batch size, so a
+    // clip's result does not depend on the batch it is in (the host entry point's chunks must equal the resident call).
+    const long long warps = (long long)c->num_sms * nwarps;
+    int best = p.T; long long best_cost = -1;
+    for (int s = 2; s <= p.T + 1; s += 2) {
+        const int len = s < p.T ? s : p.T;
+        const int n_seg = (p.T + len - 1) / len;
+        const long long per_warp = ((long long)N * n_seg + warps - 1) / warps;
+        const long long cost = per_warp * ((len + 1) + (len + 1) / 2);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = len; }
+    }
+    if (const char* e = getenv("GAT_YIN_SEG")) { const int s = atoi(e); if (s >= 2) best = s < p.T ? (s & ~1) : p.T; }    // test hook: force a segment length
+    p.seg_frames = best;
+    p.tw = c->tw32.as<Cpx<float>>();
+    const long long work = (long long)N * ((p.T + p.seg_frames - 1) / p.seg_frames);
+    const long long ctas = (work + nwarps - 1) / nwarps;
+    const unsigned grid = (unsigned)(ctas < c->num_sms ? ctas : c->num_sms);
+    KNAME("yin_kernel");
+    LAUNCH(c, kfn, grid, 32 * nwarps, smem, stream, p);
+    return 0;
+}
+
 int run_yin(gat_ctx* c, const float* audio, int64_t N, int64_t n, bool normalize, bool scale_ready, double* hz, double* f0_frames,
             float* feat, int ld, int col, void* stream) {
     const int T = (int)(1 + n / 512);
@@ -697,7 +728,11 @@ int run_yin(gat_ctx* c, const float* audio, int64_t N, int64_t n, bool normalize
     p.seg_frames = T < seg ? T : seg;
     const int lags = p.max_period + 1;
     int rc;
-    if (lags <= 7 * 32) rc = launch_yin_pair<7>(c, p, stream);
+    static const bool direct_form = getenv("GAT_YIN_DIRECT") != nullptr;      // A/B switch for the profiling tools
+    if (!direct_form && lags <= 7 * 32 && n < 0x7fff0000LL) rc = launch_yin_fft<7>(c, p, N, stream);
+    else if (!direct_form && lags <= 14 * 32 && n < 0x7fff0000LL) rc = launch_yin_fft<14>(c, p, N, stream);
+    else if (!direct_form && lags <= 16 * 32 && n < 0x7fff0000LL) rc = launch_yin_fft<16>(c, p, N, stream);
+    else if (lags <= 7 * 32) rc = launch_yin_pair<7>(c, p, stream);
     else if (lags <= 14 * 32) rc = launch_yin_pair<14>(c, p, stream);     // sr 22050: 442 lags -> 448 computed (15 per lane would be 480)
     else if (lags <= 15 * 32) rc = launch_yin_pair<15>(c, p, stream);
     else rc = launch_yin<33>(c, p, stream);

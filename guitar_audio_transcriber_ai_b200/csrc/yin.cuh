@@ -12,6 +12,7 @@
 // f0 = sr / period in float64.
 #pragma once
 #include "common.cuh"
+#include "fft.cuh"
 
 namespace gat {
 
@@ -27,6 +28,7 @@ struct YinParams {
     double trough_threshold;  // 0.1
     int seg_frames;           // frames per work item
     double* f0;               // [N][T]
+    const Cpx<float>* tw;     // yin_fft_kernel: W_1024^(n1*k2) table of the warp FFT (fft.cuh), else unused
 };
 
 constexpr int kYinFrame = 2048;
@@ -385,6 +387,352 @@ __global__ void __launch_bounds__(512, 1) yin_pair_kernel(YinParams p) {
             for (int q = 0; q < kLPT; ++q) prev_acc[q] = accs[q];
             prev_e = e_blk;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The difference function through FFTs, as librosa forms it - but per 512-sample BLOCK instead of per frame.
+//
+// With hop = W/2 a frame's autocorrelation is the sum of two block partials, acf_t = P_t + P_{t+1},
+//     P_b[tau] = sum_{j=1..512} xs[j] xs[j+tau],  xs[j] = padded[512 b + j],
+// and P_b is a linear correlation of u = xs[1..512] with v = xs[1..1024]: for tau <= 512 nothing wraps in a cyclic
+// correlation of length 1024.  Both are real, so ONE complex 1024-point FFT of z = v + i u_padded carries the two
+// spectra (Z = V + iU), and with A = Z[k], Z' = Z[1024-k]
+//     C_b[k] = conj(U[k]) V[k] = ( (A.x Z'.y + A.y Z'.x) / 2,  (|A|^2 - |Z'|^2) / 4 ).
+// C_b is Hermitian (its inverse transform is real), so TWO frames share one inverse transform:
+//     G = (C_t + C_{t+1}) + i (C_{t+1} + C_{t+2}),   IFFT(G) = acf_t + i acf_{t+1},   IFFT(G) = conj(FFT(conj G)) / 1024.
+// A warp walks a segment of frames of one clip: one forward transform per block, one inverse per frame pair: ~1.6 FFTs
+// of 51 kFLOP per frame where the direct form (yin_pair_kernel) spends 500 kFLOP.  The transform is the warp FFT of
+// the STFT kernels (32 complex registers per lane, one transpose through shared memory); its output layout - bin
+// 32 k1 + lane in register bitrev5(k1) - is the input layout of the next transform up to a register renaming, the
+// partner bin Z[1024-k] sits in lane (32 - lane) % 32 (one shuffle), and the running G lives in a lane-private 8 KB
+// strip of shared memory.  The energy terms slide along the lags as before (block sums of squares from the transform's
+// own inputs, a warp scan over the per-lane increments).  float32 throughout, like numpy's rfft on float32 frames;
+// the summation order differs from both numpy's and the direct kernels' at float32 rounding level.
+// Valid while max_period <= 512 (sample rates up to 25.6 kHz at fmin = 50 Hz); run_yin falls back to the direct form.
+// 12 warps: three per scheduler, 168 registers each.  (Shared memory would hold a 13th, but four warps on one scheduler
+// cap every thread at 128 registers and the block prefetch below then spills.)
+template <int kLPT>
+__host__ __device__ constexpr int yin_fft_warps() { return 12; }
+template <int kLPT>
+__host__ __device__ constexpr size_t yin_fft_scratch_bytes() {        // per warp: transpose buffer, reused by the frame finish
+    return (size_t)kXbufStride * 32 * sizeof(Cpx<float>) > (size_t)512 * kLPT ? (size_t)kXbufStride * 32 * sizeof(Cpx<float>) : (size_t)512 * kLPT;
+}
+template <int kLPT>
+__host__ __device__ constexpr size_t yin_fft_smem_bytes() {
+    return 1024 * sizeof(Cpx<float>) + (size_t)yin_fft_warps<kLPT>() * (yin_fft_scratch_bytes<kLPT>() + 1024 * sizeof(Cpx<float>)) + 64;
+}
+
+// Forward complex FFT of 1024 points held as v[r] = z[lane + 32 r]; on return v[bitrev5(k1)] = Z[32 k1 + lane].
+// (The first half of frame_fft_power in stft2.cuh: two in-lane 32-point transforms around a twiddled transpose.)
+__device__ __forceinline__ void warp_cfft1024(Cpx<float> (&v)[32], Cpx<float>* xbuf, const Cpx<float>* tw) {
+    const int lane = lane_id();
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        fft_dif<float, 32, 0, 32>(v);
+        if (pass == 0) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const int k2 = bitrev5(r);
+                const Cpx<float> w = tw[k2 * 32 + lane];
+                xbuf[k2 * kXbufStride + lane] = (k2 == 0) ? v[r] : cmul(v[r], w);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) v[n1] = xbuf[lane * kXbufStride + n1];
+            __syncwarp();
+        }
+    }
+}
+
+// Tail of one frame for the FFT kernel: the arithmetic of yin_finish_frame (same operations in the same order, so the two
+// give identical results on identical d), but the float64 divisions run in a ROLLED loop over shared memory - fourteen
+// inlined divisions were a tenth of the kernel's code, and its warps, each somewhere else in an 80 KB loop, stalled on
+// instruction fetch (ncu: "no instruction" 2.0 per issue).
+template <int kLPT>
+__device__ __forceinline__ void yin_finish_frame_rolled(const float (&dl)[kLPT], int b, const YinParams& p, double* yv, int nl, int clip, int t) {
+    const int lane = lane_id();
+    const double tiny = 1.1754943508222875e-38;                    // np.finfo(float32).tiny
+    float run = 0.0f, cl[kLPT];
+#pragma unroll
+    for (int i = 0; i < kLPT; ++i) {
+        const int tau = b + i;
+        if (tau >= 1 && tau <= p.max_period) run += dl[i];
+        cl[i] = run;
+    }
+    float offs = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float u = __shfl_up_sync(0xffffffffu, offs, o);
+        if (lane >= o) offs += u;
+    }
+    offs -= run;                                        // exclusive prefix of lane totals
+    float2* dc = reinterpret_cast<float2*>(yv);         // (d, cumulative sum) in the slot its quotient will take
+#pragma unroll
+    for (int i = 0; i < kLPT; ++i) {
+        const int tau = b + i;
+        if (tau >= p.min_period && tau <= p.max_period) dc[tau - p.min_period] = make_float2(dl[i], offs + cl[i]);
+    }
+    __syncwarp();
+    // Quotients and trough tests 32 lags at a time, in increasing lag order, and NO FURTHER than the first trough under the
+    // threshold: the result is that trough (librosa takes the first), so the lags behind it are never needed - for a pitched
+    // frame that is most of them.  Chunk j is tested once chunk j + 1 has its quotients (a lag's test reads its right
+    // neighbour).  The global minimum is only used when no chunk had such a trough, i.e. when all were visited.
+    int first = 0x7fffffff;
+    double best = 1e300; int best_i = 0x7fffffff;
+    const int nch = (nl + 31) >> 5;
+#pragma unroll 1
+    for (int j = 0; j <= nch; ++j) {
+        const int i = lane + 32 * j;
+        if (i < nl) {                                   // every lane rewrites only the slot it reads
+            const float2 q = dc[i];
+            const double dt = (double)(i + p.min_period);
+            yv[i] = ((double)q.x * dt) / ((double)q.y + tiny * dt);     // d / (cumsum / tau + tiny) with one division, as above
+        }
+        __syncwarp();
+        const int it = i - 32;
+        if (j >= 1 && it < nl) {
+            const double y0 = yv[it];
+            bool trough;
+            if (it == 0) trough = nl > 1 && y0 < yv[1];
+            else if (it == nl - 1) trough = y0 < yv[it - 1];
+            else trough = (y0 < yv[it - 1]) && (y0 <= yv[it + 1]);
+            if (trough && y0 < p.trough_threshold && it < first) first = it;
+            if (y0 < best) { best = y0; best_i = it; }
+        }
+        if (__any_sync(0xffffffffu, first != 0x7fffffff)) break;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int f2 = __shfl_xor_sync(0xffffffffu, first, o);
+        first = f2 < first ? f2 : first;
+        const double b2 = __shfl_xor_sync(0xffffffffu, best, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (b2 < best || (b2 == best && i2 < best_i)) { best = b2; best_i = i2; }
+    }
+    if (lane == 0) {
+        const int idx = first != 0x7fffffff ? first : (best_i != 0x7fffffff ? best_i : 0);
+        double shift = 0.0;
+        if (idx > 0 && idx < nl - 1) {
+            const double ym = yv[idx - 1], y0 = yv[idx], yp = yv[idx + 1];
+            const double aa = yp + ym - 2.0 * y0;
+            const double bb = (yp - ym) / 2.0;
+            if (!(fabs(bb) >= fabs(aa))) shift = -bb / aa;
+        }
+        p.f0[(long long)clip * p.T + t] = (double)p.sr / ((double)(p.min_period + idx) + shift);
+    }
+    __syncwarp();
+}
+
+template <int kLPT>
+__global__ void __launch_bounds__(32 * yin_fft_warps<kLPT>(), 1) yin_fft_kernel(YinParams p) {
+    GAT_DYN_SMEM(smem_raw);
+    const int nwarps = blockDim.x >> 5;
+    const int lane = lane_id(), warp = warp_id();
+    Cpx<float>* tw = reinterpret_cast<Cpx<float>*>(smem_raw);
+    unsigned char* mine = smem_raw + 1024 * sizeof(Cpx<float>) + (size_t)warp * (yin_fft_scratch_bytes<kLPT>() + 1024 * sizeof(Cpx<float>));
+    Cpx<float>* xbuf = reinterpret_cast<Cpx<float>*>(mine);                 // transpose buffer / stash of the next inverse's input
+    Cpx<float>* gs = reinterpret_cast<Cpx<float>*>(mine + yin_fft_scratch_bytes<kLPT>());   // running G, slot k1*32 + lane = bin 32 k1 + lane
+    // the frame finish reuses the transpose buffer between transforms
+    double* yv = reinterpret_cast<double*>(mine);                           // CMND, index tau - min_period
+    float* dsm = reinterpret_cast<float*>(mine);                            // energy increments: consumed before yv is written
+    float* acf_a = reinterpret_cast<float*>(yv + 32 * kLPT);                // autocorrelations of the pair's two frames
+    float* acf_b = acf_a + 32 * kLPT;
+    float* stage = reinterpret_cast<float*>(mine);                          // 1024 samples of a block that touches the padding
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) tw[i] = p.tw[i];
+    __syncthreads();           // the only block barrier
+
+    const int nl = p.max_period - p.min_period + 1;
+    const int partner = (32 - lane) & 31;
+    const int n32 = (int)p.n;                                               // run_yin: n < 2^31 - 2^16
+    const int n_seg = (p.T + p.seg_frames - 1) / p.seg_frames;
+    const long long n_work = (long long)p.N * n_seg;
+    for (long long work = (long long)blockIdx.x * nwarps + warp; work < n_work; work += (long long)gridDim.x * nwarps) {
+        const int clip = (int)(work / n_seg);
+        const int f0 = (int)(work % n_seg) * p.seg_frames;
+        const int nf = min(p.seg_frames, p.T - f0);
+        const float* src = p.audio + (long long)clip * p.n;
+        // normalised path: multiply by 1/c (the direct kernels divide every sample: an ulp of difference per sample)
+        const float ic = p.clip_scale ? 1.0f / p.clip_scale[clip] : 1.0f;
+        auto padded = [&](int i) {                                  // centre-padded (zeros), UNSCALED signal
+            const int s = i - kYinFrame / 2;
+            return ((unsigned)s < (unsigned)n32) ? src[s] : 0.0f;
+        };
+        // Samples of a block are fetched one step ahead (the loads of block idx + 1 fly during block idx's spectrum
+        // product and, for every second block, the inverse transform): ncu's top stall was the wait for these loads.
+        float nx[32];
+        bool pre = false;                                           // nx holds the next block (it touches no padding)
+        auto prefetch = [&](int blk) {
+            const int s0 = kYinBlock * blk + 1 - kYinFrame / 2;     // source index of xs[1]
+            pre = s0 >= 0 && s0 + 1024 <= n32;
+            if (pre) {
+                const float* g = src + s0 + lane;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) nx[r] = g[32 * r];
+            }
+        };
+        prefetch(f0);
+#pragma unroll
+        for (int k1 = 0; k1 < 32; ++k1) gs[k1 * 32 + lane] = Cpx<float>{0.0f, 0.0f};
+        float tb0 = 0.0f, tb1 = 0.0f, tb2 = 0.0f;                   // sum_{j=1..512} xs[j]^2 of this block and the two before
+        float e0_a = 0.0f, e0_b = 0.0f;                             // E[0] of the frames of the pending inverse
+        int idx = 0, inv_frames = 0;
+        bool inv = false;
+        Cpx<float> v[32];
+#pragma unroll 1
+        while (true) {
+            if (!inv) {
+                // ---- block f0 + idx: z[j] = xs[1 + j] * (1 + i [j < 512])
+                if (!pre) {                                         // rolled: stage the padded block through shared memory
+                    const int base = kYinBlock * (f0 + idx) + 1;
+#pragma unroll 1
+                    for (int e0 = lane; e0 < 1024; e0 += 32 * 8) {
+                        float val[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) val[u] = padded(base + e0 + 32 * u);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) stage[e0 + 32 * u] = val[u];
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) nx[r] = stage[lane + 32 * r];
+                    __syncwarp();
+                }
+                float es = 0.0f;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    const float x = nx[r] * ic;
+                    v[r] = Cpx<float>{x, r < 16 ? x : 0.0f};
+                    if (r < 16) es = fmaf(x, x, es);
+                }
+                tb2 = tb1; tb1 = tb0;
+                tb0 = warp_sum(es);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 32; ++r) v[r] = xbuf[r * 32 + lane];
+                __syncwarp();                                       // the stash is consumed before the transpose overwrites it
+            }
+            warp_cfft1024(v, xbuf, tw);
+            if (!inv) {
+                // ---- C_b from Z, folded into the running G.  Position of block idx in its frame pair:
+                //   first block of the segment (gs = 0)   gs += C
+                //   odd idx, more blocks follow           gs += (1 + i) C
+                //   odd idx, last block (nf odd)          stash = gs + C            -> inverse, one frame  (idx - 1)
+                //   even idx >= 2                         stash = gs + i C, gs = C  -> inverse, two frames (idx - 2, idx - 1)
+                const bool first = idx == 0, odd = (idx & 1) != 0, last = idx == nf;
+                const bool to_gs = first || (odd && !last);
+                const bool end = !odd && !first;
+                // out = t + m C with m = 1, 1 + i, 1, i, conjugated for the stash (it holds conj(G): input n = lane + 32 k1
+                // of the inverse).  With C = (kH P, kQ Q) the multiplier, the conjugation and the inverse transform's 1/1024
+                // (kH, kQ: exact powers of two) fold into four warp-uniform scalars: out = (tx + a1 P - a2 Q, sg ty + b1 Q + b2 P).
+                constexpr float kH = 0.5f / 1024.0f, kQ = 0.25f / 1024.0f;
+                const float mx = end ? 0.0f : 1.0f, my = (odd && last) || first ? 0.0f : 1.0f;
+                const float sg = to_gs ? 1.0f : -1.0f;
+                const float a1 = mx * kH, a2 = my * kQ, b1 = sg * mx * kQ, b2 = sg * my * kH;
+                Cpx<float>* const dst = (to_gs ? gs : xbuf) + lane;
+                Cpx<float>* const g = gs + lane;
+                Cpx<float>* const dst2 = end ? g : dst;             // second store: C for the next pair, else the first one again
+                                                                    // (a conditional store made the compiler clone the loop)
+                if (!last) prefetch(f0 + idx + 1);
+                // straight-line code (selects and one predicated store, no branches), eight bins at a time: loads and
+                // shuffles first, stores last
+#pragma unroll
+                for (int c8 = 0; c8 < 32; c8 += 8) {
+                    float zx[8], zy[8];
+                    Cpx<float> t[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int k1 = c8 + q;
+                        const Cpx<float> other = v[bitrev5(31 - k1)];
+                        const Cpx<float> self = v[bitrev5((32 - k1) & 31)];
+                        const float sx = __shfl_sync(0xffffffffu, other.x, partner);
+                        const float sy = __shfl_sync(0xffffffffu, other.y, partner);
+                        zx[q] = lane == 0 ? self.x : sx;
+                        zy[q] = lane == 0 ? self.y : sy;
+                        t[q] = g[k1 * 32];
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int k1 = c8 + q;
+                        const Cpx<float> a = v[bitrev5(k1)];
+                        const float P = a.x * zy[q] + a.y * zx[q];
+                        const float Q = (a.x * a.x + a.y * a.y) - (zx[q] * zx[q] + zy[q] * zy[q]);
+                        const float ox = fmaf(a1, P, fmaf(-a2, Q, t[q].x)), oy = fmaf(b1, Q, fmaf(b2, P, sg * t[q].y));
+                        dst[k1 * 32] = Cpx<float>{ox, oy};
+                        dst2[k1 * 32] = Cpx<float>{end ? P * kH : ox, end ? Q * kQ : oy};
+                    }
+                }
+                __syncwarp();
+                if (to_gs) {
+                    ++idx;
+                } else {
+                    inv = true;
+                    inv_frames = odd ? 1 : 2;
+                    if (odd) { e0_a = tb1 + tb0; } else { e0_a = tb2 + tb1; e0_b = tb1 + tb0; }
+                }
+            } else {
+                // ---- FFT(conj G) = conj(acf_a + i acf_b); lag 32 k1 + lane in register bitrev5(k1)
+#pragma unroll
+                for (int k1 = 0; k1 < kLPT; ++k1) {
+                    acf_a[32 * k1 + lane] = v[bitrev5(k1)].x;
+                    acf_b[32 * k1 + lane] = -v[bitrev5(k1)].y;
+                }
+                __syncwarp();
+#pragma unroll 1
+                for (int fi = 0; fi < inv_frames; ++fi) {
+                    const int t = f0 + idx - inv_frames + fi;
+                    const float* ac = fi ? acf_b : acf_a;
+                    const float e_first = fi ? e0_b : e0_a;                    // E[0] = sum_{j=1..1024} fx[j]^2, fx[j] = padded[512 t + j]
+                    // E[tau+1] - E[tau] = fx[tau+1025]^2 - fx[tau+1]^2: coalesced loads, then through shared memory to
+                    // the consecutive-lag mapping of the finish
+                    const int fb = kYinBlock * t + 1 + lane;                   // padded index of fx[1 + lane]
+                    const int s_lo = fb - lane - kYinFrame / 2;
+                    if (s_lo >= 0 && s_lo + kYinWin + 32 * kLPT <= n32) {
+                        const float* g = src + s_lo + lane;
+#pragma unroll
+                        for (int i = 0; i < kLPT; ++i) {
+                            const float xin = g[32 * i + kYinWin] * ic, xout = g[32 * i] * ic;
+                            dsm[32 * i + lane] = xin * xin - xout * xout;
+                        }
+                    } else {
+#pragma unroll 2
+                        for (int i = 0; i < kLPT; ++i) {
+                            const float xin = padded(fb + 32 * i + kYinWin) * ic, xout = padded(fb + 32 * i) * ic;
+                            dsm[32 * i + lane] = xin * xin - xout * xout;
+                        }
+                    }
+                    __syncwarp();
+                    const int b = kLPT * lane;
+                    float inc[kLPT], tot = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < kLPT; ++i) { inc[i] = dsm[b + i]; tot += inc[i]; }
+                    float offs = tot;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const float u = __shfl_up_sync(0xffffffffu, offs, o);
+                        if (lane >= o) offs += u;
+                    }
+                    float e_tau = e_first + (offs - tot);                      // E[b]
+                    const float e0 = fabsf(e_first) < 1e-6f ? 0.0f : e_first;  // librosa's 1e-6 dead zones
+                    float dl[kLPT];
+#pragma unroll
+                    for (int i = 0; i < kLPT; ++i) {
+                        float a = ac[b + i];
+                        if (fabsf(a) < 1e-6f) a = 0.0f;
+                        float e = e_tau;
+                        if (fabsf(e) < 1e-6f) e = 0.0f;
+                        dl[i] = __fsub_rn(__fadd_rn(e0, e), __fmul_rn(2.0f, a));
+                        e_tau += inc[i];
+                    }
+                    __syncwarp();                                              // dsm (aliasing yv) is consumed
+                    yin_finish_frame_rolled<kLPT>(dl, b, p, yv, nl, clip, t);
+                }
+                inv = false;
+                if (idx == nf) break;
+                ++idx;
+            }
+        }
+        __syncwarp();
     }
 }
 
