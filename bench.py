@@ -325,11 +325,12 @@ def work_table(n_clips: int, n: int, T: int, n_fft: int = 2048, full: bool = Fal
             # one FFT per image frame + 4 edge frames of the MFCC chain; the Slaney bank rides on every other image frame
             "stft_frames_dual": ("hbm", n_clips * (4 * n + 4 * 64 * T + 4 * 65), n_clips * ((T + 4) * stft_flops_per_frame(n_fft) + T512 * 4.0 * 1025)),
             "stft_frames_mfcc": ("hbm", n_clips * (4 * n + 4 * 65), n_clips * T512 * stft_flops_per_frame(2048)),
-            # EXECUTED work of the block-shared direct form: a frame is two 512-sample block partials and consecutive frames
-            # share one, so a warp walking 11 frames does 12 blocks; every block is 512 samples x 448 lags (14 per lane, the
-            # 442 needed rounded up to the lane tiling).  (The naive per-frame form of SURVEY 8(d), 2*1024*442 per frame, is
-            # twice that and is NOT what runs.)
-            "yin_kernel": ("hbm", n_clips * (4 * n + 8 * T512), n_clips * (T512 + -(-T512 // 11)) * 2.0 * 512 * 448),
+            # EXECUTED work of the block-FFT form (csrc/yin.cuh, yin_fft_kernel): per clip one forward complex 1024-point
+            # transform per 512-sample block (T512 frames + one extra block per segment of ~12 frames), one inverse per frame
+            # pair, 5 N log2 N = 51 200 FLOP each, plus the spectrum product (12 FLOP per bin and block).  (The direct form
+            # this replaced executed 2 * 512 * 448 FLOP per block, ten times as much; SURVEY 8(d)'s naive per-frame form twice that.)
+            "yin_kernel": ("hbm", n_clips * (4 * n + 8 * T512),
+                           n_clips * ((T512 + -(-T512 // 12) + -(-T512 // 2)) * 51200.0 + (T512 + -(-T512 // 12)) * 1024 * 12.0)),
             "yin_median_kernel": ("hbm", n_clips * (8 * T512 + 12), None),
             "mlp_ensemble_kernel": ("hbm", n_clips * (4 * 65 + 4 * 47 * 3 + 12), None),
         })
@@ -353,7 +354,7 @@ def kernel_rows(prof: dict, steps: int, work: dict, peaks: dict, fma_peak: float
         if flops and fma_peak and per_step_ms > 0:
             f = flops / (per_step_ms * 1e-3) / 1e12
             row["fp32"] = {"achieved": f, "peak": fma_peak, "unit": "TFLOP/s", "frac": f / fma_peak,
-                           "what": "executed algorithmic FP32 work (rFFT 2.5 N log2 N + 2 MAC per bin sparse mel; YIN: block-shared direct difference form, 512 x 448 FMAs per block) vs the FP32-FMA peak measured live"}
+                           "what": "executed algorithmic FP32 work (rFFT 2.5 N log2 N + 2 MAC per bin sparse mel; YIN: block-FFT difference form, 1.6 complex 1024-point FFTs per frame) vs the FP32-FMA peak measured live"}
         rows.append(row)
     return rows
 

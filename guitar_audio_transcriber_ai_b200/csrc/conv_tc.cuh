@@ -88,9 +88,15 @@ __global__ void __launch_bounds__(conv_tc_threads(conv_tc_epi_groups(COUT)), 1) 
     constexpr int EPI = conv_tc_epi_groups(COUT);          // epilogue groups (4 warps each), channel blocks interleaved between them
     constexpr int kAWarp = 2 + 4 * EPI;                    // the activation producer is the last warp
     constexpr int NKB = CIN / 32;
-    constexpr uint32_t W_STAGE = 6 * COUT * 16;            // wf | wb | wl, each 2 chunks x COUT x 16 B
-    constexpr int ACC = (2 * kTcTiles * COUT <= 512) ? 2 : 1;      // accumulator sets in TMEM (conv2: 2 x 192 columns)
-    constexpr uint32_t TMEM_COLS = ACC * kTcTiles * COUT <= 256 ? 256 : 512;
+    constexpr uint32_t W_STAGE = 6 * COUT * 16;            // wf | wb | wl, each 2 chunks x COUT x 16 B (FUSE: {wf, wl} | wb)
+    // conv2 (N = 64) is bound by the tensor core's operand fetch, not its math: an M128 N64 K16 MMA reads 4 KB of pixels and
+    // 2 KB of weights for 32 clocks of work.  hf*wf and hf*wl read the SAME pixel tile, so with the two weight parts stacked
+    // along N they are ONE N = 128 MMA into 128 accumulator columns per tile ([0, 64): hf*wf + lb*wb, [64, 128): hf*wl;
+    // the epilogue adds the halves): 14 KB of operand fetch per (tap, 16 channels) instead of 18 KB, two MMAs instead of three.
+    constexpr bool FUSE = COUT == 64;
+    constexpr int DCOLS = FUSE ? 2 * COUT : COUT;          // accumulator columns per 128-pixel tile
+    constexpr int ACC = (2 * kTcTiles * DCOLS <= 512) ? 2 : 1;     // accumulator sets in TMEM
+    constexpr uint32_t TMEM_COLS = ACC * kTcTiles * DCOLS <= 256 ? 256 : 512;
     extern __shared__ __align__(128) unsigned char smem[];
     const int Wp = p.W + 2, Hp = p.H + 2;
     const int seg = p.seg;
@@ -103,14 +109,17 @@ __global__ void __launch_bounds__(conv_tc_threads(conv_tc_epi_groups(COUT)), 1) 
     float* pooled = staging + (size_t)EPI * kTcStageFloats;   // only present (and used) when COUT == 128
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(staging) + (size_t)EPI * kTcStageFloats * 4
                                                  + (COUT == 128 ? (size_t)EPI * kTcPooledPix * kTcStageStride * 4 : 0));
+    // acc_empty is PER TILE (set * kTcTiles + tile): with a single accumulator set the next group's MMAs on a tile start as
+    // soon as the epilogue has that tile in registers, not when the whole group has been drained
     uint64_t* a_full = bars + 0; uint64_t* a_empty = bars + 2; uint64_t* acc_full = bars + 4; uint64_t* acc_empty = bars + 6;
-    uint64_t* w_full = bars + 8; uint64_t* w_empty = bars + 8 + NSTAGE;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * NSTAGE);
+    uint64_t* w_full = bars + 6 + 2 * kTcTiles; uint64_t* w_empty = w_full + NSTAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + NSTAGE);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4 * EPI); }
+        for (int s = 0; s < 2; ++s) mbar_init(acc_full + s, 1);
+        for (int s = 0; s < 2 * kTcTiles; ++s) mbar_init(acc_empty + s, 4 * EPI);
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1); }
         fence_barrier_init();
     }
@@ -182,11 +191,12 @@ __global__ void __launch_bounds__(conv_tc_threads(conv_tc_epi_groups(COUT)), 1) 
         // ===================================================== MMA issuer (the warp runs the loop, one elected lane issues)
         {
             const bool leader = elect_one();
-            const uint32_t idesc_h = idesc_f16(128, COUT), idesc_b = idesc_bf16(128, COUT);
+            const uint32_t idesc_h = idesc_f16(128, DCOLS), idesc_b = idesc_bf16(128, COUT);
             // Descriptors differ only in their start address: keep the low words as integers and add offsets.
             // low word = (addr >> 4) | (LBO >> 4) << 16 ; high word = (SBO >> 4) | version 1 at bit 46.
             constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
             const uint32_t a_lbo = (plane >> 4) << 16, b_lbo = ((uint32_t)(COUT * 16) >> 4) << 16;
+            const uint32_t b_lbo2 = ((uint32_t)(2 * COUT * 16) >> 4) << 16;      // FUSE: a K chunk of {wf, wl} is 2 * COUT rows
             const uint32_t a_hf = (smem_u32(a_buf) >> 4) | a_lbo;
             const uint32_t a_lb = a_hf + ((4 * plane) >> 4);
             const uint32_t a_step = (2 * plane) >> 4;                     // two 16-byte K chunks (16 channels) per MMA
@@ -195,11 +205,7 @@ __global__ void __launch_bounds__(conv_tc_threads(conv_tc_epi_groups(COUT)), 1) 
             long long t_acc = 0, t_a = 0, t_w = 0, t0 = 0, t_begin = clock64();
             for (int work = blockIdx.x; work < n_work; work += gridDim.x, ++wi) {
                 const uint32_t as = wi % ACC;
-                t0 = clock64();
-                mbar_wait(acc_empty + as, ((wi / ACC) & 1) ^ 1);
-                t_acc += clock64() - t0;
-                fence_after_thread_sync();
-                const uint32_t d_base = tmem + as * (uint32_t)(kTcTiles * COUT);
+                const uint32_t d_base = tmem + as * (uint32_t)(kTcTiles * DCOLS);
                 uint32_t accumulate = 0;
                 for (int kb = 0; kb < NKB; ++kb, ++it) {
                     for (int half = 0; half < 2; ++half) {
@@ -213,16 +219,25 @@ __global__ void __launch_bounds__(conv_tc_threads(conv_tc_epi_groups(COUT)), 1) 
                             t_w += clock64() - t0;
                             fence_after_thread_sync();
                             const uint32_t row_off = (uint32_t)((tap / 3) * seg + (tap % 3));         // in 16-byte units
-                            const uint32_t w_hf = ((smem_u32(w_buf) + st * W_STAGE) >> 4) | b_lbo;
-                            const uint32_t w_hb = w_hf + ((2 * COUT * 16) >> 4), w_lf = w_hf + ((4 * COUT * 16) >> 4);
+                            const uint32_t w_base = (smem_u32(w_buf) + st * W_STAGE) >> 4;
+                            const uint32_t w_hf = w_base | (FUSE ? b_lbo2 : b_lbo);                  // FUSE: {wf, wl}, N = 128
+                            const uint32_t w_hb = (w_base | b_lbo) + ((FUSE ? 4 : 2) * COUT * 16 >> 4);
+                            const uint32_t w_lf = w_hf + ((4 * COUT * 16) >> 4);                     // unused when FUSE
                             const uint32_t a_off = row_off + (uint32_t)half * a_step;
 #pragma unroll
                             for (int g = 0; g < kTcTiles; ++g) {
-                                const uint32_t d = d_base + (uint32_t)(g * COUT);
+                                const uint32_t d = d_base + (uint32_t)(g * DCOLS);
+                                if (accumulate == 0) {                  // first MMA of the group on this tile: its accumulators must be drained
+                                    t0 = clock64();
+                                    mbar_wait(acc_empty + as * kTcTiles + g, ((wi / ACC) & 1) ^ 1);
+                                    t_acc += clock64() - t0;
+                                    fence_after_thread_sync();
+                                }
                                 if (leader) {
-                                    mma_16bit(d, desc(a_hf + a_off + g * 128), desc(w_hf), idesc_h, accumulate);   // hf * wf   (FP16)
+                                    mma_16bit(d, desc(a_hf + a_off + g * 128), desc(w_hf), idesc_h, accumulate);   // hf * wf (FUSE: and hf * wl)  (FP16)
                                     mma_16bit(d, desc(a_lb + a_off + g * 128), desc(w_hb), idesc_b, 1u);           // lb * wb   (BF16)
-                                    mma_16bit(d, desc(a_hf + a_off + g * 128), desc(w_lf), idesc_h, 1u);           // hf * wl   (FP16)
+                                    if constexpr (!FUSE)
+                                        mma_16bit(d, desc(a_hf + a_off + g * 128), desc(w_lf), idesc_h, 1u);       // hf * wl   (FP16)
                                 }
                             }
                             accumulate = 1;
@@ -261,7 +276,7 @@ __global__ void __launch_bounds__(conv_tc_threads(conv_tc_epi_groups(COUT)), 1) 
             int pcol = Wpool - colb * (p.cw / 2);             // pooled columns produced by this group
             pcol = pcol < p.cw / 2 ? pcol : p.cw / 2;
             const uint32_t as = wi % ACC;
-            const uint32_t t_acc = tmem + as * (uint32_t)(kTcTiles * COUT);
+            const uint32_t t_acc = tmem + as * (uint32_t)(kTcTiles * DCOLS);
             const long long e0 = clock64();
             mbar_wait(acc_full + as, (wi / ACC) & 1);
             e_wait += clock64() - e0;
@@ -270,19 +285,29 @@ __global__ void __launch_bounds__(conv_tc_threads(conv_tc_epi_groups(COUT)), 1) 
 #pragma unroll
                 for (int g = 0; g < kTcTiles; ++g) {
                     float v[32];
-                    tmem_ld32(t_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * COUT + cb * 32), v);
+                    if constexpr (FUSE) {                                 // the two halves of the split product, one wait
+                        uint32_t r0[32], r1[32];
+                        const uint32_t ta = t_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * DCOLS + cb * 32);
+                        tmem_ld32_issue(ta, r0);
+                        tmem_ld32_issue(ta + COUT, r1);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+                    } else {
+                        tmem_ld32(t_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * COUT + cb * 32), v);
+                    }
                     const int pixel = g * 128 + quarter * 32 + lane;      // this thread's accumulator row
                     const int prow_ = pixel / seg;
                     float* dst = stage_g + prow_ * RS + (pixel - prow_ * seg) + 1;
+                    if (cb + EPI > kLastCb) {               // this group's last block of tile g is in registers: (with the others) the
+                        fence_before_thread_sync();         // next group's MMAs on this tile may start
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(acc_empty + as * kTcTiles + g);
+                    }
                     if (prow_ < p.R) {                                    // tile slots past the group's R rows hold nothing
 #pragma unroll
                         for (int j = 0; j < 32; ++j) dst[j * kTcStagePlane] = v[j];
                     }
-                }
-                if (cb + EPI > kLastCb) {                   // this group's last block is out of TMEM: (with the others) the next MMAs may start
-                    fence_before_thread_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty + as);
                 }
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
                 const int n_items = prow * pcol * 4;            // one item = one pooled pixel x 8 channels

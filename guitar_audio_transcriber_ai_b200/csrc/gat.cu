@@ -369,7 +369,12 @@ extern "C" int gat_ctx_create(const gat_config* cfg, int device, gat_ctx** out) 
     for (float& w : win_mfcc) w *= 0.5f;       // the Hermitian split's 1/2, exact
     rc |= upload(c->win_mfcc_half, win_mfcc.data(), 2048);
     rc |= upload(c->win64, cfg->stft_window, 2048);
-    rc |= upload(c->dct, cfg->dct, (size_t)cfg->mfcc_n_mfcc * cfg->mfcc_n_mels);
+    {   // DCT-II rows transposed to [mel band][coefficient]: the finish reads a band's coefficients with ONE coalesced load
+        std::vector<float> dct_t((size_t)cfg->mfcc_n_mfcc * cfg->mfcc_n_mels);
+        for (int k = 0; k < cfg->mfcc_n_mfcc; ++k)
+            for (int j = 0; j < cfg->mfcc_n_mels; ++j) dct_t[(size_t)j * cfg->mfcc_n_mfcc + k] = cfg->dct[(size_t)k * cfg->mfcc_n_mels + j];
+        rc |= upload(c->dct, dct_t.data(), dct_t.size());
+    }
     rc |= build_sparse_fb(c->fb_mel, cfg->mel_fb, cfg->mel_n_mels, cfg->mel_n_fft / 2 + 1, 1, cfg->mel_n_mels);
     rc |= build_sparse_fb(c->fb_mfcc, cfg->mfcc_fb, cfg->mfcc_n_mels, 1025, 1025, 1);
     if (rc) { gat_ctx_destroy(c); return 1; }
@@ -448,7 +453,12 @@ extern "C" int gat_load_cnn(gat_ctx* c, int32_t n_conv, const int32_t* ch, const
                     const int kh = ci / 16, c = ci % 16;                   // kh = K block * 2 + half
                     unsigned short* st = t.data() + (size_t)(kh * 9 + tap) * stage;
                     const size_t idx = ((size_t)(c / 8) * cout + oc) * 8 + (c % 8);
-                    tc::split16_weight_host(w, st[idx], st[(size_t)2 * cout * 8 + idx], st[(size_t)4 * cout * 8 + idx]);
+                    if (cout == 64) {      // conv2: {wf, wl} stacked along N per K chunk, then wb (conv_tc.cuh, FUSE)
+                        const size_t cmb = ((size_t)(c / 8) * 2 * cout + oc) * 8 + (c % 8);
+                        tc::split16_weight_host(w, st[cmb], st[(size_t)4 * cout * 8 + idx], st[cmb + (size_t)cout * 8]);
+                    } else {
+                        tc::split16_weight_host(w, st[idx], st[(size_t)2 * cout * 8 + idx], st[(size_t)4 * cout * 8 + idx]);
+                    }
                 }
         if (upload(c->conv_w_tc[i], t.data(), t.size())) return 1;
     }
@@ -825,7 +835,7 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
     const int H0 = c->cfg.mel_n_mels, W0 = T;
     const int H1 = H0 / 2, W1 = W0 / 2, H2 = H1 / 2, W2 = W1 / 2, H3 = H2 / 2, W3 = W2 / 2;
     if (H3 < 1 || W3 < 1) return fail("infer: mel image %dx%d too small for three 2x2 pools", H0, W0);
-    const ConvTiling t2 = conv_tc_tiling<64>(H1, W1, 6), t3 = conv_tc_tiling<128>(H2, W2, 3);
+    const ConvTiling t2 = conv_tc_tiling<64>(H1, W1, 8), t3 = conv_tc_tiling<128>(H2, W2, 3);
     if (t2.R < 2 || t3.R < 2 || t2.smem > 227 * 1024 || t3.smem > 227 * 1024)
         return fail("infer: no tensor-core conv tiling for a mel image of %d x %d", H0, W0);
     const size_t smem2 = t2.smem, smem3 = t3.smem;
@@ -857,7 +867,7 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
     float* feat_hi = c->feat_planes.as<float>();
     float* feat_lo = reinterpret_cast<float*>(c->feat_planes.as<unsigned char>() + feat_bytes);
     const bool fuse_avgpool = t3.groups_per_clip == 1 && H3 * W3 <= kTcPooledPix;
-    auto k2 = conv_tc_kernel<32, 64, 6>;
+    auto k2 = conv_tc_kernel<32, 64, 8>;
     auto k3 = conv_tc_kernel<64, 128, 3>;
     GAT_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     GAT_CUDA(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));

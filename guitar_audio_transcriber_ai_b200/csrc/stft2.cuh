@@ -41,7 +41,7 @@ struct StftFramesParams {
     SparseFb fb2; int norm_spec;
     float* spec_scratch;           // [N][T2][128] mel dB (L2-resident between the write and the finish)
     unsigned* clip_count;          // [N] arrival counters, zeroed by the launcher
-    const float* dct; int n_mfcc; float top_db; float* mfcc_out; int ld;
+    const float* dct /* [128][n_mfcc], transposed */; int n_mfcc; float top_db; float* mfcc_out; int ld;
     // ---- work items: per clip `fa` image frames then `fb_items` spec-only frames
     int fa, fb_items;
     long long items_per_cta;
@@ -101,7 +101,8 @@ __device__ __forceinline__ void mfcc_finish_warp(const StftFramesParams& p, int 
     const int lane = lane_id();
     const float4* rows = reinterpret_cast<const float4*>(p.spec_scratch + (long long)clip * p.T2 * 128);
     float mx = -3.0e38f;
-    for (int t = 0; t < p.T2; ++t) {
+#pragma unroll 4
+    for (int t = 0; t < p.T2; ++t) {                    // L2 latency-bound: four rows in flight
 #ifndef GAT_CPU_EMU
         const float4 v = __ldcg(rows + (long long)t * 32 + lane);
 #else
@@ -112,6 +113,7 @@ __device__ __forceinline__ void mfcc_finish_warp(const StftFramesParams& p, int 
     mx = warp_max(mx);
     const float floor_db = mx - p.top_db;
     float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll 4
     for (int t = 0; t < p.T2; ++t) {
 #ifndef GAT_CPU_EMU
         const float4 v = __ldcg(rows + (long long)t * 32 + lane);
@@ -125,11 +127,15 @@ __device__ __forceinline__ void mfcc_finish_warp(const StftFramesParams& p, int 
     __syncwarp();
     reinterpret_cast<float4*>(scratch_smem)[lane] = make_float4(s0 / inv, s1 / inv, s2 / inv, s3 / inv);
     __syncwarp();
+    // p.dct is TRANSPOSED, [band j][coefficient k]: lane k reads dct[j][k], one 128-byte line per band, eight bands in
+    // flight.  (With the row-major table every lane walked its own row: 32 cache lines per load instruction, and ncu had a
+    // fifth of an MFCC-only launch's warp time waiting in this loop.)  Per coefficient the sum still runs over the bands
+    // in increasing order.
     for (int k = lane; k < p.n_mfcc; k += 32) {
-        const float* d = p.dct + (long long)k * 128;
+        const float* d = p.dct + k;
         float acc = 0.0f;
-#pragma unroll 4
-        for (int j = 0; j < 128; ++j) acc += __ldg(d + j) * scratch_smem[j];
+#pragma unroll 8
+        for (int j = 0; j < 128; ++j) acc += __ldg(d + (long long)j * p.n_mfcc) * scratch_smem[j];
         p.mfcc_out[(long long)clip * p.ld + k] = acc;
     }
     __syncwarp();
