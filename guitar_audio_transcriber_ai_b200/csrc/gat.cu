@@ -656,7 +656,8 @@ int run_dual(gat_ctx* c, const float* audio, int64_t N, int64_t n, bool norm_mel
 
 template <int kLPT>
 int launch_yin(gat_ctx* c, const YinParams& p, void* stream) {
-    const int threads = 384;
+    int threads = 384;                        // as many warps (at most 12) as 227 KB of shared memory hold: 10 at 33 lags per lane
+    while (threads > 32 && (size_t)(threads / 32) * yin_smem_per_warp<kLPT>() + 64 > (size_t)227 * 1024) threads -= 32;
     const size_t smem = (size_t)(threads / 32) * yin_smem_per_warp<kLPT>() + 64;
     auto kfn = yin_kernel<kLPT>;
     GAT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -75,3 +75,20 @@ def test_emu_segment_batch_equals_per_signal(emu_tr, golden_phrases):
         assert np.array_equal(clips[row:row + m], one["clips"].numpy())
         row += m
     assert row == table.shape[0]
+
+
+@pytest.mark.parametrize("seg", ["2", "6", "44"])
+def test_emu_yin_block_fft_segmentations(emu_tr, seg, monkeypatch):
+    """yin_fft_kernel: every position of a block in its frame pair (first / odd / even / odd-and-last), at forced segment
+    lengths, frame by frame against the restated librosa.yin - and identical frames whatever the segment length."""
+    import librosa_shim as L
+    from guitar_audio_transcriber_ai_b200 import synth
+    clips, _ = synth.clip_batch(2, 1.0, 22050, seed0=77)
+    monkeypatch.setenv("GAT_YIN_SEG", seg)
+    _, f0 = emu_tr.engine.yin(clips)
+    monkeypatch.setenv("GAT_YIN_SEG", "12")
+    _, f12 = emu_tr.engine.yin(clips)
+    assert torch.equal(f0, f12)
+    for i in range(2):
+        ref = L.yin(clips[i], fmin=50, fmax=1000, sr=22050)
+        assert f0[i].shape == ref.shape and np.max(cents(f0[i].numpy(), ref)) <= 0.5

@@ -74,6 +74,41 @@ def test_yin_frames_and_notes(tr22, golden_clips_22050):
             assert info["midi"] == int(g[f"yin_midi_{k}"]) and info["note_name"] == str(g[f"yin_note_{k}"])
 
 
+@pytest.mark.parametrize("sr", [11025, 16000, 22050, 25000, 44100])
+def test_yin_block_fft_against_oracle_at_other_rates(sr):
+    """The block-FFT difference function (csrc/yin.cuh, yin_fft_kernel: 7 / 14 / 16 lags per lane) and, above 25.6 kHz,
+    the direct form it falls back to, frame by frame against the restated librosa.yin; odd frame counts, raw and
+    volume-normalised input, and a batch big enough that segments are longer than one frame pair."""
+    import librosa_shim as L
+    from guitar_audio_transcriber_ai_b200 import synth
+    from guitar_audio_transcriber_ai_b200.engine import Engine
+    eng = Engine(sr, device="cuda:0")
+    try:
+        for dur, n_clips in ((0.61, 6), (1.0, 700)):
+            clips, _ = synth.clip_batch(n_clips, dur, sr, seed0=400 + sr % 97)
+            for norm in (False, True):
+                hz, f0 = eng.yin(clips, normalize=norm)
+                hz, f0 = hz.cpu().numpy(), f0.cpu().numpy()
+                for i in range(0, n_clips, max(1, n_clips // 6)):
+                    y = clips[i]
+                    if norm:
+                        y = (y / (np.sqrt(np.mean(y ** 2)) + 1e-9)).astype(np.float32)
+                    ref = L.yin(y, fmin=50, fmax=1000, sr=sr)
+                    # frames 0 and 1 integrate over the zero padding (and a synthetic note starts at a zero crossing): their
+                    # difference function is an energy ramp without troughs, and which lag wins is decided by the float32
+                    # rounding noise of whoever computes it (tolerances.py) - they must be finite, the rest must agree
+                    assert f0[i].shape == ref.shape and np.all(np.isfinite(f0[i]))
+                    assert np.max(cents(f0[i][2:], ref[2:])) <= 0.5, (sr, dur, norm, i, np.max(cents(f0[i][2:], ref[2:])))
+                    assert cents(hz[i], np.median(ref)) <= YIN_CENTS
+        # a clip's frames do not depend on the batch it is in (segment lengths do): the first 6 of 700 alone
+        clips, _ = synth.clip_batch(700, 1.0, sr, seed0=400 + sr % 97)
+        _, f_all = eng.yin(clips)
+        _, f_few = eng.yin(clips[:6])
+        assert torch.equal(f_all[:6], f_few)
+    finally:
+        eng.close()
+
+
 @pytest.mark.parametrize("which", ["22050", "11025"])
 def test_predict_from_golden_features(which, tr22, tr11, golden_clips_22050, golden_clips_11025):
     """NotePredictor.predict on the reference's own features: isolates the CNN/MLP/ensemble kernels."""
