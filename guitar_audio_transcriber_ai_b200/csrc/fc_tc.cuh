@@ -163,29 +163,73 @@ struct Fc2Params {
 __global__ void __launch_bounds__(256) fc2_softmax_kernel(Fc2Params p) {
     GAT_DYN_SMEM(smem_raw);
     float* w = reinterpret_cast<float*>(smem_raw);                 // [hidden][classes]
-    float* hbuf = w + p.hidden * p.classes;                        // [warps][hidden] activated hidden vectors
-    for (int i = threadIdx.x; i < p.hidden * p.classes; i += blockDim.x) w[i] = p.w2[i];
+    float* hbuf = w + ((p.hidden * p.classes + 3) & ~3);           // [warps][hidden] activated hidden vectors (16-byte aligned)
+    // FC2's weights: 128-bit loads, four in flight per thread (one 4-byte load at a time, 47 dependent round trips to L2
+    // per CTA, was most of this kernel's 50 us)
+    {
+        const int n4 = (p.hidden * p.classes) >> 2;
+        const float4* src = reinterpret_cast<const float4*>(p.w2);
+        float4* dst = reinterpret_cast<float4*>(w);
+        for (int i0 = threadIdx.x; i0 < n4; i0 += 4 * blockDim.x) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int i = i0 + u * blockDim.x; v[u] = i < n4 ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int i = i0 + u * blockDim.x; if (i < n4) dst[i] = v[u]; }
+        }
+        for (int i = 4 * n4 + threadIdx.x; i < p.hidden * p.classes; i += blockDim.x) w[i] = p.w2[i];
+    }
     __syncthreads();
     const int lane = lane_id(), nwarps = blockDim.x >> 5;
     float* h = hbuf + warp_id() * p.hidden;
     for (int clip = blockIdx.x * nwarps + warp_id(); clip < p.N; clip += gridDim.x * nwarps) {
-        for (int k = lane; k < p.hidden; k += 32) {
-            float acc = 0.0f;
-            for (int s = 0; s < p.k_splits; ++s) acc += __ldg(p.hid + ((long long)s * p.N + clip) * p.hidden + k);
-            const float z = acc + __ldg(p.b1 + k);
-            h[k] = z > 0.0f ? z : z * p.slope;
+        // hidden unit k = lane + 32 j: the K slices of FC1 are added in slice order (a clip's value does not depend on the
+        // batch); the loads of four units (up to 32) are issued together
+        for (int k0 = lane; k0 < p.hidden; k0 += 128) {
+            float part[4][8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const int k = k0 + 32 * j;
+                    part[j][s] = (s < p.k_splits && k < p.hidden) ? __ldg(p.hid + ((long long)s * p.N + clip) * p.hidden + k) : 0.0f;
+                }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = k0 + 32 * j;
+                if (k < p.hidden) {
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) acc += part[j][s];
+                    for (int s = 8; s < p.k_splits; ++s) acc += __ldg(p.hid + ((long long)s * p.N + clip) * p.hidden + k);
+                    const float z = acc + __ldg(p.b1 + k);
+                    h[k] = z > 0.0f ? z : z * p.slope;
+                }
+            }
         }
         __syncwarp();
-        float a0 = 0.0f, a1 = 0.0f;
+        // logits: four interleaved partial sums per class (k mod 4), folded as (s0 + s1) + (s2 + s3): a fixed order, and a
+        // dependent chain of hidden / 4 FMAs instead of hidden
+        float a0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, a1[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         const bool has0 = lane < p.classes, has1 = lane + 32 < p.classes;
-        for (int k = 0; k < p.hidden; ++k) {
-            const float x = h[k];
-            if (has0) a0 = fmaf(x, w[k * p.classes + lane], a0);
-            if (has1) a1 = fmaf(x, w[k * p.classes + lane + 32], a1);
+        const int c0 = has0 ? lane : 0, c1 = has1 ? lane + 32 : 0;          // clamped: inactive lanes read a valid weight
+        int k = 0;
+        for (; k + 4 <= p.hidden; k += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(h + k);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float xu = u == 0 ? x.x : u == 1 ? x.y : u == 2 ? x.z : x.w;
+                a0[u] = fmaf(xu, w[(k + u) * p.classes + c0], a0[u]);
+                a1[u] = fmaf(xu, w[(k + u) * p.classes + c1], a1[u]);
+            }
+        }
+        for (; k < p.hidden; ++k) {
+            a0[k & 3] = fmaf(h[k], w[k * p.classes + c0], a0[k & 3]);
+            a1[k & 3] = fmaf(h[k], w[k * p.classes + c1], a1[k & 3]);
         }
         __syncwarp();
-        const float v0 = has0 ? a0 + p.b2[lane] : -3.0e38f;
-        const float v1 = has1 ? a1 + p.b2[lane + 32] : -3.0e38f;
+        const float v0 = has0 ? ((a0[0] + a0[1]) + (a0[2] + a0[3])) + p.b2[lane] : -3.0e38f;
+        const float v1 = has1 ? ((a1[0] + a1[1]) + (a1[2] + a1[3])) + p.b2[lane + 32] : -3.0e38f;
         const float mx = warp_max(fmaxf(v0, v1));
         const float e0 = has0 ? expf(v0 - mx) : 0.0f;
         const float e1 = has1 ? expf(v1 - mx) : 0.0f;

@@ -909,7 +909,7 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
     LAUNCH(c, kf, dim3((unsigned)row_blocks, (unsigned)k_splits), 192, fc_smem, stream, pf);
     Fc2Params p2f{c->hid.as<float>(), (int)N, 256, k_splits, c->fc1_b.as<float>(), 0.01f, c->fc2_w.as<float>(), c->fc2_b.as<float>(),
                   c->classes, cnn_logits, cnn_probs};
-    const size_t fc2_smem = (size_t)256 * c->classes * 4 + (size_t)8 * 256 * 4 + 64;
+    const size_t fc2_smem = (size_t)((256 * c->classes + 3) & ~3) * 4 + (size_t)8 * 256 * 4 + 64;
     GAT_CUDA(cudaFuncSetAttribute(fc2_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fc2_smem));
     const long long ctas2 = (N + 7) / 8;
     LAUNCH(c, fc2_softmax_kernel, (unsigned)(ctas2 < 2 * c->num_sms ? ctas2 : 2 * c->num_sms), 256, fc2_smem, stream, p2f);

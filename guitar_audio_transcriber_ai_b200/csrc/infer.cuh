@@ -45,7 +45,19 @@ __global__ void __launch_bounds__(256) mlp_ensemble_kernel(MlpParams p) {
     GAT_DYN_SMEM(smem_raw);
     float* wsm = reinterpret_cast<float*>(smem_raw);                         // all parameters
     float* scratch = wsm + p.n_params;                                       // per warp 2 * kMlpMaxWidth
-    for (int i = threadIdx.x; i < p.n_params; i += blockDim.x) wsm[i] = p.params[i];
+    {   // parameters: 128-bit loads, four in flight per thread (80 dependent 4-byte round trips to L2 per CTA before)
+        const int n4 = p.n_params >> 2;
+        const float4* src = reinterpret_cast<const float4*>(p.params);
+        float4* dst = reinterpret_cast<float4*>(wsm);
+        for (int i0 = threadIdx.x; i0 < n4; i0 += 4 * blockDim.x) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int i = i0 + u * blockDim.x; v[u] = i < n4 ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int i = i0 + u * blockDim.x; if (i < n4) dst[i] = v[u]; }
+        }
+        for (int i = 4 * n4 + threadIdx.x; i < p.n_params; i += blockDim.x) wsm[i] = p.params[i];
+    }
     __syncthreads();
     const int lane = lane_id(), warp = warp_id(), nwarps = blockDim.x >> 5;
     float* bufa = scratch + (size_t)warp * 2 * kMlpMaxWidth;
