@@ -82,7 +82,10 @@ __host__ __device__ inline size_t conv_tc_smem_bytes(int seg, int nstage) {
          + 256;                                                    // barriers, tmem slot, alignment
 }
 
-template <int CIN, int COUT, int NSTAGE>
+// TILES: 128-pixel tiles per group that are actually multiplied (3, or 2 when a clip's image fits 256 pixels: half-second
+// clips in conv3 fill 208 of a group's 384 pixels, so the third tile was a third of the MMAs for nothing - and with two
+// tiles TMEM holds TWO accumulator sets again).  The shared-memory layout is that of three tiles either way.
+template <int CIN, int COUT, int NSTAGE, int TILES = kTcTiles>
 __global__ void __launch_bounds__(conv_tc_threads(conv_tc_epi_groups(COUT)), 1) conv_tc_kernel(ConvTcParams p) {
     using namespace tc;
     constexpr int EPI = conv_tc_epi_groups(COUT);          // epilogue groups (4 warps each), channel blocks interleaved between them
@@ -95,8 +98,8 @@ __global__ void __launch_bounds__(conv_tc_threads(conv_tc_epi_groups(COUT)), 1) 
     // the epilogue adds the halves): 14 KB of operand fetch per (tap, 16 channels) instead of 18 KB, two MMAs instead of three.
     constexpr bool FUSE = COUT == 64;
     constexpr int DCOLS = FUSE ? 2 * COUT : COUT;          // accumulator columns per 128-pixel tile
-    constexpr int ACC = (2 * kTcTiles * DCOLS <= 512) ? 2 : 1;     // accumulator sets in TMEM
-    constexpr uint32_t TMEM_COLS = ACC * kTcTiles * DCOLS <= 256 ? 256 : 512;
+    constexpr int ACC = (2 * TILES * DCOLS <= 512) ? 2 : 1;        // accumulator sets in TMEM
+    constexpr uint32_t TMEM_COLS = ACC * TILES * DCOLS <= 256 ? 256 : 512;
     extern __shared__ __align__(128) unsigned char smem[];
     const int Wp = p.W + 2, Hp = p.H + 2;
     const int seg = p.seg;
@@ -205,7 +208,7 @@ __global__ void __launch_bounds__(conv_tc_threads(conv_tc_epi_groups(COUT)), 1) 
             long long t_acc = 0, t_a = 0, t_w = 0, t0 = 0, t_begin = clock64();
             for (int work = blockIdx.x; work < n_work; work += gridDim.x, ++wi) {
                 const uint32_t as = wi % ACC;
-                const uint32_t d_base = tmem + as * (uint32_t)(kTcTiles * DCOLS);
+                const uint32_t d_base = tmem + as * (uint32_t)(TILES * DCOLS);
                 uint32_t accumulate = 0;
                 for (int kb = 0; kb < NKB; ++kb, ++it) {
                     for (int half = 0; half < 2; ++half) {
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(conv_tc_threads(conv_tc_epi_groups(COUT)), 1) 
                             const uint32_t w_lf = w_hf + ((4 * COUT * 16) >> 4);                     // unused when FUSE
                             const uint32_t a_off = row_off + (uint32_t)half * a_step;
 #pragma unroll
-                            for (int g = 0; g < kTcTiles; ++g) {
+                            for (int g = 0; g < TILES; ++g) {
                                 const uint32_t d = d_base + (uint32_t)(g * DCOLS);
                                 if (accumulate == 0) {                  // first MMA of the group on this tile: its accumulators must be drained
                                     t0 = clock64();
@@ -276,14 +279,14 @@ __global__ void __launch_bounds__(conv_tc_threads(conv_tc_epi_groups(COUT)), 1) 
             int pcol = Wpool - colb * (p.cw / 2);             // pooled columns produced by this group
             pcol = pcol < p.cw / 2 ? pcol : p.cw / 2;
             const uint32_t as = wi % ACC;
-            const uint32_t t_acc = tmem + as * (uint32_t)(kTcTiles * DCOLS);
+            const uint32_t t_acc = tmem + as * (uint32_t)(TILES * DCOLS);
             const long long e0 = clock64();
             mbar_wait(acc_full + as, (wi / ACC) & 1);
             e_wait += clock64() - e0;
             fence_after_thread_sync();
             for (int cb = eg; cb < COUT / 32; cb += EPI) {
 #pragma unroll
-                for (int g = 0; g < kTcTiles; ++g) {
+                for (int g = 0; g < TILES; ++g) {
                     float v[32];
                     if constexpr (FUSE) {                                 // the two halves of the split product, one wait
                         uint32_t r0[32], r1[32];

@@ -802,32 +802,37 @@ constexpr size_t kActGuard = 65536;   // bytes before/after the plane buffers: h
 
 // Tiling of one conv layer: column blocks of `cw` output columns (one block spanning the width when the staged
 // planes fit in shared memory), R image rows per group so that R * seg <= 384 tile pixels.
-struct ConvTiling { int seg, cw, col_blocks, R, groups_per_clip; size_t smem; };
+struct ConvTiling { int seg, cw, col_blocks, R, groups_per_clip; size_t smem; int tiles; };
 
 // Picks the column blocking that needs the fewest 384-pixel groups per clip: nb column blocks of cw output
 // columns (cw even when nb > 1 so that 2x2 pool pairs stay inside a block), seg = cw + 2 staged pixels per row,
 // R rows per group.  Narrower blocks than shared memory allows often waste less of a group (W = 86: two blocks
 // of 44 columns x 8 rows fill 90 % of a group, one 64-column block x 6 rows + a 24-column remainder only 60 %).
 template <int COUT>
-ConvTiling conv_tc_tiling(int H, int W, int nstage) {
+ConvTiling conv_tc_tiling(int H, int W, int nstage, bool allow_two_tiles = false) {
     ConvTiling best{};
+    long long best_cost = 0;
     const size_t budget = 227 * 1024;
     const int hmax = 2 * (H / 2);
-    for (int nb = 1; nb <= (W + 1) / 2; ++nb) {
-        int cw = (W + nb - 1) / nb;
-        if (nb > 1 && (cw & 1)) ++cw;
-        const int seg = cw + 2;
-        if (2 * seg > kTcGroupPix || conv_tc_smem_bytes<COUT>(seg, nstage) > budget) continue;
-        ConvTiling t{};
-        t.seg = seg; t.cw = cw; t.col_blocks = (W + cw - 1) / cw;
-        int R = 2 * (kTcGroupPix / (2 * seg));
-        R = R < kTcMaxRows ? R : kTcMaxRows;                          // the epilogue's staged planes pad every row by one float
-        t.R = R < hmax ? R : hmax;
-        if (t.R < 2) continue;
-        t.groups_per_clip = ceil_div(H / 2, t.R / 2) * t.col_blocks;
-        t.smem = conv_tc_smem_bytes<COUT>(seg, nstage);
-        if (best.groups_per_clip == 0 || t.groups_per_clip < best.groups_per_clip) best = t;
-    }
+    // groups of 3 tiles (384 pixels) or, where offered, of 2: the cost of a clip is its number of 128-pixel tiles multiplied
+    for (int tiles = kTcTiles; tiles >= (allow_two_tiles ? 2 : kTcTiles); --tiles)
+        for (int nb = 1; nb <= (W + 1) / 2; ++nb) {
+            int cw = (W + nb - 1) / nb;
+            if (nb > 1 && (cw & 1)) ++cw;
+            const int seg = cw + 2;
+            const int group_pix = 128 * tiles;
+            if (2 * seg > group_pix || conv_tc_smem_bytes<COUT>(seg, nstage) > budget) continue;
+            ConvTiling t{};
+            t.seg = seg; t.cw = cw; t.col_blocks = (W + cw - 1) / cw; t.tiles = tiles;
+            int R = 2 * (group_pix / (2 * seg));
+            R = R < kTcMaxRows ? R : kTcMaxRows;                          // the epilogue's staged planes pad every row by one float
+            t.R = R < hmax ? R : hmax;
+            if (t.R < 2) continue;
+            t.groups_per_clip = ceil_div(H / 2, t.R / 2) * t.col_blocks;
+            t.smem = conv_tc_smem_bytes<COUT>(seg, nstage);
+            const long long cost = (long long)t.groups_per_clip * tiles;
+            if (best.groups_per_clip == 0 || cost < best_cost) { best = t; best_cost = cost; }
+        }
     return best;
 }
 
@@ -836,7 +841,7 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
     const int H0 = c->cfg.mel_n_mels, W0 = T;
     const int H1 = H0 / 2, W1 = W0 / 2, H2 = H1 / 2, W2 = W1 / 2, H3 = H2 / 2, W3 = W2 / 2;
     if (H3 < 1 || W3 < 1) return fail("infer: mel image %dx%d too small for three 2x2 pools", H0, W0);
-    const ConvTiling t2 = conv_tc_tiling<64>(H1, W1, 8), t3 = conv_tc_tiling<128>(H2, W2, 3);
+    const ConvTiling t2 = conv_tc_tiling<64>(H1, W1, 8), t3 = conv_tc_tiling<128>(H2, W2, 3, true);
     if (t2.R < 2 || t3.R < 2 || t2.smem > 227 * 1024 || t3.smem > 227 * 1024)
         return fail("infer: no tensor-core conv tiling for a mel image of %d x %d", H0, W0);
     const size_t smem2 = t2.smem, smem3 = t3.smem;
@@ -869,7 +874,7 @@ int run_cnn(gat_ctx* c, const float* mel, int64_t N, int T, float* cnn_probs, fl
     float* feat_lo = reinterpret_cast<float*>(c->feat_planes.as<unsigned char>() + feat_bytes);
     const bool fuse_avgpool = t3.groups_per_clip == 1 && H3 * W3 <= kTcPooledPix;
     auto k2 = conv_tc_kernel<32, 64, 8>;
-    auto k3 = conv_tc_kernel<64, 128, 3>;
+    auto k3 = t3.tiles == 2 ? conv_tc_kernel<64, 128, 3, 2> : conv_tc_kernel<64, 128, 3, 3>;   // two tiles: short clips (<= 256 staged pixels)
     GAT_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     GAT_CUDA(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
     for (long long c0 = 0; c0 < N; c0 += chunk) {
