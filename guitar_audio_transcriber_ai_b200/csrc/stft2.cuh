@@ -459,7 +459,10 @@ __global__ void __launch_bounds__(kThreads, 1) onset_frames_kernel(OnsetFramesPa
         }
         frame_fft_power<double>(v, xbuf, tab);
         const double* pf = pbuf + kPbufLead;
-        // banded-sparse Slaney filterbank, sequential accumulation per filter (the order of the kernel this replaces)
+        // banded-sparse Slaney filterbank: four interleaved partial sums per filter (bin mod 4), folded as (a0 + a1) + (a2 + a3).
+        // (One running sum was a chain of four dependent DFMAs per step at two warps per scheduler.  Widening the weights to
+        // float64 in shared memory instead of converting them at every use was tried and lost: the gather is half of the
+        // kernel's shared-memory wavefronts, and 32-byte weight loads made it 5 % slower.)
         double wmax = -1e300;
         double* dst = p.out + ((long long)clip * p.T + t) * p.fb.n_mels;
         for (int q = 0; q < p.fb.n_slots; ++q) {
@@ -468,15 +471,17 @@ __global__ void __launch_bounds__(kThreads, 1) onset_frames_kernel(OnsetFramesPa
             const int ln = fb_len[e];
             const Vec4<double>* pb = reinterpret_cast<const Vec4<double>*>(pf + fb_start[e]);
             const float4* w = reinterpret_cast<const float4*>(fb_w + fb_off[e]);
-            double acc = 0.0;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 2
             for (int k = 0; k < ln; ++k) {
                 const Vec4<double> pv = pb[k];
                 const float4 wv = w[k];
-                acc += pv.x * (double)wv.x;
-                acc += pv.y * (double)wv.y;
-                acc += pv.z * (double)wv.z;
-                acc += pv.w * (double)wv.w;
+                a0 += pv.x * (double)wv.x;
+                a1 += pv.y * (double)wv.y;
+                a2 += pv.z * (double)wv.z;
+                a3 += pv.w * (double)wv.w;
             }
+            const double acc = (a0 + a1) + (a2 + a3);
             if (m >= 0) {
                 const double db = db10(acc > p.amin ? acc : p.amin);
                 dst[m] = db;
