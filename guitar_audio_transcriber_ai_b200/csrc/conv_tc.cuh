@@ -1,5 +1,5 @@
 // conv2 / conv3 of the CNN (training/cnn_trainer.py:52-76: Conv2d 3x3 pad 1 -> BatchNorm -> LeakyReLU ->
-// MaxPool2) as an implicit GEMM on the Blackwell tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM).
+// MaxPool2) as an implicit GEMM on the Blackwell tensor cores (tcgen05.mma kind::f16, accumulators in TMEM).
 //
 //   D[pixel (M = 128)][c_out (N)] += A[pixel][k] * B[c_out][k],   k = (tap, c_in)
 //
@@ -9,7 +9,8 @@
 // * Split product: x = hf + lo with hf = FP16(x), for activations (lo kept as BF16: lb) and for weights (pre-scaled by
 //   a power of two per layer so that lo sits in FP16's normal range: wf, wl in FP16, plus wb = BF16(wf)).
 //   x*w ~= hf*wf (FP16 MMA) + lb*wb (BF16 MMA) + hf*wl (FP16 MMA): three kind::f16 MMAs of K = 16 per 16 channels into
-//   one FP32 TMEM tile where 3xTF32 needs six, 4 bytes per stored activation instead of 8, and the error of three TF32
+//   one FP32 TMEM tile (conv2: TWO MMAs - hf * {wf, wl} stacked along N - into two column halves the epilogue adds,
+//   see FUSE below) where 3xTF32 needs six, 4 bytes per stored activation instead of 8, and the error of three TF32
 //   passes (tests/gpu_probe/tc_probe_hybrid.cu: 4.9e-6 on |x| ~ 7; one TF32 pass: 5e-3).  The reference runs the CNN in
 //   fp32.  (A and B of one MMA must share a format - mixing F16 and BF16 is an illegal instruction - hence wb.)
 // * One CTA per SM, warp-specialised: warp 0 = weight producer, warp 1 = MMA issuer (one thread), then one (conv2) or

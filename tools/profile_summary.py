@@ -17,8 +17,9 @@ INDEX = """## Files of this round
 |---|---|
 | `r02_bench.json`, `r02_bench_reference.json` | the driver's two arms for cfg 2 (`bench.py`, `bench.py --impl reference`) as run by the builder at HEAD |
 | `r02_bench_cfg1.json`, `_cfg3.json`, `_cfg4.json`, `_cfg4_file.json`, `_cfg5_1gpu.json` | `bench.py --config 1 / 3 / 4 / 4 --cfg4-mode file / 5` on one B200 |
-| `r02_cfg4_{1,2,4,8}gpu.json`, `r02_cfg4_file_8gpu.json` | BASELINE configs[3]: one hour of audio at 1 / 2 / 4 / 8 GPUs (phrases sharded; one contiguous file) |
-| `r02_cfg5_8gpu.json`, `r02_cfg3_8gpu.json`, `r02_bench_8gpu.json` | BASELINE configs[4] sweep with the CPU column, the full ensemble, and cfg 2, on 8 GPUs |
+| `r02_cfg4_{1,2,4,8}gpu.json`, `r02_cfg4_file_8gpu.json` | BASELINE configs[3]: one hour of audio at 1 / 2 / 4 / 8 GPUs (phrases sharded; one contiguous file); the 8-GPU line re-run with the block-FFT YIN, 1 / 2 / 4 and the file mode mid-round |
+| `r02_bench_2gpu.json` | cfg 2 on two GPUs at HEAD (`torchrun ... bench.py --gpus 2`) |
+| `r02_cfg5_8gpu.json`, `r02_cfg3_8gpu.json`, `r02_bench_8gpu.json` | BASELINE configs[4] sweep with the CPU column, the full ensemble, and cfg 2, on 8 GPUs (mid-round kernels) |
 | `r02_h2d_probe.json` | pure pinned H2D copies at 1 / 2 / 4 / 8 ranks (`tools/h2d_probe.py`): the end-to-end ceiling |
 | `r02_parity.json` | error distribution of every stage over all 4096 bench clips (`tools/parity_report.py`) |
 | `r02_launches.csv`, `r02_ncu_full_raw.csv` | ncu launch list and `--set full` raw page at HEAD |
