@@ -2,14 +2,16 @@
 //
 // librosa builds the difference function from an FFT autocorrelation,
 //     d[tau] = E[0] + E[tau] - 2 acf[tau],  acf[tau] = sum_{j=1..W} x[j] x[j+tau],  E[tau] = sum_{j=tau+1..tau+W} x[j]^2
-// with W = 1024 inside frames of 2048 (hop 512, zero centre padding).  Here acf is evaluated directly as a
-// register-tiled sliding dot product: lane l owns the kLPT consecutive lags [kLPT*l, kLPT*l + kLPT) and keeps
-// the kLPT-sample window x[j+lag] in a register ring, so one broadcast load + one window load feed kLPT FMAs.
-// Consecutive frames overlap by half a window (hop = W/2), so the sums are formed per 512-sample BLOCK and a
-// frame is the sum of two consecutive block partials: a warp walks a segment of frames of one clip and does
-// one block of work per frame instead of two.  The cumulative-mean normalisation, trough search and parabolic
-// refinement follow librosa's dtypes: d in float32, CMND and shifts in float64 (float32 / int64 promotes),
-// f0 = sr / period in float64.
+// with W = 1024 inside frames of 2048 (hop 512, zero centre padding).  Consecutive frames overlap by half a window
+// (hop = W/2), so every kernel here forms the sums per 512-sample BLOCK - a frame is the sum of two consecutive block
+// partials - and a warp walks a segment of frames of one clip with one block of work per frame instead of two.
+//   yin_fft_kernel   (bottom of the file; the one run_yin launches while max_period <= 512, i.e. up to 25.6 kHz): block
+//                    partials through warp FFTs, one forward transform per block and one inverse per frame pair.
+//   yin_pair_kernel  / yin_kernel: the block partials as a register-tiled sliding dot product (lane l owns kLPT lags and
+//                    keeps the window x[j+lag] in a register ring, so one broadcast load + one window load feed kLPT FMAs);
+//                    ten times the FLOPs, kept for higher sample rates and as the A/B reference (GAT_YIN_DIRECT).
+// The cumulative-mean normalisation, trough search and parabolic refinement follow librosa's dtypes: d in float32, CMND
+// and shifts in float64 (float32 / int64 promotes), f0 = sr / period in float64.
 #pragma once
 #include "common.cuh"
 #include "fft.cuh"
