@@ -374,6 +374,32 @@ def test_full_size_properties(tr22):
     assert out1["indices"][:64].cpu().numpy().tolist() == probs.argmax(1).tolist()
 
 
+def test_yin_full_size_properties(tr22):
+    """The block-FFT YIN at BASELINE config 3's size (4096 one-second clips): properties that need no oracle."""
+    from guitar_audio_transcriber_ai_b200 import synth
+    eng = tr22.engine
+    base, midi = synth.clip_batch(64, 1.0, 22050, seed0=9100)
+    dev = torch.from_numpy(np.concatenate([base] * 64)).cuda()
+    hz1, f1 = eng.yin(dev)
+    hz2, f2 = eng.yin(dev)
+    assert torch.equal(f1, f2) and torch.equal(hz1, hz2)                       # deterministic
+    assert torch.equal(f1.view(64, 64, -1), f1[:64].unsqueeze(0).expand(64, -1, -1))   # position in the batch does not matter
+    _, solo = eng.yin(dev[1000:1003].contiguous())
+    assert torch.equal(solo, f1[1000:1003])                                    # nor does the batch size (segment lengths differ)
+    # a power-of-two gain scales every sample, product, butterfly and sum exactly: the same f0 bit for bit, except where an
+    # autocorrelation value or an energy crosses librosa's absolute 1e-6 dead zone (frames in the padding, a few lags a million)
+    _, f3 = eng.yin(dev * 0.5)
+    a, b = f1[:, 2:].cpu().numpy(), f3[:, 2:].cpu().numpy()
+    assert np.mean(a == b) > 0.999 and np.max(cents(a, b)) < 1e-2
+    # volume normalisation (the in-memory path) makes the pitch gain-invariant up to float32 rounding of y * (1 / c)
+    hz_n, _ = eng.yin(dev, normalize=True)
+    hz_g, _ = eng.yin(dev * 0.37, normalize=True)
+    assert np.max(cents(hz_n.cpu().numpy(), hz_g.cpu().numpy())) < 1e-2
+    # and it is a pitch detector: the median lands on the synthesised note for most clips (octave errors are YIN's own)
+    got = np.round(12 * np.log2(hz1[:64].cpu().numpy() / 440.0) + 69).astype(int)
+    assert np.mean(got == np.asarray(midi)[:64]) > 0.75
+
+
 def test_host_buffer_entry_point(tr22):
     from guitar_audio_transcriber_ai_b200 import synth
     clips, _ = synth.clip_batch(700, 0.5, 22050, seed0=7000)   # > one 512-clip chunk: exercises the double buffer
