@@ -574,6 +574,26 @@ int launch_stft_frames(gat_ctx* c, StftFramesParams p, void* stream) {
     return 0;
 }
 
+// Frame-per-warp image chain at n_fft 1024 / 512 (csrc/stft2.cuh, stft_frames_small_kernel): F = 2 / 4 frames per warp.
+template <int P>
+int launch_stft_frames_small(gat_ctx* c, StftFramesParams p, void* stream) {
+    constexpr int F = FftGeom<P>::F;
+    const long long n_items = (long long)p.N * ((p.T + F - 1) / F);
+    if (n_items <= 0) return 0;
+    const int nwarps = 20;
+    const size_t smem = stft_frames_small_smem_bytes<P>(nwarps, p.fb.nnz + 3);
+    if (smem > (size_t)227 * 1024) return fail("stft_frames_small: %zu bytes of shared memory needed", smem);
+    long long ctas = (n_items + nwarps - 1) / nwarps;
+    ctas = ctas < c->num_sms ? ctas : c->num_sms;
+    p.items_per_cta = (n_items + ctas - 1) / ctas;
+    ctas = (n_items + p.items_per_cta - 1) / p.items_per_cta;
+    auto kfn = stft_frames_small_kernel<640, P>;
+    GAT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KNAME("stft_frames_image");
+    LAUNCH(c, kfn, (unsigned)ctas, 640, smem, stream, p);
+    return 0;
+}
+
 // Fills the chain-independent fields and the two chains' halves of StftFramesParams.
 void stft_frames_common(gat_ctx* c, StftFramesParams& p, const float* audio, int64_t N, int64_t n, bool dual_or_img) {
     p.audio = audio; p.n = n; p.N = (int)N; p.clip_scale = c->clip_scale.as<float>();
@@ -609,6 +629,15 @@ int run_melspec(gat_ctx* c, const float* audio, int64_t N, int64_t n, bool norma
         return launch_stft_frames(c, q, stream);
     }
 #endif
+    static const bool chunked = getenv("GAT_STFT_CHUNKED") != nullptr;      // A/B switch: the round-1 kernel for n_fft 512 / 1024
+    if ((n_fft == 1024 || n_fft == 512) && !chunked && n < 0x7fff0000LL) {
+        StftFramesParams q{};
+        q.audio = audio; q.n = n; q.N = (int)N; q.clip_scale = c->clip_scale.as<float>();
+        q.window_half = c->win_mel_half.as<float>(); q.tw = c->tw_mel.as<Cpx<float>>(); q.w2 = c->w2_mel.as<Cpx<float>>();
+        q.amin = 1e-10f;
+        stft_frames_image(c, q, n, normalize, power_out, out);
+        return n_fft == 1024 ? launch_stft_frames_small<16>(c, q, stream) : launch_stft_frames_small<8>(c, q, stream);
+    }
     StftMelParams<float> p{};
     p.audio = audio; p.n = n; p.N = (int)N; p.clip_scale = normalize ? c->clip_scale.as<float>() : nullptr;
     p.frame_gate = nullptr; p.sample_gate = 0.0f; p.gate_hop = 512;

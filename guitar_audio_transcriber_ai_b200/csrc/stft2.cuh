@@ -335,6 +335,134 @@ __global__ void __launch_bounds__(kThreads, 1) stft_frames_kernel(StftFramesPara
 }
 
 // ---------------------------------------------------------------------------------------------------
+// The image chain at n_fft 1024 / 512 (MelSpecConfig.N_FFT is configurable: features.py:296-302; BASELINE config 5 sweeps
+// it) in the same frame-per-warp form.  A frame folds to 512 / 256 complex points, 16 / 8 per lane, so a warp transforms
+// F = 2 / 4 CONSECUTIVE frames of a clip at once (warp_rfft_power<float, P>, fft.cuh: lane = frame * P + k2 in the second
+// pass) and then applies the filterbank to each spectrum in turn.  No block-level staging, no block barriers, volume
+// normalisation in the power domain - everything stft_frames_kernel does for n_fft 2048, minus the MFCC chain (librosa's
+// n_fft is fixed at 2048).  Replaces the round-1 chunked kernel (stft_mel_kernel) for these sizes.
+template <int P>
+__host__ __device__ inline size_t stft_frames_small_smem_bytes(int nwarps, int nnz) {
+    return sizeof(FftTables<float, P>) + (size_t)64 * P * sizeof(float) + (size_t)4 * kMaxMelsPerLane * 32 * sizeof(int)
+         + ((size_t)nnz + 3) / 4 * 4 * sizeof(float) + (size_t)nwarps * FftGeom<P>::kXbufElems * sizeof(Cpx<float>) + 64;
+}
+
+template <int kThreads, int P>
+__global__ void __launch_bounds__(kThreads, 1) stft_frames_small_kernel(StftFramesParams p) {
+    using G = FftGeom<P>;
+    constexpr int NF = G::N, F = G::F;                       // samples per frame, frames per warp
+    static_assert(G::V == 32 && F * NF == 2048, "one warp holds 2048 samples in 32 complex registers per lane");
+    GAT_DYN_SMEM(smem_raw);
+    const int nwarps = kThreads / 32;
+    const int lane = lane_id(), warp = warp_id();
+    unsigned char* sp = smem_raw;
+    FftTables<float, P>* tab = reinterpret_cast<FftTables<float, P>*>(sp);  sp += sizeof(FftTables<float, P>);
+    float* win = reinterpret_cast<float*>(sp);                 sp += NF * sizeof(float);
+    constexpr int kSlotEntries = kMaxMelsPerLane * 32;
+    int* fbi = reinterpret_cast<int*>(sp);                     sp += (size_t)4 * kSlotEntries * sizeof(int);
+    float* fbw = reinterpret_cast<float*>(sp);                 sp += ((size_t)p.fb.nnz + 3) / 4 * 4 * sizeof(float);
+    Cpx<float>* xbuf = reinterpret_cast<Cpx<float>*>(sp) + (size_t)warp * G::kXbufElems;
+    float* pbuf = reinterpret_cast<float*>(xbuf);
+
+    fill_fft_tables<float, P>(tab, p.tw, p.w2);
+    for (int i = threadIdx.x; i < NF; i += kThreads) win[i] = p.window_half[i];
+    for (int i = threadIdx.x; i < kSlotEntries; i += kThreads) {
+        const bool live = i < p.fb.n_slots * 32;
+        fbi[0 * kSlotEntries + i] = live ? p.fb.start[i] : 0;  fbi[1 * kSlotEntries + i] = live ? p.fb.len[i] : 0;
+        fbi[2 * kSlotEntries + i] = live ? p.fb.off[i] : 0;    fbi[3 * kSlotEntries + i] = live ? p.fb.mel[i] : -1;
+    }
+    for (int i = threadIdx.x; i < p.fb.nnz; i += kThreads) fbw[i] = p.fb.w[i];
+    __syncthreads();          // the only block barrier
+    const FbShared fb1{fbi, fbi + kSlotEntries, fbi + 2 * kSlotEntries, fbi + 3 * kSlotEntries, fbw};
+    const Cpx<float>* win2 = reinterpret_cast<const Cpx<float>*>(win);
+
+    const int gpc = (p.T + F - 1) / F;                               // groups of F frames per clip
+    const long long n_items = (long long)p.N * gpc;
+    const long long lo = (long long)blockIdx.x * p.items_per_cta;
+    long long hi = lo + p.items_per_cta;
+    hi = hi > n_items ? n_items : hi;
+    const int n32 = (int)p.n;
+    for (long long item = lo + warp; item < hi; item += nwarps) {
+        const int clip = (int)(item / gpc);
+        const int t0 = (int)(item - (long long)clip * gpc) * F;
+        const float* src = p.audio + (long long)clip * p.n;
+        const int s_first = t0 * p.hop - NF / 2;                     // first sample of the group's first frame
+        // every frame of the group inside the clip (and a real frame): straight from global memory into the FFT's registers
+        const bool interior = s_first >= 0 && s_first + (F - 1) * p.hop + NF <= n32 && t0 + F <= p.T;
+        const bool aligned = (reinterpret_cast<unsigned long long>(src + s_first) & 7ull) == 0ull && (p.hop & 1) == 0;
+        Cpx<float> v[32];
+        if (interior && aligned) {
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+                const float2* g = reinterpret_cast<const float2*>(src + s_first + f * p.hop);
+#pragma unroll
+                for (int r = 0; r < P; ++r) { const float2 x = g[lane + 32 * r]; v[f * P + r] = Cpx<float>{x.x, x.y}; }
+            }
+        } else if (interior) {                                       // clips that start on odd words: 32-bit loads
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+                const float* g1 = src + s_first + f * p.hop + 2 * lane;
+#pragma unroll
+                for (int r = 0; r < P; ++r) v[f * P + r] = Cpx<float>{g1[64 * r], g1[64 * r + 1]};
+            }
+        } else {
+            // a frame touches the clip's ends (torch.stft reflect) or lies past the last frame (zeros, never stored):
+            // stage the F frames through the warp's scratch with a rolled loop
+#pragma unroll 1
+            for (int f = 0; f < F; ++f) {
+                const int sf = s_first + f * p.hop;
+                const bool real = t0 + f < p.T;
+#pragma unroll 1
+                for (int e0 = lane; e0 < NF; e0 += 32 * 8) {
+                    float val[8];
+#pragma unroll
+                    for (int u8 = 0; u8 < 8; ++u8) {
+                        int s = sf + e0 + 32 * u8;
+                        bool inside = s >= 0 && s < n32;
+                        if (!inside) {                               // one mirror suffices: the launcher requires n > n_fft / 2
+                            const int m = s < 0 ? -s : 2 * (n32 - 1) - s;
+                            inside = m >= 0 && m < n32;
+                            s = m;
+                        }
+                        val[u8] = (inside && real && e0 + 32 * u8 < NF) ? src[s] : 0.0f;
+                    }
+#pragma unroll
+                    for (int u8 = 0; u8 < 8; ++u8) if (e0 + 32 * u8 < NF) pbuf[f * NF + e0 + 32 * u8] = val[u8];
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+                const float2* g = reinterpret_cast<const float2*>(pbuf + f * NF);
+#pragma unroll
+                for (int r = 0; r < P; ++r) { const float2 x = g[lane + 32 * r]; v[f * P + r] = Cpx<float>{x.x, x.y}; }
+            }
+            __syncwarp();                            // staged samples are consumed before the transpose reuses the scratch
+        }
+#pragma unroll
+        for (int r = 0; r < P; ++r) {
+            const Cpx<float> w = win2[lane + 32 * r];
+#pragma unroll
+            for (int f = 0; f < F; ++f) { v[f * P + r].x *= w.x; v[f * P + r].y *= w.y; }
+        }
+        warp_rfft_power<float, P>(v, xbuf, kPbufLead, tab);
+        float ic2 = 1.0f;
+        if (p.norm_img) { const float ic = 1.0f / p.clip_scale[clip]; ic2 = ic * ic; }
+        const int T = p.T;
+#pragma unroll 1
+        for (int f = 0; f < F; ++f) {
+            const int t = t0 + f;
+            if (t < T) {
+                float* dst = p.out + (long long)clip * p.fb.n_mels * T + t;
+                apply_filterbank(pbuf + f * G::kPbufStride + kPbufLead, fb1, p.fb.n_slots, lane, ic2, p.amin, p.power_out != 0,
+                                 [&](int m, float val) { dst[(long long)m * T] = val; });
+            }
+        }
+        __syncwarp();                                 // pbuf (= xbuf) is rewritten by the next group
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // The float64 mel spectrogram of the onset chain (audio/slicing.py:107, librosa.onset.onset_strength on the float64 gated
 // signal) in the same frame-per-warp form: zero centre padding, any even hop, the two gates of sliceNsave fused into the
 // loads (sample gate |y| >= g, per-block frame gate), Slaney mel-128, 10 log10, per-signal running maximum.
