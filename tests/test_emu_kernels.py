@@ -92,3 +92,23 @@ def test_emu_yin_block_fft_segmentations(emu_tr, seg, monkeypatch):
     for i in range(2):
         ref = L.yin(clips[i], fmin=50, fmax=1000, sr=22050)
         assert f0[i].shape == ref.shape and np.max(cents(f0[i].numpy(), ref)) <= 0.5
+
+
+@pytest.mark.parametrize("n_fft,hop", [(1024, 256), (512, 100)])
+def test_emu_small_n_fft_frame_kernel(emu_tr, n_fft, hop):
+    """stft_frames_small_kernel (two / four frames per warp) against genuine torchaudio: interior groups, groups that touch
+    the reflect padding, a ragged last group, clips with an odd sample count (32-bit loads), hops that are not 256."""
+    import port
+    from guitar_audio_transcriber_ai_b200 import synth
+    from guitar_audio_transcriber_ai_b200.engine import Engine
+    eng = Engine(22050, {"N_MELS": 64, "N_FFT": n_fft, "HOP_LENGTH": hop}, device="cpu")
+    try:
+        clips, _ = synth.clip_batch(2, 0.3337, 22050, seed0=40 + n_fft)
+        mel = eng.melspec_db(clips).numpy()
+        for i in range(2):
+            ref = port.melspec_image(clips[i], 22050, 64, n_fft, hop).numpy()
+            assert mel[i].shape == ref.shape
+            bound = 1e-4 if n_fft >= 1024 else 5e-4          # n_fft 512: see test_other_n_fft_against_torchaudio
+            assert np.all(np.abs(mel[i] - ref) <= bound * np.maximum(np.abs(ref), 20.0))
+    finally:
+        eng.close()
